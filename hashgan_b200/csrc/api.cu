@@ -1,0 +1,325 @@
+// Misc C-ABI entry points: version / errors / device facts, lib/metric.py:24 (mean over kept queries),
+// the host-buffer end-to-end call (== MAPs(R).get_maps_by_feature, main.py:164) and the POPC-pipe
+// microbenchmark that gives the Hamming kernel its roofline denominator.
+#include "common.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+namespace hg {
+
+char* last_error_buf()
+{
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int PhaseTimer::ensure()
+{
+    if (!created) {
+        for (int i = 0; i <= kNumPhases; ++i) HG_CUDA_TRY(cudaEventCreate(&ev[i]));
+        created = true;
+    }
+    return HG_OK;
+}
+PhaseTimer& phase_timer()
+{
+    static thread_local PhaseTimer t;
+    return t;
+}
+
+const DeviceFacts& device_facts()
+{
+    static DeviceFacts facts[64];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        static DeviceFacts none;
+        (void)cudaGetLastError();
+        return none;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    DeviceFacts& f = facts[dev];
+    if (!f.ok) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) f.sm_count = v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess) f.cc_major = v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev) == cudaSuccess) f.cc_minor = v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev) == cudaSuccess) f.l2_bytes = (size_t)v;
+        f.ok = f.sm_count > 0;
+        (void)cudaGetLastError();
+    }
+    return f;
+}
+
+// NumPy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, pairwise_sum_DOUBLE), so that the
+// mean over the kept queries is bit-identical to the reference's np.mean (lib/metric.py:24).
+static double pairwise_sum(const double* a, int64_t n)
+{
+    if (n < 8) {
+        double r = 0.0;  // numpy starts from -0.0; identical for our non-negative inputs except n == 0
+        for (int64_t i = 0; i < n; ++i) r += a[i];
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int k = 0; k < 8; ++k) r[k] = a[k];
+        int64_t i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int k = 0; k < 8; ++k) r[k] += a[i + k];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return pairwise_sum(a, n2) + pairwise_sum(a + n2, n - n2);
+}
+
+// -------------------------------------------------------------------------------------------------
+// POPC-pipe microbenchmark
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) popc_peak_kernel(uint32_t* __restrict__ out, int iters, uint32_t seed)
+{
+    constexpr int K = 8;
+    uint32_t x[K], acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        x[k] = seed * (2654435761u * (threadIdx.x + 1 + k * 977u)) + blockIdx.x * 40503u;
+        acc[k] = 0;
+    }
+    uint32_t y = seed ^ (threadIdx.x * 2246822519u);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] += __popc(x[k] ^ y);
+        y = y * 1664525u + 1013904223u;
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) s += acc[k];
+    if (s == 0xdeadbeefu) out[0] = s;  // keeps the chain alive without a store on the timed path
+}
+
+// -------------------------------------------------------------------------------------------------
+// Cached device arena for the host-buffer entry point
+// -------------------------------------------------------------------------------------------------
+struct Arena {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    double* pinned_ap = nullptr;
+    size_t pinned_n = 0;
+    cudaStream_t stream = nullptr;
+    int device = -1;
+};
+static Arena g_arena;
+static std::mutex g_arena_mu;
+
+static int arena_reserve(Arena& a, size_t bytes, size_t n_ap)
+{
+    int dev = 0;
+    HG_CUDA_TRY(cudaGetDevice(&dev));
+    if (a.device != dev) {
+        if (a.ptr) cudaFree(a.ptr);
+        if (a.pinned_ap) cudaFreeHost(a.pinned_ap);
+        if (a.stream) cudaStreamDestroy(a.stream);
+        a = Arena();
+        a.device = dev;
+    }
+    if (!a.stream) HG_CUDA_TRY(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+    if (bytes > a.bytes) {
+        if (a.ptr) HG_CUDA_TRY(cudaFree(a.ptr));
+        a.ptr = nullptr; a.bytes = 0;
+        const size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&a.ptr, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(HG_ENOMEM, "hg_maps_by_feature_host: cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        }
+        a.bytes = want;
+    }
+    if (n_ap > a.pinned_n) {
+        if (a.pinned_ap) HG_CUDA_TRY(cudaFreeHost(a.pinned_ap));
+        a.pinned_ap = nullptr; a.pinned_n = 0;
+        HG_CUDA_TRY(cudaMallocHost(&a.pinned_ap, sizeof(double) * n_ap));
+        a.pinned_n = n_ap;
+    }
+    return HG_OK;
+}
+
+}  // namespace hg
+
+extern "C" int hg_version(void) { return 100; }  // 0.1.0
+
+extern "C" int64_t hg_launch_count(int reset)
+{
+    const long long v = hg::g_launches.load(std::memory_order_relaxed);
+    if (reset) hg::g_launches.store(0, std::memory_order_relaxed);
+    return (int64_t)v;
+}
+
+extern "C" int hg_hamming_map_phase_ms(float out[5])
+{
+    hg::PhaseTimer& t = hg::phase_timer();
+    if (!out || !t.created || !t.armed) return hg::fail(HG_EINVAL, "hg_hamming_map_phase_ms: no timed hg_hamming_map call on this thread");
+    HG_CUDA_TRY(cudaEventSynchronize(t.ev[hg::kNumPhases]));
+    for (int i = 0; i < hg::kNumPhases; ++i) HG_CUDA_TRY(cudaEventElapsedTime(&out[i], t.ev[i], t.ev[i + 1]));
+    return HG_OK;
+}
+
+extern "C" const char* hg_last_error(void) { return hg::last_error_buf(); }
+
+extern "C" int hg_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes)
+{
+    const hg::DeviceFacts& f = hg::device_facts();
+    if (!f.ok) return hg::fail(HG_ECUDA, "hg_device_info: no usable CUDA device");
+    if (sm_count) *sm_count = f.sm_count;
+    if (cc_major) *cc_major = f.cc_major;
+    if (cc_minor) *cc_minor = f.cc_minor;
+    if (l2_bytes) *l2_bytes = f.l2_bytes;
+    return HG_OK;
+}
+
+// Host-only half of hg_mean_ap, exported so the CPU test-suite can pin it against np.mean.
+extern "C" int hg_mean_ap_host(const double* h_ap, int64_t nq, double* map_out, int64_t* n_used)
+{
+    if (nq < 0 || (nq > 0 && !h_ap) || !map_out) return hg::fail(HG_EINVAL, "hg_mean_ap_host: bad arguments");
+    std::vector<double> kept;
+    kept.reserve((size_t)nq);
+    for (int64_t i = 0; i < nq; ++i)
+        if (!std::isnan(h_ap[i])) kept.push_back(h_ap[i]);
+    if (n_used) *n_used = (int64_t)kept.size();
+    *map_out = kept.empty() ? std::nan("") : hg::pairwise_sum(kept.data(), (int64_t)kept.size()) / (double)kept.size();
+    return HG_OK;
+}
+
+extern "C" int hg_mean_ap(const double* d_ap, int64_t nq, double* map_out, int64_t* n_used, void* stream)
+{
+    if (nq < 0 || (nq > 0 && !d_ap) || !map_out) return hg::fail(HG_EINVAL, "hg_mean_ap: bad arguments");
+    std::vector<double> host((size_t)nq);
+    if (nq > 0) {
+        HG_CUDA_TRY(cudaMemcpyAsync(host.data(), d_ap, sizeof(double) * (size_t)nq, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        HG_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    }
+    return hg_mean_ap_host(host.data(), nq, map_out, n_used);
+}
+
+extern "C" int hg_popc_peak(double* wordops_per_s, double* ms_out, int iters, void* stream)
+{
+    if (!wordops_per_s || iters <= 0) return hg::fail(HG_EINVAL, "hg_popc_peak: bad arguments");
+    const hg::DeviceFacts& f = hg::device_facts();
+    if (!f.ok) return hg::fail(HG_ECUDA, "hg_popc_peak: no CUDA device");
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* d_out = nullptr;
+    HG_CUDA_TRY(cudaMalloc(&d_out, 256));
+    cudaEvent_t e0, e1;
+    HG_CUDA_TRY(cudaEventCreate(&e0));
+    HG_CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = f.sm_count * 8, threads = 256;
+    hg::count_launch(2);
+    hg::popc_peak_kernel<<<blocks, threads, 0, st>>>(d_out, iters / 8 + 1, 12345u);  // warm-up
+    HG_CUDA_TRY(cudaEventRecord(e0, st));
+    hg::popc_peak_kernel<<<blocks, threads, 0, st>>>(d_out, iters, 98765u);
+    HG_CUDA_TRY(cudaEventRecord(e1, st));
+    HG_CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    HG_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    HG_CUDA_TRY(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    const double ops = (double)blocks * threads * (double)iters * 8.0;
+    *wordops_per_s = ops / ((double)ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    return HG_OK;
+}
+
+extern "C" int hg_release_cached(void)
+{
+    std::lock_guard<std::mutex> lock(hg::g_arena_mu);
+    hg::Arena& a = hg::g_arena;
+    if (a.ptr) cudaFree(a.ptr);
+    if (a.pinned_ap) cudaFreeHost(a.pinned_ap);
+    if (a.stream) cudaStreamDestroy(a.stream);
+    a = hg::Arena();
+    (void)cudaGetLastError();
+    return HG_OK;
+}
+
+extern "C" int hg_maps_by_feature_host(const float* h_db_feat, const void* h_db_lab, int64_t ndb, const float* h_q_feat,
+                                       const void* h_q_lab, int64_t nq, int b, int L, int lab_elem_bytes, int64_t R, unsigned flags,
+                                       double* map_out, double* h_ap_out)
+{
+    if (!map_out) return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: map_out is NULL");
+    if (nq < 0 || ndb < 0) return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: negative size");
+    if (R <= 0) return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: R must be positive");
+    if (R > ndb) return hg::fail(HG_ERANGE, "hg_maps_by_feature_host: R=%lld exceeds the database size %lld", (long long)R, (long long)ndb);
+    if (nq == 0) { *map_out = std::nan(""); return HG_OK; }
+    const int W = hg_code_words(b), LW = hg_label_words(L);
+    if (W == 0) return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: unsupported hash length b=%d", b);
+    if (LW == 0) return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: unsupported label width L=%d", L);
+    if (lab_elem_bytes != 8 && lab_elem_bytes != 4 && lab_elem_bytes != 1)
+        return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: lab_elem_bytes must be 8, 4 or 1");
+    if (!h_db_feat || !h_db_lab || !h_q_feat || !h_q_lab) return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: NULL pointer");
+    const size_t ws_bytes = hg_hamming_map_workspace_bytes(nq, ndb, b, L, R);
+    if (ws_bytes == 0) return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: sizes out of range");
+
+    std::lock_guard<std::mutex> lock(hg::g_arena_mu);
+    hg::Arena& a = hg::g_arena;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+    const size_t o_dbf = take(sizeof(float) * (size_t)ndb * b);
+    const size_t o_qf = take(sizeof(float) * (size_t)nq * b);
+    const size_t o_dbl = take((size_t)lab_elem_bytes * ndb * L);
+    const size_t o_ql = take((size_t)lab_elem_bytes * nq * L);
+    const size_t o_dbc = take(sizeof(uint32_t) * (size_t)ndb * W);
+    const size_t o_qc = take(sizeof(uint32_t) * (size_t)nq * W);
+    const size_t o_dblp = take(sizeof(uint32_t) * (size_t)ndb * LW);
+    const size_t o_qlp = take(sizeof(uint32_t) * (size_t)nq * LW);
+    const size_t o_ap = take(sizeof(double) * (size_t)nq);
+    const size_t o_bad = take(256);
+    const size_t o_ws = take(ws_bytes);
+    int rc = hg::arena_reserve(a, off, (size_t)nq + 8);
+    if (rc != HG_OK) return rc;
+    char* base = static_cast<char*>(a.ptr);
+    cudaStream_t st = a.stream;
+    float* d_dbf = reinterpret_cast<float*>(base + o_dbf);
+    float* d_qf = reinterpret_cast<float*>(base + o_qf);
+    uint32_t* d_dbc = reinterpret_cast<uint32_t*>(base + o_dbc);
+    uint32_t* d_qc = reinterpret_cast<uint32_t*>(base + o_qc);
+    uint32_t* d_dblp = reinterpret_cast<uint32_t*>(base + o_dblp);
+    uint32_t* d_qlp = reinterpret_cast<uint32_t*>(base + o_qlp);
+    double* d_ap = reinterpret_cast<double*>(base + o_ap);
+    int* d_bad = reinterpret_cast<int*>(base + o_bad);
+
+    HG_CUDA_TRY(cudaMemsetAsync(d_bad, 0, 256, st));
+    // queries first (small), then the database in row chunks so that packing overlaps the next copy
+    HG_CUDA_TRY(cudaMemcpyAsync(d_qf, h_q_feat, sizeof(float) * (size_t)nq * b, cudaMemcpyHostToDevice, st));
+    HG_CUDA_TRY(cudaMemcpyAsync(base + o_ql, h_q_lab, (size_t)lab_elem_bytes * nq * L, cudaMemcpyHostToDevice, st));
+    if ((rc = hg_pack_sign_f32(d_qf, nq, b, b, d_qc, st)) != HG_OK) return rc;
+    if ((rc = hg_pack_labels(base + o_ql, lab_elem_bytes, nq, L, d_qlp, d_bad, st)) != HG_OK) return rc;
+    const int64_t chunk = 1 << 18;
+    for (int64_t r0 = 0; r0 < ndb; r0 += chunk) {
+        const int64_t n = std::min<int64_t>(chunk, ndb - r0);
+        HG_CUDA_TRY(cudaMemcpyAsync(d_dbf + r0 * b, h_db_feat + r0 * b, sizeof(float) * (size_t)n * b, cudaMemcpyHostToDevice, st));
+        HG_CUDA_TRY(cudaMemcpyAsync(base + o_dbl + (size_t)r0 * L * lab_elem_bytes,
+                                    static_cast<const char*>(h_db_lab) + (size_t)r0 * L * lab_elem_bytes,
+                                    (size_t)lab_elem_bytes * n * L, cudaMemcpyHostToDevice, st));
+    }
+    if ((rc = hg_pack_sign_f32(d_dbf, ndb, b, b, d_dbc, st)) != HG_OK) return rc;
+    if ((rc = hg_pack_labels(base + o_dbl, lab_elem_bytes, ndb, L, d_dblp, d_bad, st)) != HG_OK) return rc;
+    if ((rc = hg_hamming_map(d_qc, d_qlp, nq, d_dbc, d_dblp, ndb, b, L, R, flags, d_ap, nullptr, nullptr, nullptr, base + o_ws,
+                             ws_bytes, st)) != HG_OK)
+        return rc;
+    HG_CUDA_TRY(cudaMemcpyAsync(a.pinned_ap, d_ap, sizeof(double) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+    int* h_bad = reinterpret_cast<int*>(a.pinned_ap + nq);
+    HG_CUDA_TRY(cudaMemcpyAsync(h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    HG_CUDA_TRY(cudaStreamSynchronize(st));
+    if (*h_bad) return hg::fail(HG_ELABEL, "hg_maps_by_feature_host: labels must be 0/1");
+    if (h_ap_out) memcpy(h_ap_out, a.pinned_ap, sizeof(double) * (size_t)nq);
+    return hg_mean_ap_host(a.pinned_ap, nq, map_out, nullptr);
+}

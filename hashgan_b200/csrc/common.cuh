@@ -1,0 +1,92 @@
+// Shared helpers for libhashgan_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+
+#include "../../include/hashgan_b200.h"
+
+namespace hg {
+
+// ---- error plumbing --------------------------------------------------------------------------
+char* last_error_buf();
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(last_error_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define HG_CUDA_TRY(expr)                                                                            \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return hg::fail(HG_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// every kernel launch of the library is counted (bench.py reports it as gpu_launches)
+void count_launch(int n = 1);
+
+// optional per-phase CUDA-event timing of hg_hamming_map (flag HG_FLAG_TIMING)
+enum Phase { kPhaseSample = 0, kPhaseThreshold, kPhaseSelect, kPhaseAp, kPhaseExact, kNumPhases };
+struct PhaseTimer {
+    cudaEvent_t ev[kNumPhases + 1] = {};
+    bool created = false, armed = false;
+    int ensure();
+    void mark(int i, cudaStream_t st) { if (armed) cudaEventRecord(ev[i], st); }
+};
+PhaseTimer& phase_timer();
+
+struct DeviceFacts {
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t l2_bytes = 0;
+    bool ok = false;
+};
+const DeviceFacts& device_facts();
+
+// ---- entry layout of a candidate ---------------------------------------------------------------
+// [0,21) row inside the db split, [21,31) Hamming distance, bit 31 relevance (set by the AP kernel).
+constexpr int kIdxBits = 21;
+constexpr uint32_t kIdxMask = (1u << kIdxBits) - 1;
+constexpr uint32_t kDistMask = 0x3FFu;
+constexpr int64_t kMaxSplitRows = int64_t(1) << kIdxBits;
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// ---- PTX wrappers: mbarrier + 1-D bulk TMA (cp.async.bulk) -------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "HG_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra HG_DONE;\n"
+        "bra HG_WAIT;\n"
+        "HG_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (TMA, SASS UBLKCP); bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+#endif
+
+}  // namespace hg

@@ -1,0 +1,863 @@
+// Hamming ranking + mAP@R on bit-packed codes: the metric hot path (lib/metric.py:12-23).
+//
+//   lib/metric.py:13  ips = np.dot(query.output, database.output.T)   -> d_H = popc(q ^ db)   (ip = b - 2 d_H on +-1 codes)
+//   lib/metric.py:14  ids = np.argsort(-ips, 1)                       -> exact (d_H asc, db row asc) ranking of the top R
+//   lib/metric.py:16-23 relevance / cumsum / AP                       -> integer prefix counts, fp64 divides
+//
+// Design: keys take only b+1 values, so ranking is a counting sort, never a comparison
+// sort, and the [Nq, Ndb] matrix is never materialised.
+//   1. hist_kernel on a strided SAMPLE of the database -> per-query distance histogram.
+//   2. thr_kernel: per-query threshold T_q such that count(d <= T_q) >= R with high probability.
+//   3. select_kernel (the hot kernel): ONE pass over all pairs.  Thread <-> query (QT queries in
+//      registers), database tiles staged into shared memory by 1-D bulk TMA and read as warp broadcasts;
+//      per pair: W x (XOR, POPC), adds, one compare; pairs with d <= T_q (about R/Ndb of them) are appended to
+//      the thread's PRIVATE bin (query, db split) -> entries are in database-row order with no atomics.
+//   4. ap_kernel: one warp per query walks its bins in row order; per-distance running counters give
+//      every candidate its exact rank and relevant-prefix count -> AP in fp64; optional ids/dist output.
+//   5. Exactness guard: a query whose candidate count fell short of R, or whose bin overflowed, is put on
+//      a fail list and redone by the two-pass exact path (full per-split histograms -> exact d*, exact bin
+//      offsets/quotas -> select_kernel<EXACT> -> ap_kernel).  All launches are unconditional and sized for
+//      the worst case; CTAs beyond the fail count exit at once, so the call stays asynchronous.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace hg {
+
+// ================================================================================================
+// Plan: all sizes derived from (nq, ndb, b, L, R) and the SM count, shared by the workspace query and
+// the launcher.
+// ================================================================================================
+struct Plan {
+    int b = 0, L = 0, W = 0, LW = 0, QT = 0, TQ = 0, TILE = 0, P = 0, nqt = 0;
+    int64_t nq = 0, ndb = 0, R = 0, SL = 0;
+    uint32_t cap = 0;
+    // sample pass
+    int64_t n_seg = 0, seg_stride = 0, sample_rows = 0;
+    int seg_per_chunk = 0, n_chunks = 0;
+    // workspace byte offsets
+    size_t off_ctrl = 0, off_thr = 0, off_thr2 = 0, off_fail = 0, off_hist_s = 0, off_bin_cnt = 0, off_bin_cnt2 = 0,
+           off_bin_off2 = 0, off_bin_cap2 = 0, off_quota2 = 0, off_hist2 = 0, off_lists = 0, total = 0;
+    bool ok = false;
+};
+
+constexpr int kSelectThreads = 128;
+constexpr int kHistThreads = 128;
+constexpr int kApWarps = 8;
+constexpr int64_t kSampleTarget = 16384;
+constexpr float kSampleZ = 4.0f;
+
+static int tile_rows_for(int W) { return W == 1 ? 2048 : (W == 2 ? 1024 : (W <= 4 ? 512 : 256)); }
+
+static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R)
+{
+    Plan p;
+    p.W = hg_code_words(b);
+    p.LW = hg_label_words(L);
+    if (p.W == 0 || p.LW == 0 || nq <= 0 || ndb <= 0 || R <= 0 || R > ndb || ndb >= (int64_t(1) << 31) || nq >= (int64_t(1) << 31))
+        return p;
+    p.b = b; p.L = L; p.nq = nq; p.ndb = ndb; p.R = R;
+    const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
+    p.QT = nq >= 4096 ? 4 : (nq >= 1024 ? 2 : 1);
+    p.TQ = kSelectThreads * p.QT;
+    p.nqt = (int)ceil_div(nq, p.TQ);
+    p.TILE = tile_rows_for(p.W);
+    // db splits: enough CTAs for ~8 per SM, split length a multiple of the tile, at most 2^21 rows
+    const int64_t target_ctas = (int64_t)sms * 8;
+    int64_t P0 = std::max<int64_t>(1, ceil_div(target_ctas, p.nqt));
+    int64_t SL = round_up(ceil_div(ndb, P0), p.TILE);
+    SL = std::min<int64_t>(SL, kMaxSplitRows);
+    SL = std::max<int64_t>(SL, p.TILE);
+    p.SL = SL;
+    p.P = (int)ceil_div(ndb, SL);
+    // candidate budget per query, spread evenly over the bins
+    const int64_t all_rows = (int64_t)p.P * SL;
+    int64_t capq = std::min<int64_t>(all_rows, std::max<int64_t>(6 * R, R + 16384));
+    int64_t cap = round_up(ceil_div(capq, p.P), 8);
+    cap = std::min<int64_t>(cap, SL);
+    while (cap * p.P < R) cap += 8;  // the exact path reuses the list area and needs R entries per query
+    p.cap = (uint32_t)cap;
+    // sample: kSampleTarget rows in TILE-row segments spread evenly; the whole db when it is small
+    const int64_t tiles_total = ceil_div(ndb, p.TILE);
+    int64_t want_seg = std::max<int64_t>(1, kSampleTarget / p.TILE);
+    if (tiles_total <= 2 * want_seg || R * 4 >= ndb) {
+        p.n_seg = tiles_total;
+        p.seg_stride = p.TILE;
+        p.sample_rows = ndb;
+    } else {
+        p.n_seg = want_seg;
+        p.seg_stride = (tiles_total / want_seg) * p.TILE;
+        p.sample_rows = want_seg * p.TILE;  // every sampled segment is a full tile by construction
+    }
+    {
+        const int64_t hist_qt = ceil_div(nq, kHistThreads);
+        int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(p.n_seg, ceil_div((int64_t)sms * 4, hist_qt)));
+        p.seg_per_chunk = (int)ceil_div(p.n_seg, chunks);
+        p.n_chunks = (int)ceil_div(p.n_seg, p.seg_per_chunk);
+    }
+    // workspace
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+    const size_t bins = (size_t)nq * p.P;
+    p.off_ctrl = take(256);
+    p.off_thr = take(sizeof(int) * nq);
+    p.off_thr2 = take(sizeof(int) * nq);
+    p.off_fail = take(sizeof(int) * nq);
+    p.off_hist_s = take(sizeof(uint32_t) * (size_t)nq * (b + 1));
+    p.off_bin_cnt = take(sizeof(uint32_t) * bins);
+    p.off_bin_cnt2 = take(sizeof(uint32_t) * bins);
+    p.off_bin_off2 = take(sizeof(uint32_t) * bins);
+    p.off_bin_cap2 = take(sizeof(uint32_t) * bins);
+    p.off_quota2 = take(sizeof(uint32_t) * bins);
+    p.off_hist2 = take(sizeof(uint32_t) * bins * (b + 1));
+    p.off_lists = take(sizeof(uint32_t) * bins * p.cap);
+    p.total = off;
+    p.ok = true;
+    return p;
+}
+
+// ================================================================================================
+// Device helpers
+// ================================================================================================
+template <int W>
+__device__ __forceinline__ void load_code(const uint32_t* __restrict__ s, int j, uint32_t (&v)[W])
+{
+    if constexpr (W == 1) {
+        v[0] = s[j];
+    } else if constexpr (W == 2) {
+        const uint2 t = reinterpret_cast<const uint2*>(s)[j];
+        v[0] = t.x; v[1] = t.y;
+    } else if constexpr (W == 4) {
+        const uint4 t = reinterpret_cast<const uint4*>(s)[j];
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if constexpr (W == 8) {
+        const uint4 t0 = reinterpret_cast<const uint4*>(s)[2 * j];
+        const uint4 t1 = reinterpret_cast<const uint4*>(s)[2 * j + 1];
+        v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w;
+        v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+    } else {
+#pragma unroll
+        for (int w = 0; w < W; ++w) v[w] = s[j * W + w];
+    }
+}
+
+template <int W>
+__device__ __forceinline__ int hamming(const uint32_t (&a)[W], const uint32_t (&b)[W])
+{
+    int d = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) d += __popc(a[w] ^ b[w]);
+    return d;
+}
+
+// ================================================================================================
+// 1. Histogram kernel (sample pass and exact path).  Thread <-> one query; its histogram is a private
+//    column of shared memory (bank = thread), so updates need no atomics.
+// ================================================================================================
+struct HistParams {
+    const uint32_t* q_codes;
+    const uint32_t* db_codes;
+    int64_t nq, ndb;
+    int b;
+    const int* n_active;  // indirect mode (exact path): number of listed queries
+    const int* qlist;     // indirect mode: query ids
+    int64_t seg_stride, n_seg;
+    int seg_rows, seg_per_chunk;
+    uint32_t* out;   // [(slot * out_chunks + chunk') * (b+1) + d]
+    int out_chunks;  // 1 -> all chunks accumulate into one histogram per query
+};
+
+template <int W>
+__global__ void __launch_bounds__(kHistThreads) hist_kernel(HistParams p)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int nbins = p.b + 1;
+    uint32_t* h = smem;                             // [nbins][kHistThreads]
+    uint32_t* tile = smem + nbins * kHistThreads;   // [seg_rows * W]
+    const int tid = threadIdx.x;
+    const int64_t n_act = p.qlist ? (int64_t)*p.n_active : p.nq;
+    const int64_t slot0 = (int64_t)blockIdx.x * kHistThreads;
+    if (slot0 >= n_act) return;
+    const int64_t slot = slot0 + tid;
+    const bool valid = slot < n_act;
+    const int64_t q = valid ? (p.qlist ? (int64_t)p.qlist[slot] : slot) : 0;
+    uint32_t qw[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) qw[w] = valid ? p.q_codes[q * W + w] : 0u;
+    for (int i = tid; i < nbins * kHistThreads; i += kHistThreads) h[i] = 0;
+    const int chunk = blockIdx.y;
+    for (int g = 0; g < p.seg_per_chunk; ++g) {
+        const int64_t seg = (int64_t)chunk * p.seg_per_chunk + g;
+        if (seg >= p.n_seg) break;
+        const int64_t row0 = seg * p.seg_stride;
+        if (row0 >= p.ndb) break;
+        const int rows = (int)min((int64_t)p.seg_rows, p.ndb - row0);
+        __syncthreads();  // previous tile fully consumed (and h zeroed on the first trip)
+        const uint32_t* src = p.db_codes + row0 * W;
+        for (int i = tid; i < rows * W; i += kHistThreads) tile[i] = __ldg(src + i);
+        __syncthreads();
+        if (valid) {
+            for (int j = 0; j < rows; ++j) {
+                uint32_t v[W];
+                load_code<W>(tile, j, v);
+                const int d = hamming<W>(qw, v);
+                h[d * kHistThreads + tid] += 1;
+            }
+        }
+    }
+    __syncthreads();
+    // flush: consecutive threads -> consecutive distances of one query (coalesced atomics)
+    const int oc = p.out_chunks > 1 ? chunk : 0;
+    for (int i = tid; i < nbins * kHistThreads; i += kHistThreads) {
+        const int ql = i / nbins, d = i - ql * nbins;
+        if (slot0 + ql < n_act) {
+            const uint32_t v = h[d * kHistThreads + ql];
+            if (v) atomicAdd(&p.out[((slot0 + ql) * p.out_chunks + oc) * nbins + d], v);
+        }
+    }
+}
+
+// ================================================================================================
+// 2. Threshold from the sampled histogram.
+// ================================================================================================
+__global__ void thr_kernel(const uint32_t* __restrict__ hist_s, int64_t nq, int b, int64_t sample_rows, int64_t ndb, int64_t R,
+                           float z, int force_exact, int* __restrict__ thr)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    if (force_exact) { thr[q] = -1; return; }
+    double need;
+    if (sample_rows >= ndb) {
+        need = (double)R;  // the "sample" is the whole database: exact
+    } else {
+        const double p0 = (double)R / (double)ndb;
+        const double mu = p0 * (double)sample_rows;
+        need = ceil(mu + (double)z * sqrt(mu * (1.0 - p0)) + 2.0);
+    }
+    int T = b;
+    double cum = 0.0;
+    const uint32_t* h = hist_s + q * (b + 1);
+    for (int d = 0; d <= b; ++d) {
+        cum += (double)h[d];
+        if (cum >= need) { T = d; break; }
+    }
+    thr[q] = T;
+}
+
+// ================================================================================================
+// 3. The hot kernel: all-pairs XOR/POPC + threshold select into private, row-ordered bins.
+// ================================================================================================
+struct SelectParams {
+    const uint32_t* q_codes;
+    const uint32_t* db_codes;
+    int64_t nq, ndb;
+    const int* thr;       // [nq] by query id
+    const int* n_active;  // EXACT: fail count
+    const int* qlist;     // EXACT: fail list
+    int P;
+    int64_t SL, R;
+    uint32_t* lists;
+    uint32_t cap;              // fast path: bin = q*P + s at lists + bin*cap
+    const uint32_t* bin_off2;  // EXACT: bin = f*P + s at lists + f*R + bin_off2[bin]
+    const uint32_t* bin_cap2;
+    const uint32_t* quota2;
+    uint32_t* bin_cnt;  // out: candidates seen per bin (may exceed the capacity -> overflow)
+};
+
+template <int W, int QT, bool EXACT>
+__global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams p)
+{
+    constexpr int NT = kSelectThreads;
+    constexpr int TILE = (W == 1 ? 2048 : (W == 2 ? 1024 : (W <= 4 ? 512 : 256)));
+    constexpr int U = (W <= 2 ? 4 : 2);
+    __shared__ __align__(128) uint32_t s_tile[2][TILE * W];
+    __shared__ __align__(8) uint64_t s_full[2];
+
+    const int tid = threadIdx.x;
+    const int split = blockIdx.y;
+    const int64_t n_act = EXACT ? (int64_t)*p.n_active : p.nq;
+    const int64_t slot0 = (int64_t)blockIdx.x * (NT * QT);
+    if (slot0 >= n_act) return;
+
+    const int64_t row0 = (int64_t)split * p.SL;
+    const int64_t row1 = min(row0 + p.SL, p.ndb);
+    const int64_t nrows = row1 > row0 ? row1 - row0 : 0;
+    const int ntiles = (int)((nrows + TILE - 1) / TILE);
+
+    uint32_t qw[QT][W];
+    int T[QT];
+    uint32_t cnt[QT], capk[QT];
+    uint32_t neq[QT], quota[QT];
+    uint32_t* lp[QT];
+    int64_t bin[QT];
+#pragma unroll
+    for (int k = 0; k < QT; ++k) {
+        const int64_t slot = slot0 + (int64_t)k * NT + tid;
+        const bool valid = slot < n_act;
+        const int64_t q = valid ? (EXACT ? (int64_t)p.qlist[slot] : slot) : 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) qw[k][w] = valid ? p.q_codes[q * W + w] : 0u;
+        T[k] = valid ? p.thr[q] : -1;
+        bin[k] = valid ? slot * p.P + split : -1;
+        cnt[k] = 0; neq[k] = 0;
+        if (EXACT) {
+            capk[k] = valid ? p.bin_cap2[bin[k]] : 0u;
+            quota[k] = valid ? p.quota2[bin[k]] : 0u;
+            lp[k] = p.lists + (valid ? slot * p.R + (int64_t)p.bin_off2[bin[k]] : 0);
+        } else {
+            capk[k] = p.cap;
+            quota[k] = 0xffffffffu;
+            lp[k] = p.lists + (valid ? bin[k] * (int64_t)p.cap : 0);
+        }
+    }
+
+    if (tid == 0) {
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const uint32_t* src0 = p.db_codes + row0 * W;
+    auto tile_rows = [&](int t) -> int { return (int)min((int64_t)TILE, nrows - (int64_t)t * TILE); };
+    auto issue = [&](int t) {
+        const int buf = t & 1;
+        const int rows = tile_rows(t);
+        const uint32_t* src = src0 + (int64_t)t * TILE * W;
+        if (rows == TILE) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&s_full[buf], TILE * W * 4);
+                tma_load_1d(&s_tile[buf][0], src, TILE * W * 4, &s_full[buf]);
+            }
+        } else {
+            for (int i = tid; i < rows * W; i += NT) s_tile[buf][i] = __ldg(src + i);
+        }
+    };
+    if (ntiles > 0) issue(0);
+    if (ntiles > 1) issue(1);
+    __syncthreads();  // ragged tiles written with plain stores become visible
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        const int rows = tile_rows(t);
+        if (rows == TILE) mbar_wait(&s_full[buf], (uint32_t)((t >> 1) & 1));
+        const uint32_t* tile = &s_tile[buf][0];
+        const uint32_t lbase = (uint32_t)t * TILE;
+
+        auto pair = [&](int k, const uint32_t (&v)[W], uint32_t lidx) {
+            const int d = hamming<W>(qw[k], v);
+            if (d <= T[k]) {
+                bool ok = true;
+                if (EXACT) {
+                    if (d == T[k]) { ok = neq[k] < quota[k]; neq[k]++; }
+                }
+                if (ok) {
+                    const uint32_t c = cnt[k];
+                    if (c < capk[k]) lp[k][c] = ((uint32_t)d << kIdxBits) | lidx;
+                    cnt[k] = c + 1;
+                }
+            }
+        };
+
+        int j = 0;
+        for (; j + U <= rows; j += U) {
+            uint32_t v[U][W];
+#pragma unroll
+            for (int u = 0; u < U; ++u) load_code<W>(tile, j + u, v[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int k = 0; k < QT; ++k) pair(k, v[u], lbase + j + u);
+            }
+        }
+        for (; j < rows; ++j) {
+            uint32_t v[W];
+            load_code<W>(tile, j, v);
+#pragma unroll
+            for (int k = 0; k < QT; ++k) pair(k, v, lbase + j);
+        }
+        __syncthreads();  // everyone is done with s_tile[buf]
+        if (t + 2 < ntiles) issue(t + 2);
+        // a ragged tile (only ever the last one) is ordered by the __syncthreads of the next trip
+    }
+
+#pragma unroll
+    for (int k = 0; k < QT; ++k)
+        if (bin[k] >= 0) p.bin_cnt[bin[k]] = cnt[k];
+}
+
+// ================================================================================================
+// 4. AP kernel: one warp per query.
+// ================================================================================================
+struct ApParams {
+    int64_t nq;
+    const int* n_active;
+    const int* qlist;  // indirect (exact path) when non-null
+    int P, b, LW;
+    int64_t SL, R;
+    uint32_t* lists;
+    uint32_t cap;
+    const uint32_t* bin_off2;  // exact path
+    const uint32_t* bin_cap2;  // exact path
+    const uint32_t* bin_cnt;
+    const int* thr;
+    const uint32_t* q_lab;
+    const uint32_t* db_lab;
+    double* ap;
+    uint32_t* ids;
+    uint16_t* dist;
+    int32_t* rel;
+    int* fail_list;  // fast path: queries to redo exactly
+    int* n_fail;
+    int no_fallback;
+};
+
+__global__ void __launch_bounds__(kApWarps * 32) ap_kernel(ApParams p)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = p.b + 1;
+    uint32_t* A = smem + (size_t)warp * 4 * nb;  // count per distance -> exclusive prefix N[d]
+    uint32_t* B = A + nb;                        // relevant count per distance -> exclusive prefix M[d]
+    uint32_t* C = B + nb;                        // running count per distance (walk 2)
+    uint32_t* D = C + nb;                        // running relevant count per distance (walk 2)
+    const bool exact = p.qlist != nullptr;
+    const int64_t n_act = exact ? (int64_t)*p.n_active : p.nq;
+    const int64_t slot = (int64_t)blockIdx.x * kApWarps + warp;
+    if (slot >= n_act) return;
+    const int64_t q = exact ? (int64_t)p.qlist[slot] : slot;
+    const int64_t binbase = slot * p.P;
+    const int T = p.thr[q];
+    const uint32_t FULL = 0xffffffffu;
+
+    for (int d = lane; d < nb; d += 32) { A[d] = 0; B[d] = 0; C[d] = 0; D[d] = 0; }
+
+    // ---- totals / overflow ----------------------------------------------------------------
+    unsigned long long total = 0;
+    int ovf = 0;
+    for (int s = lane; s < p.P; s += 32) {
+        const uint32_t c = p.bin_cnt[binbase + s];
+        const uint32_t capb = exact ? p.bin_cap2[binbase + s] : p.cap;
+        ovf |= (c > capb);
+        total += c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
+    ovf = __any_sync(FULL, ovf);
+    if (ovf || total < (unsigned long long)p.R || T < 0) {
+        if (lane == 0) {
+            if (p.fail_list != nullptr && !p.no_fallback) {
+                const int i = atomicAdd(p.n_fail, 1);
+                p.fail_list[i] = (int)q;
+            } else {
+                p.ap[q] = -1.0;  // diagnostics only: never reached with the fallback enabled
+                if (p.n_fail) atomicAdd(p.n_fail, 1);
+            }
+        }
+        return;
+    }
+    __syncwarp();
+
+    uint32_t ql[4];
+    const uint32_t* qlp = p.q_lab + q * p.LW;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) ql[w] = (w < p.LW) ? qlp[w] : 0u;
+
+    auto bin_ptr = [&](int s) -> uint32_t* {
+        return exact ? p.lists + slot * p.R + (int64_t)p.bin_off2[binbase + s] : p.lists + (binbase + s) * (int64_t)p.cap;
+    };
+
+    // ---- walk 1: relevance bit per candidate, histograms per distance ---------------------
+    for (int s = 0; s < p.P; ++s) {
+        const uint32_t c = p.bin_cnt[binbase + s];
+        uint32_t* lp = bin_ptr(s);
+        const int64_t row0 = (int64_t)s * p.SL;
+        for (uint32_t e = lane; e < c; e += 32) {
+            uint32_t ent = lp[e];
+            const uint32_t d = (ent >> kIdxBits) & kDistMask;
+            const int64_t row = row0 + (ent & kIdxMask);
+            const uint32_t* dl = p.db_lab + row * p.LW;
+            uint32_t m = 0;
+            if (p.LW <= 4) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    if (w < p.LW) m |= ql[w] & __ldg(dl + w);
+            } else {
+                for (int w = 0; w < p.LW; ++w) m |= __ldg(qlp + w) & __ldg(dl + w);
+            }
+            if (m) {
+                lp[e] = ent | 0x80000000u;
+                atomicAdd(&B[d], 1u);
+            }
+            atomicAdd(&A[d], 1u);
+        }
+    }
+    __syncwarp();
+
+    // ---- exclusive prefixes and the cut distance d* -----------------------------------------
+    int dstar = -1;
+    if (lane == 0) {
+        uint32_t cn = 0, cm = 0;
+        for (int d = 0; d <= T && d < nb; ++d) {
+            const uint32_t n = A[d], m = B[d];
+            A[d] = cn; B[d] = cm;
+            if (dstar < 0 && (unsigned long long)cn + n >= (unsigned long long)p.R) dstar = d;
+            cn += n; cm += m;
+        }
+    }
+    dstar = __shfl_sync(FULL, dstar, 0);
+    __syncwarp();
+    const uint32_t quota = (uint32_t)(p.R - (int64_t)A[dstar]);
+
+    // ---- walk 2: rank and relevant-prefix of every candidate, in database-row order -------------
+    double acc = 0.0;
+    int relc = 0;
+    for (int s = 0; s < p.P; ++s) {
+        const uint32_t c = p.bin_cnt[binbase + s];
+        const uint32_t* lp = bin_ptr(s);
+        const int64_t row0 = (int64_t)s * p.SL;
+        for (uint32_t base = 0; base < c; base += 32) {
+            const uint32_t e = base + lane;
+            const bool act = e < c;
+            const uint32_t ent = act ? lp[e] : 0u;
+            const int d = (int)((ent >> kIdxBits) & kDistMask);
+            const uint32_t match = ent >> 31;
+            const bool valid = act && d <= dstar;
+            const uint32_t key = valid ? (uint32_t)d : (1024u + lane);
+            const uint32_t peers = __match_any_sync(FULL, key);
+            const uint32_t mb = __ballot_sync(FULL, valid && match);
+            const uint32_t lt = peers & ((1u << lane) - 1u);
+            uint32_t rn = 0, rm = 0;
+            if (valid) { rn = C[d]; rm = D[d]; }
+            const uint32_t n = rn + __popc(lt) + 1u;
+            const uint32_t m = rm + __popc(lt & mb) + match;
+            const bool inc = valid && (d < dstar || n <= quota);
+            if (inc) {
+                const uint32_t pos = A[d] + n - 1u;
+                if (p.ids) p.ids[q * p.R + pos] = (uint32_t)(row0 + (ent & kIdxMask));
+                if (p.dist) p.dist[q * p.R + pos] = (uint16_t)d;
+                if (match) {
+                    acc += (double)(B[d] + m) / (double)(pos + 1u);
+                    relc += 1;
+                }
+            }
+            __syncwarp();
+            if (valid && lane == 31 - __clz(peers)) {
+                C[d] = rn + __popc(peers);
+                D[d] = rm + __popc(peers & mb);
+            }
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(FULL, acc, o);
+        relc += __shfl_xor_sync(FULL, relc, o);
+    }
+    if (lane == 0) {
+        p.ap[q] = relc ? acc / (double)relc : __longlong_as_double(0x7ff8000000000000LL);
+        if (p.rel) p.rel[q] = relc;
+    }
+}
+
+// ================================================================================================
+// 5. Exact path helpers.
+// ================================================================================================
+__global__ void zero_hist2_kernel(uint32_t* __restrict__ hist2, const int* __restrict__ n_fail, int64_t per_query)
+{
+    const int64_t n = (int64_t)*n_fail * per_query;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) hist2[i] = 0;
+}
+
+struct ExactPlanParams {
+    const uint32_t* hist2;  // [f][s][d]
+    const int* n_fail;
+    const int* fail_list;
+    int P, b;
+    int64_t R;
+    int* thr2;  // by query id
+    uint32_t* bin_off2;
+    uint32_t* bin_cap2;
+    uint32_t* quota2;
+};
+
+__global__ void __launch_bounds__(kApWarps * 32) exact_plan_kernel(ExactPlanParams p)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = p.b + 1;
+    unsigned long long* tot = reinterpret_cast<unsigned long long*>(smem) + (size_t)warp * nb;
+    const int64_t f = (int64_t)blockIdx.x * kApWarps + warp;
+    if (f >= (int64_t)*p.n_fail) return;
+    const int q = p.fail_list[f];
+    const uint32_t* h2 = p.hist2 + f * p.P * nb;
+    const uint32_t FULL = 0xffffffffu;
+    for (int d = lane; d < nb; d += 32) {
+        unsigned long long s = 0;
+        for (int sp = 0; sp < p.P; ++sp) s += h2[(int64_t)sp * nb + d];
+        tot[d] = s;
+    }
+    __syncwarp();
+    int dstar = p.b;
+    unsigned long long below = 0;
+    if (lane == 0) {
+        unsigned long long cum = 0;
+        for (int d = 0; d < nb; ++d) {
+            if (cum + tot[d] >= (unsigned long long)p.R) { dstar = d; below = cum; break; }
+            cum += tot[d];
+        }
+        p.thr2[q] = dstar;
+    }
+    dstar = __shfl_sync(FULL, dstar, 0);
+    below = __shfl_sync(FULL, below, 0);
+    const unsigned long long quota = (unsigned long long)p.R - below;
+    unsigned long long run_eq = 0, run_off = 0;
+    for (int sb = 0; sb < p.P; sb += 32) {
+        const int s = sb + lane;
+        unsigned long long lt = 0, eq = 0;
+        if (s < p.P) {
+            const uint32_t* hs = h2 + (int64_t)s * nb;
+            for (int d = 0; d < dstar; ++d) lt += hs[d];
+            eq = hs[dstar];
+        }
+        // exclusive scans over the 32 splits of this trip
+        unsigned long long eq_incl = eq;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(FULL, eq_incl, o);
+            if (lane >= o) eq_incl += t;
+        }
+        const unsigned long long eq_before = run_eq + eq_incl - eq;
+        unsigned long long take = 0;
+        if (quota > eq_before) take = min(eq, quota - eq_before);
+        const unsigned long long capb = lt + take;
+        unsigned long long cap_incl = capb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(FULL, cap_incl, o);
+            if (lane >= o) cap_incl += t;
+        }
+        if (s < p.P) {
+            p.bin_off2[f * p.P + s] = (uint32_t)(run_off + cap_incl - capb);
+            p.bin_cap2[f * p.P + s] = (uint32_t)capb;
+            p.quota2[f * p.P + s] = (uint32_t)take;
+        }
+        run_eq += __shfl_sync(FULL, eq_incl, 31);
+        run_off += __shfl_sync(FULL, cap_incl, 31);
+    }
+}
+
+// ================================================================================================
+// Launchers
+// ================================================================================================
+template <int W>
+static int launch_hist(const HistParams& hp, int64_t n_slots_max, int n_chunks, cudaStream_t st)
+{
+    const size_t smem = sizeof(uint32_t) * ((size_t)(hp.b + 1) * kHistThreads + (size_t)hp.seg_rows * W);
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        HG_CUDA_TRY(cudaFuncSetAttribute(hist_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((unsigned)ceil_div(n_slots_max, kHistThreads), (unsigned)n_chunks);
+    hist_kernel<W><<<grid, kHistThreads, smem, st>>>(hp);
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    return HG_OK;
+}
+
+template <int W, bool EXACT>
+static int launch_select_w(const SelectParams& sp, const Plan& pl, cudaStream_t st)
+{
+    dim3 grid((unsigned)pl.nqt, (unsigned)pl.P);
+    switch (pl.QT) {
+        case 4: select_kernel<W, 4, EXACT><<<grid, kSelectThreads, 0, st>>>(sp); break;
+        case 2: select_kernel<W, 2, EXACT><<<grid, kSelectThreads, 0, st>>>(sp); break;
+        default: select_kernel<W, 1, EXACT><<<grid, kSelectThreads, 0, st>>>(sp); break;
+    }
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    return HG_OK;
+}
+
+static int launch_ap(const ApParams& ap, int64_t n_slots_max, cudaStream_t st)
+{
+    const size_t smem = sizeof(uint32_t) * 4 * (size_t)(ap.b + 1) * kApWarps;
+    ap_kernel<<<(unsigned)ceil_div(n_slots_max, kApWarps), kApWarps * 32, smem, st>>>(ap);
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    return HG_OK;
+}
+
+template <int W>
+static int run_map(const Plan& pl, const uint32_t* q_codes, const uint32_t* q_lab, const uint32_t* db_codes, const uint32_t* db_lab,
+                   unsigned flags, double* d_ap, uint32_t* d_ids, uint16_t* d_dist, int32_t* d_rel, char* ws, cudaStream_t st)
+{
+    int* ctrl = reinterpret_cast<int*>(ws + pl.off_ctrl);
+    int* thr = reinterpret_cast<int*>(ws + pl.off_thr);
+    int* thr2 = reinterpret_cast<int*>(ws + pl.off_thr2);
+    int* fail_list = reinterpret_cast<int*>(ws + pl.off_fail);
+    uint32_t* hist_s = reinterpret_cast<uint32_t*>(ws + pl.off_hist_s);
+    uint32_t* bin_cnt = reinterpret_cast<uint32_t*>(ws + pl.off_bin_cnt);
+    uint32_t* bin_cnt2 = reinterpret_cast<uint32_t*>(ws + pl.off_bin_cnt2);
+    uint32_t* bin_off2 = reinterpret_cast<uint32_t*>(ws + pl.off_bin_off2);
+    uint32_t* bin_cap2 = reinterpret_cast<uint32_t*>(ws + pl.off_bin_cap2);
+    uint32_t* quota2 = reinterpret_cast<uint32_t*>(ws + pl.off_quota2);
+    uint32_t* hist2 = reinterpret_cast<uint32_t*>(ws + pl.off_hist2);
+    uint32_t* lists = reinterpret_cast<uint32_t*>(ws + pl.off_lists);
+    int* n_fail = ctrl;
+    const bool force_exact = (flags & HG_FLAG_FORCE_EXACT) != 0;
+    const bool no_fallback = (flags & HG_FLAG_NO_FALLBACK) != 0;
+    const int nb = pl.b + 1;
+
+    PhaseTimer& timer = phase_timer();
+    timer.armed = false;
+    if (flags & HG_FLAG_TIMING) {
+        int trc = timer.ensure();
+        if (trc != HG_OK) return trc;
+        timer.armed = true;
+    }
+    HG_CUDA_TRY(cudaMemsetAsync(ctrl, 0, 256, st));
+    int rc;
+    timer.mark(kPhaseSample, st);
+    if (!force_exact) {
+        // 1. sampled histogram
+        HG_CUDA_TRY(cudaMemsetAsync(hist_s, 0, sizeof(uint32_t) * (size_t)pl.nq * nb, st));
+        HistParams hp{};
+        hp.q_codes = q_codes; hp.db_codes = db_codes; hp.nq = pl.nq; hp.ndb = pl.ndb; hp.b = pl.b;
+        hp.n_active = nullptr; hp.qlist = nullptr;
+        hp.seg_stride = pl.seg_stride; hp.n_seg = pl.n_seg; hp.seg_rows = pl.TILE; hp.seg_per_chunk = pl.seg_per_chunk;
+        hp.out = hist_s; hp.out_chunks = 1;
+        if ((rc = launch_hist<W>(hp, pl.nq, pl.n_chunks, st)) != HG_OK) return rc;
+    }
+    // 2. thresholds
+    timer.mark(kPhaseThreshold, st);
+    thr_kernel<<<(unsigned)ceil_div(pl.nq, 256), 256, 0, st>>>(hist_s, pl.nq, pl.b, pl.sample_rows, pl.ndb, pl.R, kSampleZ,
+                                                               force_exact ? 1 : 0, thr);
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    timer.mark(kPhaseSelect, st);
+    if (!force_exact) {
+        // 3. single-pass select
+        SelectParams sp{};
+        sp.q_codes = q_codes; sp.db_codes = db_codes; sp.nq = pl.nq; sp.ndb = pl.ndb; sp.thr = thr;
+        sp.n_active = nullptr; sp.qlist = nullptr; sp.P = pl.P; sp.SL = pl.SL; sp.R = pl.R;
+        sp.lists = lists; sp.cap = pl.cap; sp.bin_off2 = nullptr; sp.bin_cap2 = nullptr; sp.quota2 = nullptr;
+        sp.bin_cnt = bin_cnt;
+        if ((rc = launch_select_w<W, false>(sp, pl, st)) != HG_OK) return rc;
+    } else {
+        HG_CUDA_TRY(cudaMemsetAsync(bin_cnt, 0, sizeof(uint32_t) * (size_t)pl.nq * pl.P, st));
+    }
+    // 4. AP (queries that cannot be answered exactly from their bins go to the fail list)
+    timer.mark(kPhaseAp, st);
+    {
+        ApParams ap{};
+        ap.nq = pl.nq; ap.n_active = nullptr; ap.qlist = nullptr; ap.P = pl.P; ap.b = pl.b; ap.LW = pl.LW; ap.SL = pl.SL; ap.R = pl.R;
+        ap.lists = lists; ap.cap = pl.cap; ap.bin_off2 = nullptr; ap.bin_cap2 = nullptr; ap.bin_cnt = bin_cnt; ap.thr = thr;
+        ap.q_lab = q_lab; ap.db_lab = db_lab; ap.ap = d_ap; ap.ids = d_ids; ap.dist = d_dist; ap.rel = d_rel;
+        ap.fail_list = fail_list; ap.n_fail = n_fail; ap.no_fallback = no_fallback ? 1 : 0;
+        if ((rc = launch_ap(ap, pl.nq, st)) != HG_OK) return rc;
+    }
+    timer.mark(kPhaseExact, st);
+    if (no_fallback) { timer.mark(kNumPhases, st); return HG_OK; }
+    // 5. exact path for the fail list (grids sized for nq, CTAs beyond the fail count exit immediately)
+    {
+        const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
+        zero_hist2_kernel<<<sms * 4, 256, 0, st>>>(hist2, n_fail, (int64_t)pl.P * nb);
+        count_launch();
+        HG_CUDA_TRY(cudaGetLastError());
+        HistParams hp{};
+        hp.q_codes = q_codes; hp.db_codes = db_codes; hp.nq = pl.nq; hp.ndb = pl.ndb; hp.b = pl.b;
+        hp.n_active = n_fail; hp.qlist = fail_list;
+        hp.seg_stride = pl.TILE; hp.n_seg = ceil_div(pl.ndb, pl.TILE); hp.seg_rows = pl.TILE; hp.seg_per_chunk = (int)(pl.SL / pl.TILE);
+        hp.out = hist2; hp.out_chunks = pl.P;
+        if ((rc = launch_hist<W>(hp, pl.nq, pl.P, st)) != HG_OK) return rc;
+
+        ExactPlanParams ep{};
+        ep.hist2 = hist2; ep.n_fail = n_fail; ep.fail_list = fail_list; ep.P = pl.P; ep.b = pl.b; ep.R = pl.R;
+        ep.thr2 = thr2; ep.bin_off2 = bin_off2; ep.bin_cap2 = bin_cap2; ep.quota2 = quota2;
+        const size_t smem = sizeof(unsigned long long) * (size_t)nb * kApWarps;
+        exact_plan_kernel<<<(unsigned)ceil_div(pl.nq, kApWarps), kApWarps * 32, smem, st>>>(ep);
+        count_launch();
+        HG_CUDA_TRY(cudaGetLastError());
+
+        SelectParams sp{};
+        sp.q_codes = q_codes; sp.db_codes = db_codes; sp.nq = pl.nq; sp.ndb = pl.ndb; sp.thr = thr2;
+        sp.n_active = n_fail; sp.qlist = fail_list; sp.P = pl.P; sp.SL = pl.SL; sp.R = pl.R;
+        sp.lists = lists; sp.cap = 0; sp.bin_off2 = bin_off2; sp.bin_cap2 = bin_cap2; sp.quota2 = quota2;
+        sp.bin_cnt = bin_cnt2;
+        if ((rc = launch_select_w<W, true>(sp, pl, st)) != HG_OK) return rc;
+
+        ApParams ap{};
+        ap.nq = pl.nq; ap.n_active = n_fail; ap.qlist = fail_list; ap.P = pl.P; ap.b = pl.b; ap.LW = pl.LW; ap.SL = pl.SL; ap.R = pl.R;
+        ap.lists = lists; ap.cap = 0; ap.bin_off2 = bin_off2; ap.bin_cap2 = bin_cap2; ap.bin_cnt = bin_cnt2; ap.thr = thr2;
+        ap.q_lab = q_lab; ap.db_lab = db_lab; ap.ap = d_ap; ap.ids = d_ids; ap.dist = d_dist; ap.rel = d_rel;
+        ap.fail_list = nullptr; ap.n_fail = ctrl + 1; ap.no_fallback = 0;
+        if ((rc = launch_ap(ap, pl.nq, st)) != HG_OK) return rc;
+    }
+    timer.mark(kNumPhases, st);
+    return HG_OK;
+}
+
+}  // namespace hg
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" size_t hg_hamming_map_workspace_bytes(int64_t nq, int64_t ndb, int b, int L, int64_t R)
+{
+    const hg::Plan pl = hg::make_plan(nq, ndb, b, L, R);
+    return pl.ok ? pl.total : 0;
+}
+
+extern "C" int hg_hamming_map(const uint32_t* d_q_codes, const uint32_t* d_q_lab, int64_t nq, const uint32_t* d_db_codes,
+                              const uint32_t* d_db_lab, int64_t ndb, int b, int L, int64_t R, unsigned flags, double* d_ap,
+                              uint32_t* d_ids, uint16_t* d_dist, int32_t* d_rel, void* d_workspace, size_t workspace_bytes, void* stream)
+{
+    if (nq == 0) return HG_OK;
+    if (nq < 0 || ndb < 0) return hg::fail(HG_EINVAL, "hg_hamming_map: negative size");
+    if (R <= 0) return hg::fail(HG_EINVAL, "hg_hamming_map: R must be positive (got %lld)", (long long)R);
+    if (R > ndb) return hg::fail(HG_ERANGE, "hg_hamming_map: R=%lld exceeds the database size %lld", (long long)R, (long long)ndb);
+    if (hg_code_words(b) == 0) return hg::fail(HG_EINVAL, "hg_hamming_map: unsupported hash length b=%d (1..%d)", b, HG_MAX_BITS);
+    if (hg_label_words(L) == 0) return hg::fail(HG_EINVAL, "hg_hamming_map: unsupported label width L=%d", L);
+    if (!d_q_codes || !d_q_lab || !d_db_codes || !d_db_lab || !d_ap || !d_workspace)
+        return hg::fail(HG_EINVAL, "hg_hamming_map: NULL pointer");
+    if ((reinterpret_cast<uintptr_t>(d_db_codes) & 15) || (reinterpret_cast<uintptr_t>(d_workspace) & 255))
+        return hg::fail(HG_EINVAL, "hg_hamming_map: d_db_codes must be 16-byte and the workspace 256-byte aligned");
+    if (!hg::device_facts().ok) return hg::fail(HG_ECUDA, "hg_hamming_map: no CUDA device");
+    const hg::Plan pl = hg::make_plan(nq, ndb, b, L, R);
+    if (!pl.ok) return hg::fail(HG_EINVAL, "hg_hamming_map: sizes out of range (nq=%lld ndb=%lld)", (long long)nq, (long long)ndb);
+    if (workspace_bytes < pl.total)
+        return hg::fail(HG_ENOMEM, "hg_hamming_map: workspace %zu B < required %zu B", workspace_bytes, pl.total);
+    char* ws = static_cast<char*>(d_workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (pl.W) {
+        case 1: return hg::run_map<1>(pl, d_q_codes, d_q_lab, d_db_codes, d_db_lab, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
+        case 2: return hg::run_map<2>(pl, d_q_codes, d_q_lab, d_db_codes, d_db_lab, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
+        case 3: return hg::run_map<3>(pl, d_q_codes, d_q_lab, d_db_codes, d_db_lab, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
+        case 4: return hg::run_map<4>(pl, d_q_codes, d_q_lab, d_db_codes, d_db_lab, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
+        case 8: return hg::run_map<8>(pl, d_q_codes, d_q_lab, d_db_codes, d_db_lab, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
+        default: return hg::fail(HG_EINVAL, "hg_hamming_map: unsupported word count %d", pl.W);
+    }
+}
+
+extern "C" int hg_hamming_map_stats(const void* d_workspace, size_t workspace_bytes, int64_t nq, int64_t ndb, int b, int L, int64_t R,
+                                    int64_t out[8], void* stream)
+{
+    const hg::Plan pl = hg::make_plan(nq, ndb, b, L, R);
+    if (!pl.ok || !d_workspace || workspace_bytes < pl.total || !out) return hg::fail(HG_EINVAL, "hg_hamming_map_stats: bad arguments");
+    int ctrl[4] = {0, 0, 0, 0};
+    HG_CUDA_TRY(cudaMemcpyAsync(ctrl, static_cast<const char*>(d_workspace) + pl.off_ctrl, sizeof(ctrl), cudaMemcpyDeviceToHost,
+                                (cudaStream_t)stream));
+    HG_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    out[0] = ctrl[0];
+    out[1] = pl.P;
+    out[2] = pl.SL;
+    out[3] = pl.cap;
+    out[4] = pl.TQ;
+    out[5] = pl.sample_rows;
+    out[6] = ctrl[1];
+    out[7] = pl.nqt;
+    return HG_OK;
+}

@@ -1,0 +1,304 @@
+"""mAP@R by Hamming ranking -- the drop-in for the reference's ``lib/metric.py``.
+
+Reference surface kept (thuml/HashGAN):
+    lib/metric.py:4-6    class MAPs: __init__(self, r) -> self.R
+    lib/metric.py:8-10   MAPs.distance(a, b)            (dead code in the reference; kept)
+    lib/metric.py:12-24  MAPs.get_maps_by_feature(database, query) -> numpy.float64
+    main.py:164          MAPs(cfg.DATA.MAP_R).get_maps_by_feature(db, test)
+
+``database`` / ``query`` are any objects with ``.output`` ([N, b] features) and ``.label`` ([N, L] 0/1
+integers), e.g. the EasyDict of main.py:157 or a SimpleNamespace.  Arrays may be NumPy arrays or
+torch tensors (host or CUDA).  The work is done by hand-written sm_100a kernels behind the C ABI of
+``include/hashgan_b200.h``; torch only owns device memory and streams.  There is no CPU path.
+
+Semantics relative to the reference:
+  * features are binarised by sign (bit = x > 0); on {-1,+1} inputs the reference's inner-product order
+    (lib/metric.py:13-14) is exactly the Hamming order computed here (ip = b - 2 d_H);
+  * ties are broken by database row (== ``np.argsort(kind='stable')``); the reference's default argsort
+    leaves tie order to the NumPy build;
+  * queries with no relevant row in their top-R are skipped (lib/metric.py:22-23), all skipped -> nan;
+  * R > Ndb raises ValueError (the reference fails in the broadcast of lib/metric.py:21).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _native
+
+__all__ = ["MAPs", "MAPs_CQ", "pack_codes", "pack_labels", "hamming_map_device"]
+
+# One call of hg_hamming_map handles a query chunk whose workspace stays under this many bytes.
+DEFAULT_WORKSPACE_LIMIT = 24 << 30
+
+
+def _torch():
+    import torch  # torch is the device-memory / stream / process-group plumbing
+
+    return torch
+
+
+def _require_cuda(torch, device):
+    if not torch.cuda.is_available():
+        raise _native.NativeLibraryError(
+            "hashgan_b200 needs a CUDA device (sm_100a); there is no CPU fallback for the metric path")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise ValueError("device must be a CUDA device")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def _stream_ptr(torch, device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _features_to_device(torch, x, device):
+    """[N, b] features -> contiguous float32 CUDA tensor (non-blocking copy when the source is pinned)."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        a = np.asarray(x)
+        if a.dtype != np.float32:
+            a = a.astype(np.float32)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.dim() != 2:
+        raise ValueError(f"features must be 2-D [N, b], got shape {tuple(t.shape)}")
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+_LABEL_BYTES = {}
+
+
+def _labels_to_device(torch, x, device):
+    """[N, L] 0/1 labels -> contiguous CUDA tensor of int64 / int32 / int8 (as given) and its item size."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        a = np.asarray(x)
+        if a.dtype == np.bool_:
+            a = a.astype(np.int8)
+        elif a.dtype.kind not in "iu":
+            raise TypeError(f"labels must be an integer 0/1 matrix, got dtype {a.dtype}")
+        elif a.dtype.itemsize == 2:
+            a = a.astype(np.int32)
+        elif a.dtype.kind == "u" and a.dtype.itemsize in (4, 8):
+            a = a.astype(np.int64)
+        elif a.dtype == np.uint8:
+            a = a.view(np.int8)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.dim() != 2:
+        raise ValueError(f"labels must be 2-D [N, L], got shape {tuple(t.shape)}")
+    if t.dtype == torch.bool:
+        t = t.to(torch.int8)
+    elif t.dtype == torch.uint8:
+        t = t.view(torch.int8)
+    elif t.dtype == torch.int16:
+        t = t.to(torch.int32)
+    elif t.dtype not in (torch.int64, torch.int32, torch.int8):
+        raise TypeError(f"labels must be an integer 0/1 matrix, got dtype {t.dtype}")
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    t = t.contiguous()
+    return t, t.element_size()
+
+
+def pack_codes(feat, device=None):
+    """sign + bit-pack [N, b] float features on the GPU -> uint32 words as an int32 CUDA tensor
+    [N, hg_code_words(b)] (C ABI: hg_pack_sign_f32)."""
+    torch = _torch()
+    device = _require_cuda(torch, device)
+    lib = _native.lib()
+    with torch.cuda.device(device):
+        f = _features_to_device(torch, feat, device)
+        n, b = f.shape
+        W = _native.code_words(b)
+        codes = torch.empty((n, W), dtype=torch.int32, device=device)
+        _native.check(lib.hg_pack_sign_f32(f.data_ptr(), n, b, b, codes.data_ptr(), _stream_ptr(torch, device)))
+        f.record_stream(torch.cuda.current_stream(device))
+    return codes
+
+
+def pack_labels(lab, device=None, bad_flag=None):
+    """0/1 label matrix [N, L] -> bit rows, int32 CUDA tensor [N, ceil(L/32)] (C ABI: hg_pack_labels).
+    ``bad_flag`` (int32 CUDA tensor [1]) is OR-ed with 1 when a label is not 0/1."""
+    torch = _torch()
+    device = _require_cuda(torch, device)
+    lib = _native.lib()
+    with torch.cuda.device(device):
+        t, nbytes = _labels_to_device(torch, lab, device)
+        n, L = t.shape
+        LW = _native.label_words(L)
+        packed = torch.empty((n, LW), dtype=torch.int32, device=device)
+        _native.check(lib.hg_pack_labels(t.data_ptr(), nbytes, n, L, packed.data_ptr(),
+                                         bad_flag.data_ptr() if bad_flag is not None else None,
+                                         _stream_ptr(torch, device)))
+        t.record_stream(torch.cuda.current_stream(device))
+    return packed
+
+
+def _query_chunk(nq: int, ndb: int, b: int, L: int, R: int, limit: int) -> int:
+    """Largest query count whose hg_hamming_map workspace fits in `limit` bytes."""
+    lib = _native.lib()
+    need = lib.hg_hamming_map_workspace_bytes(nq, ndb, b, L, R)
+    if need == 0:
+        raise ValueError(f"sizes out of range for the Hamming kernel: nq={nq} ndb={ndb} b={b} L={L} R={R}")
+    if need <= limit:
+        return nq
+    lo, hi = 1, nq
+    while lo < hi:  # workspace is monotone in nq
+        mid = (lo + hi + 1) // 2
+        if lib.hg_hamming_map_workspace_bytes(mid, ndb, b, L, R) <= limit:
+            lo = mid
+        else:
+            hi = mid - 1
+    if lib.hg_hamming_map_workspace_bytes(lo, ndb, b, L, R) > limit:
+        raise MemoryError(f"workspace limit {limit} B is too small for a single query against ndb={ndb}")
+    return lo
+
+
+def hamming_map_device(q_codes, q_lab, db_codes, db_lab, b: int, L: int, R: int, *, flags: int = 0,
+                       want_ids: bool = False, want_rel: bool = False,
+                       workspace_limit: int = DEFAULT_WORKSPACE_LIMIT, stats: Optional[dict] = None):
+    """Per-query AP@R from packed device tensors (C ABI: hg_hamming_map).  Returns (ap, ids, dist, rel);
+    ids/dist/rel are None unless requested.  Everything stays on the device and on the current stream."""
+    torch = _torch()
+    lib = _native.lib()
+    device = db_codes.device
+    nq, ndb = int(q_codes.shape[0]), int(db_codes.shape[0])
+    if R > ndb:
+        raise ValueError(f"operands could not be broadcast together: R={R} exceeds the database size {ndb}")
+    if R <= 0:
+        raise ValueError("R must be positive")
+    with torch.cuda.device(device):
+        ap = torch.empty((nq,), dtype=torch.float64, device=device)
+        ids = torch.empty((nq, R), dtype=torch.int32, device=device) if want_ids else None
+        dist = torch.empty((nq, R), dtype=torch.int16, device=device) if want_ids else None
+        rel = torch.empty((nq,), dtype=torch.int32, device=device) if want_rel else None
+        if nq == 0:
+            return ap, ids, dist, rel
+        chunk = _query_chunk(nq, ndb, b, L, R, workspace_limit)
+        ws_bytes = lib.hg_hamming_map_workspace_bytes(chunk, ndb, b, L, R)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=device)
+        stream = _stream_ptr(torch, device)
+        for s in range(0, nq, chunk):
+            n = min(chunk, nq - s)
+            _native.check(lib.hg_hamming_map(
+                q_codes[s:s + n].data_ptr(), q_lab[s:s + n].data_ptr(), n,
+                db_codes.data_ptr(), db_lab.data_ptr(), ndb, b, L, R, flags,
+                ap[s:s + n].data_ptr(),
+                ids[s:s + n].data_ptr() if ids is not None else None,
+                dist[s:s + n].data_ptr() if dist is not None else None,
+                rel[s:s + n].data_ptr() if rel is not None else None,
+                ws.data_ptr(), ws_bytes, stream))
+            if stats is not None:
+                out = (C.c_int64 * 8)()
+                _native.check(lib.hg_hamming_map_stats(ws.data_ptr(), ws_bytes, n, ndb, b, L, R, out, stream))
+                stats.setdefault("chunks", []).append(
+                    dict(exact_queries=int(out[0]), splits=int(out[1]), rows_per_split=int(out[2]), bin_entries=int(out[3]),
+                         queries_per_cta=int(out[4]), sample_rows=int(out[5]), exact_failures=int(out[6]),
+                         query_tiles=int(out[7]), nq=n))
+    return ap, ids, dist, rel
+
+
+class MAPs:
+    """Drop-in for ``lib.metric.MAPs`` (lib/metric.py:4-24)."""
+
+    def __init__(self, r, *, device=None, flags: int = 0, workspace_limit: int = DEFAULT_WORKSPACE_LIMIT):
+        self.R = r
+        self.device = device
+        self.flags = flags
+        self.workspace_limit = workspace_limit
+        self.last_stats: dict = {}
+
+    @staticmethod
+    def distance(a, b):
+        # lib/metric.py:8-10 (unused by the reference itself)
+        return np.dot(a, b)
+
+    # -- device-side pipeline ---------------------------------------------------------------------
+    def _pack_all(self, database, query):
+        torch = _torch()
+        device = _require_cuda(torch, self.device)
+        with torch.cuda.device(device):
+            bad = torch.zeros((1,), dtype=torch.int32, device=device)
+            db_f = _features_to_device(torch, database.output, device)
+            q_f = _features_to_device(torch, query.output, device)
+            if db_f.shape[1] != q_f.shape[1]:
+                raise ValueError(f"shapes {tuple(q_f.shape)} and {tuple(db_f.shape)} not aligned: hash lengths differ")
+            db_codes = pack_codes(db_f, device)
+            q_codes = pack_codes(q_f, device)
+            db_lab = pack_labels(database.label, device, bad)
+            q_lab = pack_labels(query.label, device, bad)
+            b = int(db_f.shape[1])
+            L = int(np.shape(database.label)[1]) if not hasattr(database.label, "shape") else int(database.label.shape[1])
+            Lq = int(query.label.shape[1]) if hasattr(query.label, "shape") else int(np.shape(query.label)[1])
+            if L != Lq:
+                raise ValueError(f"label widths differ: database {L}, query {Lq}")
+            if db_codes.shape[0] != db_lab.shape[0] or q_codes.shape[0] != q_lab.shape[0]:
+                raise ValueError("output and label row counts differ")
+        return device, bad, db_codes, db_lab, q_codes, q_lab, b, L
+
+    def per_query_ap(self, database, query, *, want_ids: bool = False):
+        """Per-query AP@R as a NumPy float64 vector (NaN where the reference would skip the query).
+        With ``want_ids`` also returns (ids [Nq, R] int64, dist [Nq, R] int32) in rank order."""
+        torch = _torch()
+        device, bad, db_codes, db_lab, q_codes, q_lab, b, L = self._pack_all(database, query)
+        R = int(self.R)
+        self.last_stats = {}
+        ap, ids, dist, _ = hamming_map_device(q_codes, q_lab, db_codes, db_lab, b, L, R, flags=self.flags, want_ids=want_ids,
+                                              workspace_limit=self.workspace_limit, stats=None)
+        ap_h = ap.cpu().numpy()
+        if int(bad.item()) != 0:
+            raise ValueError("labels must be 0/1 integers (lib/metric.py:17-19 is only defined for 0/1 labels)")
+        if want_ids:
+            return ap_h, ids.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, dist.cpu().numpy().astype(np.int32) & 0xFFFF
+        return ap_h
+
+    def get_maps_by_feature(self, database, query):
+        """mAP@R; same call and return type (numpy.float64) as lib/metric.py:12-24."""
+        ap = self.per_query_ap(database, query)
+        kept = ap[~np.isnan(ap)]
+        return np.mean(kept)  # lib/metric.py:24 (nan + RuntimeWarning when every query was skipped)
+
+    def get_maps_by_feature_host(self, database, query, return_ap: bool = False):
+        """Same result through the single C call hg_maps_by_feature_host (host pointers in, scalar out)."""
+        lib = _native.lib()
+        db_f = np.ascontiguousarray(np.asarray(database.output), dtype=np.float32)
+        q_f = np.ascontiguousarray(np.asarray(query.output), dtype=np.float32)
+        db_l = np.ascontiguousarray(np.asarray(database.label))
+        q_l = np.ascontiguousarray(np.asarray(query.label))
+        if db_l.dtype != q_l.dtype or db_l.dtype.kind not in "iub" or db_l.dtype.itemsize not in (1, 4, 8):
+            db_l = db_l.astype(np.int64)
+            q_l = q_l.astype(np.int64)
+        if db_f.ndim != 2 or q_f.ndim != 2 or db_f.shape[1] != q_f.shape[1]:
+            raise ValueError("features must be [N, b] with equal b")
+        if db_l.shape[1] != q_l.shape[1]:
+            raise ValueError("label widths differ")
+        R = int(self.R)
+        if R > db_f.shape[0]:
+            raise ValueError(f"operands could not be broadcast together: R={R} exceeds the database size {db_f.shape[0]}")
+        out = C.c_double(0.0)
+        ap = np.empty((q_f.shape[0],), dtype=np.float64)
+        rc = lib.hg_maps_by_feature_host(db_f.ctypes.data, db_l.ctypes.data, db_f.shape[0], q_f.ctypes.data, q_l.ctypes.data,
+                                         q_f.shape[0], db_f.shape[1], db_l.shape[1], db_l.dtype.itemsize, R, self.flags,
+                                         C.byref(out), ap.ctypes.data)
+        if rc == _native.HG_ELABEL:
+            raise ValueError("labels must be 0/1 integers")
+        _native.check(rc)
+        val = np.float64(out.value)
+        return (val, ap) if return_ap else val
+
+
+# north_star asks for a `MAPs_CQ()` call signature; no such symbol exists in thuml/HashGAN (it belongs to
+# thuml/DeepHash).  Exported as a plain alias of the class the reference really has.
+MAPs_CQ = MAPs

@@ -1,0 +1,117 @@
+/* hashgan_b200.h -- C ABI of libhashgan_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the retrieval-evaluation hot path of thuml/HashGAN.  The reference has no
+ * FFI of its own (it is pure Python); each entry point below cites the reference code it replaces.
+ * All pointers named d_* are DEVICE pointers (e.g. torch.Tensor.data_ptr()), h_* are HOST pointers.
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream).  Every function returns
+ * 0 on success and a non-zero HG_E* code otherwise; hg_last_error() gives the message of the
+ * last failure on the calling thread.  No function allocates device memory behind the caller's back
+ * except hg_maps_by_feature_host (documented there).  Functions are thread-compatible: concurrent
+ * calls must use distinct workspaces.
+ */
+#ifndef HASHGAN_B200_H
+#define HASHGAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HG_OK 0
+#define HG_EINVAL 1      /* bad argument (NULL pointer, size, alignment, unsupported b / L) */
+#define HG_ERANGE 2      /* R > ndb: the reference raises ValueError here (lib/metric.py:21 broadcast) */
+#define HG_ENOMEM 3      /* workspace too small / allocation failed */
+#define HG_ECUDA 4       /* CUDA runtime error, see hg_last_error() */
+#define HG_ELABEL 5      /* a label was not 0/1 (lib/metric.py:17-19 is only defined for 0/1 labels) */
+
+#define HG_MAX_BITS 256  /* hash length b supported by the kernels (reference default 64, lib/config.py:10) */
+#define HG_MAX_LABELS 4096
+
+/* flags for hg_hamming_map */
+#define HG_FLAG_FORCE_EXACT 1u  /* skip the sampled-threshold fast pass; every query takes the two-pass exact path */
+#define HG_FLAG_NO_FALLBACK 2u  /* (diagnostics) do not run the exact path; failed queries get AP = -1 */
+#define HG_FLAG_TIMING 4u       /* record CUDA events around the phases, read back with hg_hamming_map_phase_ms */
+
+int hg_version(void);
+const char* hg_last_error(void);
+
+/* Device facts used for grid sizing (multiples of the SM count). */
+int hg_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes);
+
+/* Number of uint32 words per packed code row as the kernels lay them out: ceil(b/32) for b<=128,
+ * 8 for 128<b<=256 (zero pad words).  Returns 0 for unsupported b. */
+int hg_code_words(int b);
+/* Words per packed label row: ceil(L/32). */
+int hg_label_words(int L);
+
+/* sign + bit-pack.  New in the build: the reference never binarises (main.py:155-157 hands tanh
+ * outputs straight to lib/metric.py:13); on {-1,+1} inputs ip = b - 2*d_H, so ranking by inner
+ * product (lib/metric.py:13-14) == ranking by Hamming distance of these words.
+ * d_feat: [n, ld] float32 row-major, first b columns used.  d_codes: [n, hg_code_words(b)] uint32,
+ * bit j of word w = (feat[i, 32w+j] > 0); pad bits/words are zero. */
+int hg_pack_sign_f32(const float* d_feat, int64_t n, int b, int64_t ld, uint32_t* d_codes, void* stream);
+
+/* 0/1 label matrix -> bit rows.  Replaces the per-query gather/compare of lib/metric.py:17-19:
+ * imatch = any_l(db.label[l] == label[l]) with query zeros rewritten to -1  <=>  (q_bits & db_bits) != 0.
+ * d_lab: [n, L] int64 (the dtype np.array(list-of-int) gives, lib/dataloader.py:45,74) or int32/uint8
+ * (elem_bytes = 8, 4 or 1).  d_packed: [n, hg_label_words(L)] uint32.  d_bad (optional, int32[1]) is
+ * OR-ed with 1 if any label is not 0/1. */
+int hg_pack_labels(const void* d_lab, int elem_bytes, int64_t n, int L, uint32_t* d_packed, int* d_bad, void* stream);
+
+/* Workspace (bytes) hg_hamming_map needs for these sizes; 0 on invalid arguments. */
+size_t hg_hamming_map_workspace_bytes(int64_t nq, int64_t ndb, int b, int L, int64_t R);
+
+/* The metric hot path, lib/metric.py:12-23 for all queries at once:
+ *   lib/metric.py:13-14  all-pairs inner product + argsort   -> XOR/POPC Hamming distance + exact
+ *                        (distance asc, database row asc) ranking == np.argsort(kind='stable')
+ *   lib/metric.py:16-23  per-query relevance, cumsum, AP     -> integer prefix counts + fp64 divides
+ * d_ap[q] = AP@R of query q, NaN where the top-R holds no relevant row (the reference skips those
+ * queries, lib/metric.py:22-23).  Optional outputs (may be NULL): d_ids [nq, R] uint32 database rows in
+ * rank order, d_dist [nq, R] uint16 their Hamming distances, d_rel [nq] int32 relevant count in top-R.
+ * Codes/labels as produced by hg_pack_sign_f32 / hg_pack_labels; d_db_codes must be 16-byte aligned.
+ * Asynchronous on `stream`; the workspace must stay alive until the stream has drained. */
+int hg_hamming_map(const uint32_t* d_q_codes, const uint32_t* d_q_lab, int64_t nq,
+                   const uint32_t* d_db_codes, const uint32_t* d_db_lab, int64_t ndb,
+                   int b, int L, int64_t R, unsigned flags,
+                   double* d_ap, uint32_t* d_ids, uint16_t* d_dist, int32_t* d_rel,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Diagnostics of the last hg_hamming_map run on this workspace (host copy, synchronises `stream`):
+ * out[0] = queries that needed the exact two-pass path, out[1] = db splits P, out[2] = rows per split,
+ * out[3] = entries per candidate bin, out[4] = queries per CTA tile, out[5] = sample rows used. */
+int hg_hamming_map_stats(const void* d_workspace, size_t workspace_bytes, int64_t nq, int64_t ndb, int b, int L,
+                         int64_t R, int64_t out[8], void* stream);
+
+/* Device time (ms, CUDA events on the call's stream) of the phases of the last hg_hamming_map call made by this
+ * thread with HG_FLAG_TIMING: out[0] sampled histogram, out[1] thresholds, out[2] select (the all-pairs XOR/POPC
+ * kernel), out[3] AP, out[4] exact-path chain.  Synchronises on the last event. */
+int hg_hamming_map_phase_ms(float out[5]);
+
+/* Number of kernels this library has launched in this process so far (reset != 0 zeroes the counter). */
+int64_t hg_launch_count(int reset);
+
+/* lib/metric.py:24 on the device result: mean over non-NaN entries, computed on the host in fp64 from a
+ * D2H copy of d_ap (synchronises `stream`).  *map_out = NaN when every query was skipped. */
+int hg_mean_ap(const double* d_ap, int64_t nq, double* map_out, int64_t* n_used, void* stream);
+
+/* End-to-end convenience with HOST buffers == MAPs(R).get_maps_by_feature(database, query)
+ * (lib/metric.py:12-24, call site main.py:164).  Copies features/labels H2D (pinned staging, chunked and
+ * overlapped with packing), ranks, copies the per-query AP back.  Device memory is taken from a cached
+ * per-process arena that grows on demand (freed by hg_release_cached()).  h_ap_out may be NULL.
+ * lab_elem_bytes: 8 / 4 / 1. */
+int hg_maps_by_feature_host(const float* h_db_feat, const void* h_db_lab, int64_t ndb,
+                            const float* h_q_feat, const void* h_q_lab, int64_t nq,
+                            int b, int L, int lab_elem_bytes, int64_t R, unsigned flags,
+                            double* map_out, double* h_ap_out);
+int hg_release_cached(void);
+
+/* Integer-pipe microbenchmark: measured XOR+POPC word-ops per second of this GPU (the binding roofline
+ * of the Hamming kernel).  Runs `iters` dependent-free popc chains on every SM. */
+int hg_popc_peak(double* wordops_per_s, double* ms, int iters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HASHGAN_B200_H */

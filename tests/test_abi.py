@@ -1,0 +1,66 @@
+"""CPU-side checks of the C-ABI library: it loads without a GPU, exports every symbol include/*.h declares,
+and its host-only pieces behave (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from hashgan_b200 import _native
+from tests import helpers
+
+
+def _declared_symbols():
+    text = open(os.path.join(helpers.ROOT, "include", "hashgan_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.lib()
+    names = _declared_symbols()
+    assert len(names) >= 12
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/hashgan_b200.h but not exported"
+        assert name in _native.SIGNATURES, f"{name} has no ctypes signature in hashgan_b200/_native.py"
+
+
+def test_version_and_word_counts():
+    lib = _native.lib()
+    assert lib.hg_version() >= 100
+    assert [lib.hg_code_words(b) for b in (1, 32, 33, 48, 64, 96, 128, 129, 256)] == [1, 1, 2, 2, 2, 3, 4, 8, 8]
+    assert lib.hg_code_words(0) == 0 and lib.hg_code_words(257) == 0
+    assert [lib.hg_label_words(L) for L in (1, 10, 32, 33, 81)] == [1, 1, 1, 2, 3]
+    with pytest.raises(ValueError):
+        _native.code_words(300)
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    lib = _native.lib()
+    assert lib.hg_hamming_map_workspace_bytes(10, 100, 64, 10, 101) == 0  # R > ndb
+    assert lib.hg_hamming_map_workspace_bytes(10, 100, 300, 10, 10) == 0  # unsupported b
+    assert lib.hg_hamming_map_workspace_bytes(10000, 1000000, 64, 10, 5000) > 0
+    rc = lib.hg_hamming_map(None, None, 4, None, None, 10, 64, 10, 11, 0, None, None, None, None, None, 0, None)
+    assert rc == _native.HG_ERANGE and b"exceeds" in lib.hg_last_error()
+    rc = lib.hg_pack_sign_f32(None, 4, 999, 999, None, None)
+    assert rc == _native.HG_EINVAL
+    with pytest.raises(_native.HgError):
+        _native.check(rc)
+
+
+def test_mean_matches_numpy_bitwise():
+    """hg_mean_ap_host restates lib/metric.py:24 (np.mean over the kept queries) including NumPy's pairwise sum."""
+    lib = _native.lib()
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 5, 8, 9, 100, 128, 129, 1000, 4097, 10000):
+        ap = rng.random(n)
+        ap[rng.random(n) < 0.1] = np.nan
+        out, used = C.c_double(), C.c_int64()
+        assert lib.hg_mean_ap_host(ap.ctypes.data, n, C.byref(out), C.byref(used)) == 0
+        kept = ap[~np.isnan(ap)]
+        assert used.value == kept.size
+        if kept.size == 0:
+            assert np.isnan(out.value)
+        else:
+            assert out.value == float(np.mean(kept)), n

@@ -1,0 +1,309 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle on a real B200.
+
+Bit-exact for everything integer (packed words, top-R database rows, Hamming distances, relevant counts);
+per-query AP and mAP within 1e-12 of the oracle (north_star tolerance: 1e-6).
+"""
+import ctypes as C
+import warnings
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+
+from oracle import maps_oracle
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+AP_TOL = 1e-12  # fp64 summation-order noise only; north_star allows 1e-6
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import torch
+
+    assert torch.cuda.is_available(), "the -m gpu tests need a CUDA device"
+    import hashgan_b200
+    from hashgan_b200 import _native
+
+    _native.lib()  # fails loudly when the extension is missing
+    return hashgan_b200
+
+
+def _check_against_c_oracle(hb, c_oracle, db, q, R, flags=0, ids=True, device=None):
+    m = hb.MAPs(R, flags=flags, device=device)
+    if ids:
+        ap, got_ids, got_dist = m.per_query_ap(db, q, want_ids=True)
+    else:
+        ap = m.per_query_ap(db, q)
+    ref_ap, ref_rel, ref_ids, ref_dist = c_oracle.hamming_map(db, q, R, want_ids=ids)
+    if ids:
+        assert np.array_equal(got_dist, ref_dist.astype(np.int32)), "Hamming distances of the top-R differ"
+        assert np.array_equal(got_ids, ref_ids.astype(np.int64)), "top-R database rows differ"
+    assert np.array_equal(np.isnan(ap), np.isnan(ref_ap))
+    keep = ~np.isnan(ap)
+    if keep.any():
+        assert np.max(np.abs(ap[keep] - ref_ap[keep])) <= AP_TOL
+    return ap, ref_ap
+
+
+# ---------------------------------------------------------------------------------------------------
+# packers
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("b", [1, 31, 32, 33, 48, 64, 96, 100, 128, 129, 200, 256])
+def test_pack_sign_bit_exact(hb, b):
+    from hashgan_b200 import _native
+
+    rng = np.random.default_rng(b)
+    for n in (1, 7, 1000, 4099):
+        feat = rng.normal(size=(n, b)).astype(np.float32)
+        feat[rng.random((n, b)) < 0.05] = 0.0  # zero is "not positive" -> bit 0
+        got = hb.pack_codes(feat).cpu().numpy().view(np.uint32)
+        want = maps_oracle.pack_sign_bits(feat)
+        W = _native.code_words(b)
+        assert got.shape == (n, W)
+        assert np.array_equal(got[:, : want.shape[1]], want)
+        assert not got[:, want.shape[1]:].any()  # pad words are zero
+
+
+@pytest.mark.parametrize("L,dtype", [(1, np.int64), (10, np.int64), (10, np.int32), (32, np.int8), (33, np.uint8), (81, np.int64), (80, bool)])
+def test_pack_labels_bit_exact(hb, L, dtype):
+    rng = np.random.default_rng(L)
+    for n in (1, 5, 1237):
+        lab = (rng.random((n, L)) < 0.2).astype(dtype)
+        got = hb.pack_labels(lab).cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, maps_oracle.pack_label_bits(lab.astype(np.int64)))
+
+
+def test_bad_labels_are_rejected(hb):
+    rng = np.random.default_rng(0)
+    db = NS(output=(rng.integers(0, 2, (300, 32)) * 2 - 1).astype(np.float32), label=rng.integers(0, 3, (300, 4)))
+    q = NS(output=(rng.integers(0, 2, (5, 32)) * 2 - 1).astype(np.float32), label=rng.integers(0, 2, (5, 4)))
+    with pytest.raises(ValueError):
+        hb.MAPs(10).get_maps_by_feature(db, q)
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden vectors made from the unmodified reference (oracle/gen_golden.py)
+# ---------------------------------------------------------------------------------------------------
+def _names():
+    import os
+    return helpers.golden_names(np.load(os.path.join(helpers.ROOT, "tests", "golden", "metric_golden.npz")))
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+@pytest.mark.parametrize("name", _names())
+def test_golden_vectors(hb, golden, name, flags):
+    c = helpers.golden_case(golden, name)
+    m = hb.MAPs(c.R, flags=flags)
+    ap = m.per_query_ap(c.db, c.q)
+    assert np.array_equal(np.isnan(ap), np.isnan(c.ap_eps))
+    keep = ~np.isnan(ap)
+    assert np.max(np.abs(ap[keep] - c.ap_eps[keep])) <= AP_TOL
+    got = m.get_maps_by_feature(c.db, c.q)
+    assert isinstance(got, np.float64)
+    assert abs(got - c.map_eps) <= AP_TOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configs against the C oracle (ids / distances bit-exact)
+# ---------------------------------------------------------------------------------------------------
+def test_c1_full_ranking_32bit(hb, c_oracle):
+    """configs[0] shape: 1k x 54k, 32-bit, R = DB_SIZE = 54000 -> the whole database is ranked."""
+    from hashgan_b200.synthetic import make_workload
+
+    wl, db, q = make_workload("C1")
+    ap, ref = _check_against_c_oracle(hb, c_oracle, db, q, wl.R)
+    assert abs(np.mean(ap) - np.mean(ref)) <= AP_TOL
+
+
+def test_c1_class_correlated_64bit(hb, c_oracle):
+    from hashgan_b200.synthetic import make_workload
+
+    wl, db, q = make_workload("C1_64", nq=256, correlated=0.25)
+    ap, ref = _check_against_c_oracle(hb, c_oracle, db, q, wl.R)
+    assert 0.3 < np.nanmean(ap) < 0.95  # far from chance (0.1): the ranking really uses the codes
+
+
+def test_c2_48bit_full(hb, c_oracle):
+    """configs[1]: 10k x 100k, 48-bit (16 pad bits), R=5000, bit-exact rank check."""
+    from hashgan_b200.synthetic import make_workload
+
+    wl, db, q = make_workload("C2")
+    m = hb.MAPs(wl.R)
+    ap, ids, dist = m.per_query_ap(db, q, want_ids=True)
+    ref_ap, _, ref_ids, ref_dist = c_oracle.hamming_map(db, q, wl.R, want_ids=True)
+    assert np.array_equal(dist, ref_dist.astype(np.int32))
+    assert np.array_equal(ids, ref_ids.astype(np.int64))
+    assert np.max(np.abs(ap - ref_ap)) <= AP_TOL
+    assert abs(m.get_maps_by_feature(db, q) - maps_oracle.exact_mean_ap(ref_ap)) <= AP_TOL
+
+
+@pytest.mark.parametrize("corr", [None, 0.2])
+def test_c4_query_subset_1m(hb, c_oracle, corr):
+    """configs[3] database (1M x 64-bit), 192 of its queries, ids/dist bit-exact vs the C oracle."""
+    from hashgan_b200.synthetic import make_workload
+
+    wl, db, q = make_workload("C4", nq=192, correlated=corr)
+    _check_against_c_oracle(hb, c_oracle, db, q, wl.R)
+
+
+def test_c5_query_subset_2m_multilabel(hb, c_oracle):
+    """configs[4] shape: 2M x 128-bit, 81-way multi-label, 96 queries."""
+    from hashgan_b200.synthetic import make_workload
+
+    wl, db, q = make_workload("C5", nq=96)
+    _check_against_c_oracle(hb, c_oracle, db, q, wl.R)
+
+
+# ---------------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("b", [8, 32, 40, 64, 96, 128, 160, 256])
+def test_hash_lengths(hb, c_oracle, b):
+    rng = np.random.default_rng(b)
+    ndb, nq, L = 30011, 77, 7
+    db = NS(output=(rng.integers(0, 2, (ndb, b)) * 2 - 1).astype(np.float32), label=np.eye(L, dtype=np.int64)[rng.integers(0, L, ndb)])
+    q = NS(output=(rng.integers(0, 2, (nq, b)) * 2 - 1).astype(np.float32), label=np.eye(L, dtype=np.int64)[rng.integers(0, L, nq)])
+    for R in (1, 100, 4097, ndb):
+        _check_against_c_oracle(hb, c_oracle, db, q, R)
+
+
+def test_all_codes_equal_forces_exact_path(hb, c_oracle):
+    """Adversarial: one distance bucket holds the whole database -> candidate bins overflow -> exact two-pass path."""
+    rng = np.random.default_rng(1)
+    ndb, nq, b, L = 200000, 130, 64, 10
+    one = (rng.integers(0, 2, (1, b)) * 2 - 1).astype(np.float32)
+    db = NS(output=np.repeat(one, ndb, 0), label=np.eye(L, dtype=np.int64)[rng.integers(0, L, ndb)])
+    q = NS(output=(rng.integers(0, 2, (nq, b)) * 2 - 1).astype(np.float32), label=np.eye(L, dtype=np.int64)[rng.integers(0, L, nq)])
+    for R in (1, 777, 50000):
+        _check_against_c_oracle(hb, c_oracle, db, q, R)
+
+
+def test_clustered_database_order(hb, c_oracle):
+    """Database sorted by class with class-correlated codes: candidates pile up in a few splits."""
+    from hashgan_b200.synthetic import make_workload
+
+    wl, db, q = make_workload("C4", nq=300, ndb=300000, correlated=0.15)
+    order = np.argsort(db.label.argmax(1), kind="stable")
+    db = NS(output=db.output[order], label=db.label[order])
+    _check_against_c_oracle(hb, c_oracle, db, q, 5000)
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+def test_force_exact_equals_fast(hb, c_oracle, flags):
+    from hashgan_b200.synthetic import make_workload
+
+    wl, db, q = make_workload("C2", nq=700, ndb=60000)
+    _check_against_c_oracle(hb, c_oracle, db, q, 2000, flags=flags)
+
+
+def test_small_and_ragged_sizes(hb, c_oracle):
+    rng = np.random.default_rng(9)
+    for nq, ndb, b, L, R in [(1, 1, 32, 3, 1), (3, 17, 64, 5, 17), (129, 1025, 48, 10, 300), (513, 2049, 64, 10, 2049),
+                             (1025, 5000, 32, 4, 1), (2, 70000, 128, 40, 35000)]:
+        db = NS(output=(rng.integers(0, 2, (ndb, b)) * 2 - 1).astype(np.float32), label=(rng.random((ndb, L)) < 0.3).astype(np.int64))
+        q = NS(output=(rng.integers(0, 2, (nq, b)) * 2 - 1).astype(np.float32), label=(rng.random((nq, L)) < 0.3).astype(np.int64))
+        _check_against_c_oracle(hb, c_oracle, db, q, R)
+
+
+def test_reference_error_and_nan_behaviour(hb):
+    rng = np.random.default_rng(2)
+    db = NS(output=(rng.integers(0, 2, (50, 32)) * 2 - 1).astype(np.float32), label=np.eye(4, dtype=np.int64)[rng.integers(0, 4, 50)])
+    q = NS(output=(rng.integers(0, 2, (4, 32)) * 2 - 1).astype(np.float32), label=np.eye(4, dtype=np.int64)[rng.integers(0, 4, 4)])
+    with pytest.raises(ValueError):  # R > Ndb: lib/metric.py:21 raises ValueError (broadcast)
+        hb.MAPs(51).get_maps_by_feature(db, q)
+    q0 = NS(output=q.output, label=np.zeros_like(q.label))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert np.isnan(hb.MAPs(10).get_maps_by_feature(db, q0))  # lib/metric.py:24: mean of an empty list
+        assert any(issubclass(x.category, RuntimeWarning) for x in w)
+    before = q.label.copy()
+    hb.MAPs(10).get_maps_by_feature(db, q)
+    assert np.array_equal(before, q.label)
+    with pytest.raises(ValueError):
+        hb.MAPs(10).get_maps_by_feature(NS(output=np.ones((50, 300), np.float32), label=db.label), NS(output=np.ones((4, 300), np.float32), label=q.label))
+
+
+def test_inputs_may_be_torch_cuda_tensors(hb, c_oracle):
+    import torch
+    from hashgan_b200.synthetic import make_workload
+
+    wl, db, q = make_workload("C2", nq=50, ndb=20000)
+    dev = torch.device("cuda:0")
+    dbt = NS(output=torch.from_numpy(db.output).to(dev), label=torch.from_numpy(db.label).to(dev))
+    qt = NS(output=torch.from_numpy(q.output).to(dev), label=torch.from_numpy(q.label).to(dev))
+    a = hb.MAPs(1000).per_query_ap(dbt, qt)
+    b_ = hb.MAPs(1000).per_query_ap(db, q)
+    assert np.array_equal(a, b_)
+
+
+def test_host_entry_point_matches_device_path(hb):
+    from hashgan_b200.synthetic import make_workload
+
+    wl, db, q = make_workload("C2", nq=300, ndb=50000)
+    m = hb.MAPs(1500)
+    val, ap = m.get_maps_by_feature_host(db, q, return_ap=True)
+    ap2 = m.per_query_ap(db, q)
+    assert np.array_equal(ap, ap2)
+    assert val == m.get_maps_by_feature(db, q)
+
+
+def test_query_chunking_is_invisible(hb):
+    """A tiny workspace limit forces several hg_hamming_map calls; per-query results must not change."""
+    from hashgan_b200.synthetic import make_workload
+
+    wl, db, q = make_workload("C2", nq=900, ndb=40000)
+    full = hb.MAPs(800).per_query_ap(db, q)
+    small = hb.MAPs(800, workspace_limit=40 << 20).per_query_ap(db, q)
+    assert np.array_equal(full, small)
+
+
+# ---------------------------------------------------------------------------------------------------
+# full BASELINE size: size-independent properties
+# ---------------------------------------------------------------------------------------------------
+def test_c4_full_size_properties(hb, c_oracle):
+    """configs[3] at full size (10k x 1M x 64-bit, R=5000): sortedness, tie rule, batch independence and a
+    sampled bit-exact check against the C oracle."""
+    import torch
+    from hashgan_b200.synthetic import make_workload
+    from hashgan_b200.metric import hamming_map_device, pack_codes, pack_labels
+
+    wl, db, q = make_workload("C4")
+    dbc, dbl = pack_codes(db.output), pack_labels(db.label)
+    qc, ql = pack_codes(q.output), pack_labels(q.label)
+    stats = {}
+    ap, ids, dist, rel = hamming_map_device(qc, ql, dbc, dbl, wl.b, wl.L, wl.R, want_ids=True, want_rel=True, stats=stats)
+    torch.cuda.synchronize()
+    ids64 = ids.to(torch.int64) & 0xFFFFFFFF
+    d32 = dist.to(torch.int32) & 0xFFFF
+    # (1) distances non-decreasing along the ranking; (2) inside one distance the rows ascend; rows are unique
+    dd = d32[:, 1:] - d32[:, :-1]
+    assert bool((dd >= 0).all())
+    same = dd == 0
+    assert bool((ids64[:, 1:][same] > ids64[:, :-1][same]).all())
+    # (3) recomputing the distance of every returned row from the packed codes gives the reported distance
+    sel = torch.arange(0, wl.nq, 97, device=ids.device)
+    rows = ids64[sel]
+    x = dbc[rows.reshape(-1)].reshape(len(sel), wl.R, -1) ^ qc[sel][:, None, :]
+    pop = torch.zeros(x.shape[:2], dtype=torch.int32, device=x.device)
+    xi = x.to(torch.int64) & 0xFFFFFFFF
+    for k in range(32):
+        pop += ((xi >> k) & 1).sum(-1).to(torch.int32)
+    assert bool((pop == d32[sel]).all())
+    # (4) the answer of a query does not depend on which other queries share its launch
+    perm = torch.randperm(wl.nq, device=qc.device, generator=torch.Generator(device=qc.device).manual_seed(3))
+    ap_p, _, _, _ = hamming_map_device(qc[perm].contiguous(), ql[perm].contiguous(), dbc, dbl, wl.b, wl.L, wl.R)
+    assert bool((ap_p == ap[perm]).all())
+    # (5) sampled queries bit-exact against the C oracle
+    pick = np.arange(0, wl.nq, 157)
+    sub = NS(output=q.output[pick], label=q.label[pick])
+    ref_ap, ref_rel, ref_ids, ref_dist = c_oracle.hamming_map(db, sub, wl.R, want_ids=True)
+    tp = torch.from_numpy(pick).to(ids.device)
+    assert np.array_equal(ids64[tp].cpu().numpy(), ref_ids.astype(np.int64))
+    assert np.array_equal(d32[tp].cpu().numpy(), ref_dist.astype(np.int32))
+    assert np.array_equal(rel[tp].cpu().numpy().astype(np.int64), ref_rel)
+    assert np.max(np.abs(ap[tp].cpu().numpy() - ref_ap)) <= AP_TOL
+    # the sampled threshold should rarely miss on i.i.d. codes
+    assert stats["chunks"][0]["exact_queries"] <= wl.nq // 50
+    assert stats["chunks"][0]["exact_failures"] == 0
