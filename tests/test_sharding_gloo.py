@@ -1,0 +1,97 @@
+"""Host logic of the multi-GPU path (hashgan_b200/sharding.py) on CPU: world_size 2, gloo backend.
+The packers and the ranker are injected with the oracle (tests may use it as the checker); what is
+under test is the sharding / all-gather / AP-gather bookkeeping that the NCCL path shares."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests import helpers
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _make(ndb, nq, b, L, seed):
+    rng = np.random.default_rng(seed)
+    dbc = (rng.integers(0, 2, (ndb, b)) * 2 - 1).astype(np.float32)
+    qc = (rng.integers(0, 2, (nq, b)) * 2 - 1).astype(np.float32)
+    dl = np.eye(L, dtype=np.int64)[rng.integers(0, L, ndb)]
+    ql = np.eye(L, dtype=np.int64)[rng.integers(0, L, nq)]
+    return dbc, dl, qc, ql
+
+
+def _worker(rank, world, port, ndb, nq, b, L, R, seed, out_dir):
+    sys.path.insert(0, helpers.ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from types import SimpleNamespace as NS
+        from hashgan_b200.sharding import ShardedMAPs, row_shard
+        from oracle import maps_oracle
+
+        co = helpers.COracle()
+        dbc, dl, qc, ql = _make(ndb, nq, b, L, seed)
+        lo, hi = row_shard(ndb, rank, world)
+        qlo, qhi = row_shard(nq, rank, world)
+
+        def pack_codes(x):
+            return torch.from_numpy(maps_oracle.pack_sign_bits(np.asarray(x)).view(np.int32))
+
+        def pack_labels(x):
+            return torch.from_numpy(maps_oracle.pack_label_bits(np.asarray(x)).view(np.int32))
+
+        def rank_fn(q_codes, q_lab, db_codes, db_lab, b_, L_, R_):
+            qn, dn = q_codes.numpy().view(np.uint32), db_codes.numpy().view(np.uint32)
+            qln, dln = q_lab.numpy().view(np.uint32), db_lab.numpy().view(np.uint32)
+            ap = np.empty(len(qn), dtype=np.float64)
+            rc = co.lib.hgo_hamming_map(np.ascontiguousarray(qn).ctypes.data, np.ascontiguousarray(qln).ctypes.data, len(qn),
+                                        np.ascontiguousarray(dn).ctypes.data, np.ascontiguousarray(dln).ctypes.data, len(dn),
+                                        b_, L_, R_, ap.ctypes.data, None, None, None, 1)
+            assert rc == 0
+            return torch.from_numpy(ap)
+
+        m = ShardedMAPs(R, pack_codes=pack_codes, pack_labels=pack_labels, rank_fn=rank_fn)
+        ap = m.per_query_ap_device(NS(output=dbc[lo:hi], label=dl[lo:hi]), NS(output=qc[qlo:qhi], label=ql[qlo:qhi])).numpy()
+        val = m.get_maps_by_feature(NS(output=dbc[lo:hi], label=dl[lo:hi]), NS(output=qc[qlo:qhi], label=ql[qlo:qhi]))
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ap=ap, val=val, counts=np.array(m.last_counts))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ndb,nq", [(1000, 40), (1001, 37)])
+def test_two_rank_sharded_map_equals_single_process(tmp_path, c_oracle, ndb, nq):
+    from types import SimpleNamespace as NS
+
+    b, L, R, seed, world = 48, 6, 200, 5, 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, ndb, nq, b, L, R, seed, str(tmp_path)), nprocs=world, join=True)
+    dbc, dl, qc, ql = _make(ndb, nq, b, L, seed)
+    ref_ap, _, _, _ = c_oracle.hamming_map(NS(output=dbc, label=dl), NS(output=qc, label=ql), R)
+    outs = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    for o in outs:
+        assert np.array_equal(o["ap"], ref_ap, equal_nan=True)     # rank order == global query order
+        assert float(o["val"]) == float(np.mean(ref_ap[~np.isnan(ref_ap)]))
+        assert int(o["counts"].sum()) == ndb
+    assert float(outs[0]["val"]) == float(outs[1]["val"])
+
+
+def test_shard_bounds_cover_everything():
+    from hashgan_b200.sharding import shard_bounds
+
+    for n in (0, 1, 7, 8, 1000003):
+        for w in (1, 2, 3, 8):
+            bounds = shard_bounds(n, w)
+            assert bounds[0][0] == 0 and bounds[-1][1] == n
+            assert all(bounds[i][1] == bounds[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in bounds]
+            assert max(sizes) - min(sizes) <= 1
