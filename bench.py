@@ -167,7 +167,7 @@ def main():
     import torch.distributed as dist
 
     from hashgan_b200 import _native
-    from hashgan_b200.metric import MAPs, hamming_map_device, pack_codes, pack_labels
+    from hashgan_b200.metric import MAPs, hamming_map_device, pack_rows
     from hashgan_b200.sharding import ShardedMAPs, gather_rows, gather_vector, row_shard
     from hashgan_b200.synthetic import Workload, make_workload
 
@@ -201,14 +201,11 @@ def main():
     phase_acc = np.zeros(5)
 
     def step(timed: bool):
-        dbc_local, dbl_local = pack_codes(db_f, device), pack_labels(db_l, device)
-        qc, ql = pack_codes(q_f, device), pack_labels(q_l, device)
+        db_rows = pack_rows(db_f, db_l, device)
+        q_rows = pack_rows(q_f, q_l, device)
         if world > 1:
-            dbc, _ = gather_rows(dbc_local)
-            dbl, _ = gather_rows(dbl_local)
-        else:
-            dbc, dbl = dbc_local, dbl_local
-        ap_d, _, _, _ = hamming_map_device(qc, ql, dbc, dbl, wl.b, wl.L, wl.R, flags=timing_flag)
+            db_rows, _ = gather_rows(db_rows)  # the one exchange step: packed code + label words of every shard
+        ap_d, _, _, _ = hamming_map_device(q_rows, db_rows, wl.b, wl.L, wl.R, flags=timing_flag)
         ap_host.copy_(ap_d, non_blocking=True)
         stream.synchronize()
         if timed:

@@ -6,6 +6,6 @@ Public surface mirrors the reference for this path only:
     forward_all / evaluate                            main.py:151-164
 Everything numeric runs in libhashgan_b200.so (hand-written sm_100a CUDA behind include/hashgan_b200.h).
 """
-from .metric import MAPs, MAPs_CQ, hamming_map_device, pack_codes, pack_labels  # noqa: F401
+from .metric import MAPs, MAPs_CQ, hamming_map_device, pack_rows  # noqa: F401
 
 __version__ = "0.1.0"

@@ -26,10 +26,10 @@ SIGNATURES = {
     "hg_device_info": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), C.POINTER(_sz)]),
     "hg_code_words": (_int, [_int]),
     "hg_label_words": (_int, [_int]),
-    "hg_pack_sign_f32": (_int, [_vp, _i64, _int, _i64, _vp, _vp]),
-    "hg_pack_labels": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp]),
+    "hg_row_words": (_int, [_int, _int]),
+    "hg_pack_rows": (_int, [_vp, _i64, _vp, _int, _i64, _int, _int, _vp, _vp, _vp]),
     "hg_hamming_map_workspace_bytes": (_sz, [_i64, _i64, _int, _int, _i64]),
-    "hg_hamming_map": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hg_hamming_map": (_int, [_vp, _i64, _vp, _i64, _int, _int, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hg_hamming_map_stats": (_int, [_vp, _sz, _i64, _i64, _int, _int, _i64, C.POINTER(_i64), _vp]),
     "hg_hamming_map_phase_ms": (_int, [C.POINTER(C.c_float)]),
     "hg_launch_count": (_i64, [_int]),
@@ -93,5 +93,11 @@ def code_words(b: int) -> int:
 def label_words(L: int) -> int:
     w = lib().hg_label_words(int(L))
     if w == 0:
-        raise ValueError(f"label width L={L} is not supported")
+        raise ValueError(f"label width L={L} is not supported (1..128)")
     return w
+
+
+def row_words(b: int, L: int) -> int:
+    code_words(b)
+    label_words(L)
+    return lib().hg_row_words(int(b), int(L))

@@ -259,7 +259,7 @@ extern "C" int hg_maps_by_feature_host(const float* h_db_feat, const void* h_db_
     if (R <= 0) return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: R must be positive");
     if (R > ndb) return hg::fail(HG_ERANGE, "hg_maps_by_feature_host: R=%lld exceeds the database size %lld", (long long)R, (long long)ndb);
     if (nq == 0) { *map_out = std::nan(""); return HG_OK; }
-    const int W = hg_code_words(b), LW = hg_label_words(L);
+    const int W = hg_code_words(b), LW = hg_label_words(L), Wr = hg_row_words(b, L);
     if (W == 0) return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: unsupported hash length b=%d", b);
     if (LW == 0) return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: unsupported label width L=%d", L);
     if (lab_elem_bytes != 8 && lab_elem_bytes != 4 && lab_elem_bytes != 1)
@@ -276,10 +276,8 @@ extern "C" int hg_maps_by_feature_host(const float* h_db_feat, const void* h_db_
     const size_t o_qf = take(sizeof(float) * (size_t)nq * b);
     const size_t o_dbl = take((size_t)lab_elem_bytes * ndb * L);
     const size_t o_ql = take((size_t)lab_elem_bytes * nq * L);
-    const size_t o_dbc = take(sizeof(uint32_t) * (size_t)ndb * W);
-    const size_t o_qc = take(sizeof(uint32_t) * (size_t)nq * W);
-    const size_t o_dblp = take(sizeof(uint32_t) * (size_t)ndb * LW);
-    const size_t o_qlp = take(sizeof(uint32_t) * (size_t)nq * LW);
+    const size_t o_dbr = take(sizeof(uint32_t) * (size_t)ndb * Wr);
+    const size_t o_qr = take(sizeof(uint32_t) * (size_t)nq * Wr);
     const size_t o_ap = take(sizeof(double) * (size_t)nq);
     const size_t o_bad = take(256);
     const size_t o_ws = take(ws_bytes);
@@ -289,31 +287,19 @@ extern "C" int hg_maps_by_feature_host(const float* h_db_feat, const void* h_db_
     cudaStream_t st = a.stream;
     float* d_dbf = reinterpret_cast<float*>(base + o_dbf);
     float* d_qf = reinterpret_cast<float*>(base + o_qf);
-    uint32_t* d_dbc = reinterpret_cast<uint32_t*>(base + o_dbc);
-    uint32_t* d_qc = reinterpret_cast<uint32_t*>(base + o_qc);
-    uint32_t* d_dblp = reinterpret_cast<uint32_t*>(base + o_dblp);
-    uint32_t* d_qlp = reinterpret_cast<uint32_t*>(base + o_qlp);
+    uint32_t* d_dbr = reinterpret_cast<uint32_t*>(base + o_dbr);
+    uint32_t* d_qr = reinterpret_cast<uint32_t*>(base + o_qr);
     double* d_ap = reinterpret_cast<double*>(base + o_ap);
     int* d_bad = reinterpret_cast<int*>(base + o_bad);
 
     HG_CUDA_TRY(cudaMemsetAsync(d_bad, 0, 256, st));
-    // queries first (small), then the database in row chunks so that packing overlaps the next copy
     HG_CUDA_TRY(cudaMemcpyAsync(d_qf, h_q_feat, sizeof(float) * (size_t)nq * b, cudaMemcpyHostToDevice, st));
     HG_CUDA_TRY(cudaMemcpyAsync(base + o_ql, h_q_lab, (size_t)lab_elem_bytes * nq * L, cudaMemcpyHostToDevice, st));
-    if ((rc = hg_pack_sign_f32(d_qf, nq, b, b, d_qc, st)) != HG_OK) return rc;
-    if ((rc = hg_pack_labels(base + o_ql, lab_elem_bytes, nq, L, d_qlp, d_bad, st)) != HG_OK) return rc;
-    const int64_t chunk = 1 << 18;
-    for (int64_t r0 = 0; r0 < ndb; r0 += chunk) {
-        const int64_t n = std::min<int64_t>(chunk, ndb - r0);
-        HG_CUDA_TRY(cudaMemcpyAsync(d_dbf + r0 * b, h_db_feat + r0 * b, sizeof(float) * (size_t)n * b, cudaMemcpyHostToDevice, st));
-        HG_CUDA_TRY(cudaMemcpyAsync(base + o_dbl + (size_t)r0 * L * lab_elem_bytes,
-                                    static_cast<const char*>(h_db_lab) + (size_t)r0 * L * lab_elem_bytes,
-                                    (size_t)lab_elem_bytes * n * L, cudaMemcpyHostToDevice, st));
-    }
-    if ((rc = hg_pack_sign_f32(d_dbf, ndb, b, b, d_dbc, st)) != HG_OK) return rc;
-    if ((rc = hg_pack_labels(base + o_dbl, lab_elem_bytes, ndb, L, d_dblp, d_bad, st)) != HG_OK) return rc;
-    if ((rc = hg_hamming_map(d_qc, d_qlp, nq, d_dbc, d_dblp, ndb, b, L, R, flags, d_ap, nullptr, nullptr, nullptr, base + o_ws,
-                             ws_bytes, st)) != HG_OK)
+    if ((rc = hg_pack_rows(d_qf, b, base + o_ql, lab_elem_bytes, nq, b, L, d_qr, d_bad, st)) != HG_OK) return rc;
+    HG_CUDA_TRY(cudaMemcpyAsync(d_dbf, h_db_feat, sizeof(float) * (size_t)ndb * b, cudaMemcpyHostToDevice, st));
+    HG_CUDA_TRY(cudaMemcpyAsync(base + o_dbl, h_db_lab, (size_t)lab_elem_bytes * ndb * L, cudaMemcpyHostToDevice, st));
+    if ((rc = hg_pack_rows(d_dbf, b, base + o_dbl, lab_elem_bytes, ndb, b, L, d_dbr, d_bad, st)) != HG_OK) return rc;
+    if ((rc = hg_hamming_map(d_qr, nq, d_dbr, ndb, b, L, R, flags, d_ap, nullptr, nullptr, nullptr, base + o_ws, ws_bytes, st)) != HG_OK)
         return rc;
     HG_CUDA_TRY(cudaMemcpyAsync(a.pinned_ap, d_ap, sizeof(double) * (size_t)nq, cudaMemcpyDeviceToHost, st));
     int* h_bad = reinterpret_cast<int*>(a.pinned_ap + nq);

@@ -1,9 +1,9 @@
-// sign + bit-pack of features, and 0/1 label matrices -> bit rows.  HBM-bound streaming kernels:
-// coalesced loads, one warp ballot per 32 elements, direct word stores (row length % 32 == 0) or
-// one atomicOr per row/word segment (ragged rows such as b = 48 or L = 10).
+// sign + bit-pack of features and 0/1 labels into PACKED ROWS:  [ W code words | LW label words | zero pad ]
+// (row stride hg_row_words(b, L) uint32).  HBM-bound streaming kernels: coalesced loads, one warp ballot per
+// 32 elements, direct word stores when a row of bits is word-aligned, else one atomicOr per word segment.
 //
-// Replaces (new stage, the reference ranks raw tanh outputs): main.py:155-157 -> lib/metric.py:13,
-// and the label gather/compare of lib/metric.py:17-19.
+// New stage relative to the reference, which ranks raw tanh outputs (main.py:155-157 -> lib/metric.py:13);
+// the label bits replace the per-query gather/compare of lib/metric.py:17-19.
 #include "common.cuh"
 
 namespace hg {
@@ -18,42 +18,40 @@ __device__ __forceinline__ bool to_bit(T v, int& any_bad)
     return v > (T)0;
 }
 
-// Dense case: rows are contiguous (ld == cols) and cols % 32 == 0 and the output row is exactly cols/32
-// words, so flat element e lands in flat word e/32.  Four independent 128-byte warp loads in flight.
-template <typename T, bool LABEL>
-__global__ void __launch_bounds__(256) pack_bits_dense_kernel(const T* __restrict__ in, int64_t total, uint32_t* __restrict__ out,
-                                                               int* __restrict__ bad)
+// Aligned features: cols % 32 == 0 and contiguous input rows (ld == cols), so 32 consecutive flat elements are
+// exactly one output word.  Four independent 128-byte warp loads in flight per warp.
+__global__ void __launch_bounds__(256) pack_sign_aligned_kernel(const float* __restrict__ in, int64_t total, int words_per_row,
+                                                                 uint32_t* __restrict__ out, int row_words)
 {
     constexpr int U = 4;
     const int lane = threadIdx.x & 31;
     const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    int any_bad = 0;
     for (int64_t base = warp_id * (32 * U); base < total; base += n_warps * (32 * U)) {
-        T v[U];
+        float v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t e = base + u * 32 + lane;
-            v[u] = (e < total) ? in[e] : (T)0;
+            v[u] = (e < total) ? __ldg(in + e) : 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t ballot = __ballot_sync(0xffffffffu, to_bit<T, LABEL>(v[u], any_bad));
+            const uint32_t ballot = __ballot_sync(0xffffffffu, v[u] > 0.0f);
             const int64_t e0 = base + u * 32;
-            if (lane == 0 && e0 < total) out[e0 >> 5] = ballot;
+            if (lane == 0 && e0 < total) {
+                const int64_t fw = e0 >> 5;
+                const int64_t row = fw / words_per_row;
+                out[row * row_words + (fw - row * words_per_row)] = ballot;
+            }
         }
-    }
-    if (LABEL && bad != nullptr) {
-        any_bad = __any_sync(0xffffffffu, any_bad);
-        if (any_bad && lane == 0) atomicOr(bad, 1);
     }
 }
 
-// General case (ragged rows, padded output rows or strided input).  One thread per element in flat
-// order; a run of bits that lives in one output word is written with one atomicOr by its first lane.
+// General case (ragged rows or strided input).  One thread per element in flat order; a run of bits that lives
+// in one output word is OR-ed in by its first lane.  The destination words must have been zeroed.
 template <typename T, bool LABEL>
-__global__ void __launch_bounds__(256) pack_bits_kernel(const T* __restrict__ in, int64_t n, int cols, int64_t ld, int wpr,
-                                                         uint32_t* __restrict__ out, int* __restrict__ bad)
+__global__ void __launch_bounds__(256) pack_bits_kernel(const T* __restrict__ in, int64_t n, int cols, int64_t ld,
+                                                         uint32_t* __restrict__ out, int row_words, int col0, int* __restrict__ bad)
 {
     const int lane = threadIdx.x & 31;
     const int64_t total = n * (int64_t)cols;
@@ -77,7 +75,7 @@ __global__ void __launch_bounds__(256) pack_bits_kernel(const T* __restrict__ in
             if (32 - lane < len) len = 32 - lane;
             const uint32_t mask = (len >= 32) ? 0xffffffffu : ((1u << len) - 1u);
             const uint32_t seg = (ballot >> lane) & mask;
-            if (seg) atomicOr(&out[row * wpr + (col >> 5)], seg << (col & 31));
+            if (seg) atomicOr(&out[row * row_words + col0 + (col >> 5)], seg << (col & 31));
         }
     }
     if (LABEL && bad != nullptr) {
@@ -86,25 +84,19 @@ __global__ void __launch_bounds__(256) pack_bits_kernel(const T* __restrict__ in
     }
 }
 
-template <typename T, bool LABEL>
-static int launch_pack(const void* in, int64_t n, int cols, int64_t ld, int wpr, uint32_t* out, int* bad, cudaStream_t st)
+static int64_t grid_for(int64_t warps_needed, int mult)
 {
-    if (n == 0) return HG_OK;
-    const int64_t total = n * (int64_t)cols;
-    const int threads = 256;
     const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
-    const int64_t max_blocks = (int64_t)sms * 8;  // 8 resident CTAs of 256 threads per SM
-    const bool dense = ((cols & 31) == 0) && (wpr * 32 == cols) && (ld == cols);
-    if (dense) {
-        int64_t blocks = ceil_div(ceil_div(total, 32 * 4), threads / 32);
-        if (blocks > max_blocks) blocks = max_blocks;
-        pack_bits_dense_kernel<T, LABEL><<<(unsigned)blocks, threads, 0, st>>>((const T*)in, total, out, bad);
-    } else {
-        HG_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(uint32_t) * (size_t)n * wpr, st));
-        int64_t blocks = ceil_div(ceil_div(total, 32), threads / 32);
-        if (blocks > max_blocks * 4) blocks = max_blocks * 4;
-        pack_bits_kernel<T, LABEL><<<(unsigned)blocks, threads, 0, st>>>((const T*)in, n, cols, ld, wpr, out, bad);
-    }
+    const int64_t max_blocks = (int64_t)sms * 8 * mult;  // 8 resident CTAs of 256 threads per SM
+    int64_t blocks = ceil_div(warps_needed, 8);
+    return blocks > max_blocks ? max_blocks : (blocks < 1 ? 1 : blocks);
+}
+
+template <typename T>
+static int launch_labels(const void* lab, int64_t n, int L, uint32_t* rows, int row_words, int col0, int* bad, cudaStream_t st)
+{
+    const int64_t total = n * (int64_t)L;
+    pack_bits_kernel<T, true><<<(unsigned)grid_for(ceil_div(total, 32), 4), 256, 0, st>>>((const T*)lab, n, L, L, rows, row_words, col0, bad);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     return HG_OK;
@@ -125,26 +117,39 @@ extern "C" int hg_label_words(int L)
     return (L + 31) / 32;
 }
 
-extern "C" int hg_pack_sign_f32(const float* d_feat, int64_t n, int b, int64_t ld, uint32_t* d_codes, void* stream)
+extern "C" int hg_row_words(int b, int L)
 {
-    const int wpr = hg_code_words(b);
-    if (wpr == 0) return hg::fail(HG_EINVAL, "hg_pack_sign_f32: unsupported hash length b=%d (1..%d)", b, HG_MAX_BITS);
-    if (n < 0 || ld < b) return hg::fail(HG_EINVAL, "hg_pack_sign_f32: bad n=%lld / ld=%lld", (long long)n, (long long)ld);
-    if (n > 0 && (!d_feat || !d_codes)) return hg::fail(HG_EINVAL, "hg_pack_sign_f32: NULL pointer");
-    return hg::launch_pack<float, false>(d_feat, n, b, ld, wpr, d_codes, nullptr, (cudaStream_t)stream);
+    const int W = hg_code_words(b), LW = hg_label_words(L);
+    if (W == 0 || LW == 0) return 0;
+    const int align = (W == 2) ? 2 : ((W == 4 || W == 8) ? 4 : 1);  // vector loads of the code words
+    return ((W + LW + align - 1) / align) * align;
 }
 
-extern "C" int hg_pack_labels(const void* d_lab, int elem_bytes, int64_t n, int L, uint32_t* d_packed, int* d_bad, void* stream)
+extern "C" int hg_pack_rows(const float* d_feat, int64_t ld, const void* d_lab, int lab_elem_bytes, int64_t n, int b, int L,
+                            uint32_t* d_rows, int* d_bad, void* stream)
 {
-    const int wpr = hg_label_words(L);
-    if (wpr == 0) return hg::fail(HG_EINVAL, "hg_pack_labels: unsupported label width L=%d", L);
-    if (n < 0) return hg::fail(HG_EINVAL, "hg_pack_labels: negative n");
-    if (n > 0 && (!d_lab || !d_packed)) return hg::fail(HG_EINVAL, "hg_pack_labels: NULL pointer");
+    const int W = hg_code_words(b), LW = hg_label_words(L), Wr = hg_row_words(b, L);
+    if (W == 0) return hg::fail(HG_EINVAL, "hg_pack_rows: unsupported hash length b=%d (1..%d)", b, HG_MAX_BITS);
+    if (LW == 0) return hg::fail(HG_EINVAL, "hg_pack_rows: unsupported label width L=%d (1..%d)", L, HG_MAX_LABELS);
+    if (n < 0 || ld < b) return hg::fail(HG_EINVAL, "hg_pack_rows: bad n=%lld / ld=%lld", (long long)n, (long long)ld);
+    if (n == 0) return HG_OK;
+    if (!d_feat || !d_rows) return hg::fail(HG_EINVAL, "hg_pack_rows: NULL pointer");
+    if (d_lab && lab_elem_bytes != 8 && lab_elem_bytes != 4 && lab_elem_bytes != 1)
+        return hg::fail(HG_EINVAL, "hg_pack_rows: lab_elem_bytes must be 8, 4 or 1 (got %d)", lab_elem_bytes);
     cudaStream_t st = (cudaStream_t)stream;
-    switch (elem_bytes) {
-        case 8: return hg::launch_pack<long long, true>(d_lab, n, L, L, wpr, d_packed, d_bad, st);
-        case 4: return hg::launch_pack<int, true>(d_lab, n, L, L, wpr, d_packed, d_bad, st);
-        case 1: return hg::launch_pack<signed char, true>(d_lab, n, L, L, wpr, d_packed, d_bad, st);
-        default: return hg::fail(HG_EINVAL, "hg_pack_labels: elem_bytes must be 8, 4 or 1 (got %d)", elem_bytes);
+    HG_CUDA_TRY(cudaMemsetAsync(d_rows, 0, sizeof(uint32_t) * (size_t)n * Wr, st));
+    const int64_t total = n * (int64_t)b;
+    if ((b & 31) == 0 && ld == b) {
+        hg::pack_sign_aligned_kernel<<<(unsigned)hg::grid_for(hg::ceil_div(total, 128), 1), 256, 0, st>>>(d_feat, total, b / 32, d_rows, Wr);
+    } else {
+        hg::pack_bits_kernel<float, false><<<(unsigned)hg::grid_for(hg::ceil_div(total, 32), 4), 256, 0, st>>>(d_feat, n, b, ld, d_rows, Wr, 0, nullptr);
+    }
+    hg::count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    if (!d_lab) return HG_OK;
+    switch (lab_elem_bytes) {
+        case 8: return hg::launch_labels<long long>(d_lab, n, L, d_rows, Wr, W, d_bad, st);
+        case 4: return hg::launch_labels<int>(d_lab, n, L, d_rows, Wr, W, d_bad, st);
+        default: return hg::launch_labels<signed char>(d_lab, n, L, d_rows, Wr, W, d_bad, st);
     }
 }

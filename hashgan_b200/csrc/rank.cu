@@ -9,11 +9,12 @@
 //   1. hist_kernel on a strided SAMPLE of the database -> per-query distance histogram.
 //   2. thr_kernel: per-query threshold T_q such that count(d <= T_q) >= R with high probability.
 //   3. select_kernel (the hot kernel): ONE pass over all pairs.  Thread <-> query (QT queries in
-//      registers), database tiles staged into shared memory by 1-D bulk TMA and read as warp broadcasts;
-//      per pair: W x (XOR, POPC), adds, one compare; pairs with d <= T_q (about R/Ndb of them) are appended to
-//      the thread's PRIVATE bin (query, db split) -> entries are in database-row order with no atomics.
-//   4. ap_kernel: one warp per query walks its bins in row order; per-distance running counters give
-//      every candidate its exact rank and relevant-prefix count -> AP in fp64; optional ids/dist output.
+//      registers), database tiles (packed rows: code words + label words) staged into shared memory by 1-D
+//      bulk TMA and read as warp broadcasts; per pair: W x (XOR, POPC), adds, one compare; pairs with
+//      d <= T_q (about R/Ndb of them) are appended, with their relevance bit, to the thread's PRIVATE bin
+//      (query, db split) -> entries are in database-row order with no atomics.
+//   4. ap_kernel: G threads per query walk its bins sequentially in row order; private per-distance running
+//      counters give every candidate its exact rank and relevant-prefix count -> AP in fp64; optional ids/dist.
 //   5. Exactness guard: a query whose candidate count fell short of R, or whose bin overflowed, is put on
 //      a fail list and redone by the two-pass exact path (full per-split histograms -> exact d*, exact bin
 //      offsets/quotas -> select_kernel<EXACT> -> ap_kernel).  All launches are unconditional and sized for
@@ -22,6 +23,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace hg {
 
@@ -30,41 +32,55 @@ namespace hg {
 // the launcher.
 // ================================================================================================
 struct Plan {
-    int b = 0, L = 0, W = 0, LW = 0, QT = 0, TQ = 0, TILE = 0, P = 0, nqt = 0;
+    int b = 0, L = 0, W = 0, LW = 0, Wr = 0, QT = 0, TQ = 0, TILE = 0, P = 0, nqt = 0;
     int64_t nq = 0, ndb = 0, R = 0, SL = 0;
     uint32_t cap = 0;
     // sample pass
     int64_t n_seg = 0, seg_stride = 0, sample_rows = 0;
     int seg_per_chunk = 0, n_chunks = 0;
     // workspace byte offsets
-    size_t off_ctrl = 0, off_thr = 0, off_thr2 = 0, off_fail = 0, off_hist_s = 0, off_bin_cnt = 0, off_bin_cnt2 = 0,
+    size_t off_ctrl = 0, off_thr = 0, off_thr2 = 0, off_fail = 0, off_wide = 0, off_hist_s = 0, off_bin_cnt = 0, off_bin_cnt2 = 0,
            off_bin_off2 = 0, off_bin_cap2 = 0, off_quota2 = 0, off_hist2 = 0, off_lists = 0, total = 0;
     bool ok = false;
 };
 
 constexpr int kSelectThreads = 128;
+constexpr int kSelectCtasPerSm = 16;
 constexpr int kHistThreads = 128;
-constexpr int kApWarps = 8;
+constexpr int kApWarps = 8;  // exact_plan_kernel: warps per CTA
 constexpr int64_t kSampleTarget = 16384;
 constexpr float kSampleZ = 4.0f;
 
-static int tile_rows_for(int W) { return W == 1 ? 2048 : (W == 2 ? 1024 : (W <= 4 ? 512 : 256)); }
+// rows per shared-memory tile: about 8 KB per pipeline stage
+static int tile_rows_for(int Wr) { return Wr <= 2 ? 1024 : (Wr <= 4 ? 512 : (Wr <= 8 ? 256 : 128)); }
+
+static int env_int(const char* name, int fallback)
+{
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : fallback;
+}
 
 static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R)
 {
     Plan p;
     p.W = hg_code_words(b);
     p.LW = hg_label_words(L);
+    p.Wr = hg_row_words(b, L);
     if (p.W == 0 || p.LW == 0 || nq <= 0 || ndb <= 0 || R <= 0 || R > ndb || ndb >= (int64_t(1) << 31) || nq >= (int64_t(1) << 31))
         return p;
     p.b = b; p.L = L; p.nq = nq; p.ndb = ndb; p.R = R;
     const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
-    p.QT = nq >= 4096 ? 4 : (nq >= 1024 ? 2 : 1);
+    p.QT = nq >= 1024 ? 2 : 1;  // measured on B200 (C4): QT=2 with ~16 CTAs/SM beats QT=4 (scripts/tune_select.py)
+    {
+        const int qt = env_int("HG_SELECT_QT", 0);  // tuning override
+        if (qt == 1 || qt == 2 || qt == 4) p.QT = qt;
+    }
     p.TQ = kSelectThreads * p.QT;
     p.nqt = (int)ceil_div(nq, p.TQ);
-    p.TILE = tile_rows_for(p.W);
-    // db splits: enough CTAs for ~8 per SM, split length a multiple of the tile, at most 2^21 rows
-    const int64_t target_ctas = (int64_t)sms * 8;
+    p.TILE = tile_rows_for(p.Wr);
+    // db splits: one wave of CTAs that are all resident (grid ~ SMs x CTAs/SM), split length a multiple of the
+    // tile, at most 2^21 rows
+    const int64_t target_ctas = (int64_t)sms * env_int("HG_SELECT_CTAS_PER_SM", kSelectCtasPerSm);
     int64_t P0 = std::max<int64_t>(1, ceil_div(target_ctas, p.nqt));
     int64_t SL = round_up(ceil_div(ndb, P0), p.TILE);
     SL = std::min<int64_t>(SL, kMaxSplitRows);
@@ -78,6 +94,8 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R)
     cap = std::min<int64_t>(cap, SL);
     while (cap * p.P < R) cap += 8;  // the exact path reuses the list area and needs R entries per query
     p.cap = (uint32_t)cap;
+    if ((double)nq * p.P * (double)cap >= 4294967295.0 || (double)nq * (double)R >= 4294967295.0)
+        return p;  // bins are addressed with 32-bit word offsets: the caller must split the query batch
     // sample: kSampleTarget rows in TILE-row segments spread evenly; the whole db when it is small
     const int64_t tiles_total = ceil_div(ndb, p.TILE);
     int64_t want_seg = std::max<int64_t>(1, kSampleTarget / p.TILE);
@@ -104,6 +122,7 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R)
     p.off_thr = take(sizeof(int) * nq);
     p.off_thr2 = take(sizeof(int) * nq);
     p.off_fail = take(sizeof(int) * nq);
+    p.off_wide = take(sizeof(int) * nq);
     p.off_hist_s = take(sizeof(uint32_t) * (size_t)nq * (b + 1));
     p.off_bin_cnt = take(sizeof(uint32_t) * bins);
     p.off_bin_cnt2 = take(sizeof(uint32_t) * bins);
@@ -120,25 +139,26 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R)
 // ================================================================================================
 // Device helpers
 // ================================================================================================
+// code words of one packed row (row = pointer to its first word; alignment guaranteed by hg_row_words)
 template <int W>
-__device__ __forceinline__ void load_code(const uint32_t* __restrict__ s, int j, uint32_t (&v)[W])
+__device__ __forceinline__ void load_code(const uint32_t* __restrict__ row, uint32_t (&v)[W])
 {
     if constexpr (W == 1) {
-        v[0] = s[j];
+        v[0] = row[0];
     } else if constexpr (W == 2) {
-        const uint2 t = reinterpret_cast<const uint2*>(s)[j];
+        const uint2 t = *reinterpret_cast<const uint2*>(row);
         v[0] = t.x; v[1] = t.y;
     } else if constexpr (W == 4) {
-        const uint4 t = reinterpret_cast<const uint4*>(s)[j];
+        const uint4 t = *reinterpret_cast<const uint4*>(row);
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     } else if constexpr (W == 8) {
-        const uint4 t0 = reinterpret_cast<const uint4*>(s)[2 * j];
-        const uint4 t1 = reinterpret_cast<const uint4*>(s)[2 * j + 1];
+        const uint4 t0 = reinterpret_cast<const uint4*>(row)[0];
+        const uint4 t1 = reinterpret_cast<const uint4*>(row)[1];
         v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w;
         v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
     } else {
 #pragma unroll
-        for (int w = 0; w < W; ++w) v[w] = s[j * W + w];
+        for (int w = 0; w < W; ++w) v[w] = row[w];
     }
 }
 
@@ -156,10 +176,10 @@ __device__ __forceinline__ int hamming(const uint32_t (&a)[W], const uint32_t (&
 //    column of shared memory (bank = thread), so updates need no atomics.
 // ================================================================================================
 struct HistParams {
-    const uint32_t* q_codes;
-    const uint32_t* db_codes;
+    const uint32_t* q_rows;
+    const uint32_t* db_rows;
     int64_t nq, ndb;
-    int b;
+    int b, Wr;
     const int* n_active;  // indirect mode (exact path): number of listed queries
     const int* qlist;     // indirect mode: query ids
     int64_t seg_stride, n_seg;
@@ -173,8 +193,9 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(HistParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const int nbins = p.b + 1;
-    uint32_t* h = smem;                             // [nbins][kHistThreads]
-    uint32_t* tile = smem + nbins * kHistThreads;   // [seg_rows * W]
+    const int Wr = p.Wr;
+    uint32_t* tile = smem;                              // [seg_rows * Wr], 16-byte aligned
+    uint32_t* h = smem + (size_t)p.seg_rows * Wr;       // [nbins][kHistThreads]
     const int tid = threadIdx.x;
     const int64_t n_act = p.qlist ? (int64_t)*p.n_active : p.nq;
     const int64_t slot0 = (int64_t)blockIdx.x * kHistThreads;
@@ -184,7 +205,7 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(HistParams p)
     const int64_t q = valid ? (p.qlist ? (int64_t)p.qlist[slot] : slot) : 0;
     uint32_t qw[W];
 #pragma unroll
-    for (int w = 0; w < W; ++w) qw[w] = valid ? p.q_codes[q * W + w] : 0u;
+    for (int w = 0; w < W; ++w) qw[w] = valid ? p.q_rows[q * Wr + w] : 0u;
     for (int i = tid; i < nbins * kHistThreads; i += kHistThreads) h[i] = 0;
     const int chunk = blockIdx.y;
     for (int g = 0; g < p.seg_per_chunk; ++g) {
@@ -194,13 +215,16 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(HistParams p)
         if (row0 >= p.ndb) break;
         const int rows = (int)min((int64_t)p.seg_rows, p.ndb - row0);
         __syncthreads();  // previous tile fully consumed (and h zeroed on the first trip)
-        const uint32_t* src = p.db_codes + row0 * W;
-        for (int i = tid; i < rows * W; i += kHistThreads) tile[i] = __ldg(src + i);
+        const uint4* src = reinterpret_cast<const uint4*>(p.db_rows + row0 * Wr);  // row0 is a tile multiple: 16-byte aligned
+        const int n16 = (rows * Wr) >> 2;
+        for (int i = tid; i < n16; i += kHistThreads) reinterpret_cast<uint4*>(tile)[i] = __ldg(src + i);
+        for (int i = (n16 << 2) + tid; i < rows * Wr; i += kHistThreads) tile[i] = __ldg(p.db_rows + row0 * Wr + i);
         __syncthreads();
         if (valid) {
+#pragma unroll 4
             for (int j = 0; j < rows; ++j) {
                 uint32_t v[W];
-                load_code<W>(tile, j, v);
+                load_code<W>(tile + j * Wr, v);
                 const int d = hamming<W>(qw, v);
                 h[d * kHistThreads + tid] += 1;
             }
@@ -249,13 +273,13 @@ __global__ void thr_kernel(const uint32_t* __restrict__ hist_s, int64_t nq, int 
 // 3. The hot kernel: all-pairs XOR/POPC + threshold select into private, row-ordered bins.
 // ================================================================================================
 struct SelectParams {
-    const uint32_t* q_codes;
-    const uint32_t* db_codes;
+    const uint32_t* q_rows;
+    const uint32_t* db_rows;
     int64_t nq, ndb;
     const int* thr;       // [nq] by query id
     const int* n_active;  // EXACT: fail count
     const int* qlist;     // EXACT: fail list
-    int P;
+    int P, Wr, LW, TILE;
     int64_t SL, R;
     uint32_t* lists;
     uint32_t cap;              // fast path: bin = q*P + s at lists + bin*cap
@@ -265,19 +289,49 @@ struct SelectParams {
     uint32_t* bin_cnt;  // out: candidates seen per bin (may exceed the capacity -> overflow)
 };
 
-template <int W, int QT, bool EXACT>
+// row stride when the label fits one word (the common case: L <= 32) -- a compile-time constant so that a whole
+// packed row (code words + label word) is fetched with the widest shared-memory loads
+template <int W> struct RowLW1 { static constexpr int Wr = (W == 1 ? 2 : (W == 2 ? 4 : (W == 3 ? 4 : (W == 4 ? 8 : 12)))); };
+
+// code words + first label word of one packed row in shared memory
+template <int W>
+__device__ __forceinline__ void load_row_lw1(const uint32_t* __restrict__ row, uint32_t (&v)[W], uint32_t& lab)
+{
+    if constexpr (W == 1) {
+        const uint2 t = *reinterpret_cast<const uint2*>(row);
+        v[0] = t.x; lab = t.y;
+    } else if constexpr (W == 2) {
+        const uint4 t = *reinterpret_cast<const uint4*>(row);
+        v[0] = t.x; v[1] = t.y; lab = t.z;
+    } else if constexpr (W == 3) {
+        const uint4 t = *reinterpret_cast<const uint4*>(row);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; lab = t.w;
+    } else {
+        load_code<W>(row, v);
+        lab = row[W];
+    }
+}
+
+// LW1 = true : L <= 32, row stride RowLW1<W>::Wr, the relevance bit costs one AND on registers in the rare path
+// LW1 = false: any label width, runtime row stride, label words read from the tile in the rare path
+template <int W, int QT, bool EXACT, bool LW1>
 __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams p)
 {
     constexpr int NT = kSelectThreads;
-    constexpr int TILE = (W == 1 ? 2048 : (W == 2 ? 1024 : (W <= 4 ? 512 : 256)));
+    constexpr int TQ = NT * QT;
     constexpr int U = (W <= 2 ? 4 : 2);
-    __shared__ __align__(128) uint32_t s_tile[2][TILE * W];
+    extern __shared__ __align__(128) uint32_t smem[];
     __shared__ __align__(8) uint64_t s_full[2];
+    const int Wr = LW1 ? RowLW1<W>::Wr : p.Wr;
+    const int LW = LW1 ? 1 : p.LW;
+    const int TILE = p.TILE;
+    const int tile_words = TILE * Wr;          // smem: [2][tile_words] database tiles, then (generic labels) [LW][TQ]
+    uint32_t* s_qlab = smem + 2 * tile_words;  // only used when !LW1
 
     const int tid = threadIdx.x;
     const int split = blockIdx.y;
     const int64_t n_act = EXACT ? (int64_t)*p.n_active : p.nq;
-    const int64_t slot0 = (int64_t)blockIdx.x * (NT * QT);
+    const int64_t slot0 = (int64_t)blockIdx.x * TQ;
     if (slot0 >= n_act) return;
 
     const int64_t row0 = (int64_t)split * p.SL;
@@ -285,11 +339,13 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams p)
     const int64_t nrows = row1 > row0 ? row1 - row0 : 0;
     const int ntiles = (int)((nrows + TILE - 1) / TILE);
 
+    // per-query state: code words, label word, threshold, and the private bin as 32-bit word offsets into p.lists
+    // (make_plan keeps the whole list area below 2^32 entries): pos counts every candidate seen, stores stop at end.
     uint32_t qw[QT][W];
+    uint32_t qlab[QT];
     int T[QT];
-    uint32_t cnt[QT], capk[QT];
+    uint32_t pos[QT], start[QT], end[QT];
     uint32_t neq[QT], quota[QT];
-    uint32_t* lp[QT];
     int64_t bin[QT];
 #pragma unroll
     for (int k = 0; k < QT; ++k) {
@@ -297,20 +353,25 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams p)
         const bool valid = slot < n_act;
         const int64_t q = valid ? (EXACT ? (int64_t)p.qlist[slot] : slot) : 0;
 #pragma unroll
-        for (int w = 0; w < W; ++w) qw[k][w] = valid ? p.q_codes[q * W + w] : 0u;
+        for (int w = 0; w < W; ++w) qw[k][w] = valid ? p.q_rows[q * Wr + w] : 0u;
+        qlab[k] = valid ? p.q_rows[q * Wr + W] : 0u;
+        if (!LW1)
+            for (int w = 0; w < LW; ++w) s_qlab[w * TQ + k * NT + tid] = valid ? p.q_rows[q * Wr + W + w] : 0u;
         T[k] = valid ? p.thr[q] : -1;
         bin[k] = valid ? slot * p.P + split : -1;
-        cnt[k] = 0; neq[k] = 0;
+        neq[k] = 0;
         if (EXACT) {
-            capk[k] = valid ? p.bin_cap2[bin[k]] : 0u;
+            start[k] = valid ? (uint32_t)(slot * p.R + (int64_t)p.bin_off2[bin[k]]) : 0u;
+            end[k] = start[k] + (valid ? p.bin_cap2[bin[k]] : 0u);
             quota[k] = valid ? p.quota2[bin[k]] : 0u;
-            lp[k] = p.lists + (valid ? slot * p.R + (int64_t)p.bin_off2[bin[k]] : 0);
         } else {
-            capk[k] = p.cap;
+            start[k] = valid ? (uint32_t)(bin[k] * (int64_t)p.cap) : 0u;
+            end[k] = start[k] + (valid ? p.cap : 0u);
             quota[k] = 0xffffffffu;
-            lp[k] = p.lists + (valid ? bin[k] * (int64_t)p.cap : 0);
         }
+        pos[k] = start[k];
     }
+    uint32_t* const lists = p.lists;
 
     if (tid == 0) {
         mbar_init(&s_full[0], 1);
@@ -319,19 +380,21 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams p)
     }
     __syncthreads();
 
-    const uint32_t* src0 = p.db_codes + row0 * W;
+    const uint32_t* src0 = p.db_rows + row0 * Wr;
+    const uint32_t tile_bytes = (uint32_t)tile_words * 4;
     auto tile_rows = [&](int t) -> int { return (int)min((int64_t)TILE, nrows - (int64_t)t * TILE); };
     auto issue = [&](int t) {
         const int buf = t & 1;
         const int rows = tile_rows(t);
-        const uint32_t* src = src0 + (int64_t)t * TILE * W;
+        const uint32_t* src = src0 + (int64_t)t * tile_words;
         if (rows == TILE) {
             if (tid == 0) {
-                mbar_arrive_expect_tx(&s_full[buf], TILE * W * 4);
-                tma_load_1d(&s_tile[buf][0], src, TILE * W * 4, &s_full[buf]);
+                mbar_arrive_expect_tx(&s_full[buf], tile_bytes);
+                tma_load_1d(smem + buf * tile_words, src, tile_bytes, &s_full[buf]);
             }
         } else {
-            for (int i = tid; i < rows * W; i += NT) s_tile[buf][i] = __ldg(src + i);
+            uint32_t* dst = smem + buf * tile_words;
+            for (int i = tid; i < rows * Wr; i += NT) dst[i] = __ldg(src + i);
         }
     };
     if (ntiles > 0) issue(0);
@@ -342,111 +405,149 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams p)
         const int buf = t & 1;
         const int rows = tile_rows(t);
         if (rows == TILE) mbar_wait(&s_full[buf], (uint32_t)((t >> 1) & 1));
-        const uint32_t* tile = &s_tile[buf][0];
+        const uint32_t* tile = smem + buf * tile_words;
         const uint32_t lbase = (uint32_t)t * TILE;
 
-        auto pair = [&](int k, const uint32_t (&v)[W], uint32_t lidx) {
-            const int d = hamming<W>(qw[k], v);
-            if (d <= T[k]) {
-                bool ok = true;
-                if (EXACT) {
-                    if (d == T[k]) { ok = neq[k] < quota[k]; neq[k]++; }
+        // rare path (about R/Ndb of the pairs): append (relevance, distance, row) to this thread's private bin
+        auto emit = [&](int k, int d, uint32_t lab, const uint32_t* row, uint32_t lidx) {
+            bool ok = true;
+            if (EXACT) {
+                if (d == T[k]) { ok = neq[k] < quota[k]; neq[k]++; }
+            }
+            if (ok) {
+                const uint32_t at = pos[k];
+                if (at < end[k]) {
+                    uint32_t m = lab & qlab[k];
+                    if (!LW1) {
+#pragma unroll 1
+                        for (int w = 1; w < LW; ++w) m |= row[W + w] & s_qlab[w * TQ + k * NT + tid];
+                    }
+                    lists[at] = ((uint32_t)d * (1u << kIdxBits) + lidx) | (m ? 0x80000000u : 0u);
                 }
-                if (ok) {
-                    const uint32_t c = cnt[k];
-                    if (c < capk[k]) lp[k][c] = ((uint32_t)d << kIdxBits) | lidx;
-                    cnt[k] = c + 1;
-                }
+                pos[k] = at + 1;
             }
         };
 
         int j = 0;
         for (; j + U <= rows; j += U) {
-            uint32_t v[U][W];
+            uint32_t v[U][W], lab[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) load_code<W>(tile, j + u, v[u]);
+            for (int u = 0; u < U; ++u) {
+                if (LW1) load_row_lw1<W>(tile + (j + u) * Wr, v[u], lab[u]);
+                else { load_code<W>(tile + (j + u) * Wr, v[u]); lab[u] = 0; }
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
 #pragma unroll
-                for (int k = 0; k < QT; ++k) pair(k, v[u], lbase + j + u);
+                for (int k = 0; k < QT; ++k) {
+                    const int d = hamming<W>(qw[k], v[u]);
+                    if (d <= T[k]) {
+                        const uint32_t* row = tile + (j + u) * Wr;
+                        emit(k, d, LW1 ? lab[u] : row[W], row, lbase + j + u);
+                    }
+                }
             }
         }
         for (; j < rows; ++j) {
+            const uint32_t* row = tile + j * Wr;
             uint32_t v[W];
-            load_code<W>(tile, j, v);
+            load_code<W>(row, v);
 #pragma unroll
-            for (int k = 0; k < QT; ++k) pair(k, v, lbase + j);
+            for (int k = 0; k < QT; ++k) {
+                const int d = hamming<W>(qw[k], v);
+                if (d <= T[k]) emit(k, d, row[W], row, lbase + j);
+            }
         }
-        __syncthreads();  // everyone is done with s_tile[buf]
+        __syncthreads();  // everyone is done with this buffer
         if (t + 2 < ntiles) issue(t + 2);
         // a ragged tile (only ever the last one) is ordered by the __syncthreads of the next trip
     }
 
 #pragma unroll
     for (int k = 0; k < QT; ++k)
-        if (bin[k] >= 0) p.bin_cnt[bin[k]] = cnt[k];
+        if (bin[k] >= 0) p.bin_cnt[bin[k]] = pos[k] - start[k];
 }
 
 // ================================================================================================
-// 4. AP kernel: one warp per query.
+// 4. AP kernel.  G threads per query, each walks a contiguous range of the query's bins SEQUENTIALLY (bins and
+//    entries are in database-row order).  Per-thread private counters per distance (a shared-memory column per
+//    thread, bank == thread: no atomics, no conflicts):
+//      phase A  count entries / relevant entries per distance in my range;
+//      phase A2 per distance: exclusive scan over the G threads of the query + running totals over distances
+//               -> my counters now hold "rank before my first entry of that distance" (N_d + earlier ranges);
+//      phase B  walk again: rank = ++N[d], cum = (M[d] += relevant); an entry is in the top-R iff rank <= R;
+//               relevant entries add cum / rank (fp64); optional ids / dist output at position rank-1.
+//    WINDOW = true : 32 counters per thread indexed by (distance & 31) -- exact whenever the candidate distances of
+//               a query span fewer than 32 values (always, on hash codes: the top-R tail of a binomial is a few
+//               sigma wide); 256 B of shared memory per thread -> 6 CTAs per SM.  Queries with a wider span are
+//               put on the wide list and redone by the WINDOW = false variant (b+1 counters per thread).
 // ================================================================================================
 struct ApParams {
     int64_t nq;
-    const int* n_active;
-    const int* qlist;  // indirect (exact path) when non-null
-    int P, b, LW;
+    const int* n_active;  // indirect modes: number of listed queries
+    const int* qlist;     // indirect modes: query ids (wide list or fail list)
+    int bins_by_slot;     // exact path: bins/offsets are indexed by the position in qlist, not by the query id
+    int P, b, G;
     int64_t SL, R;
-    uint32_t* lists;
+    const uint32_t* lists;
     uint32_t cap;
     const uint32_t* bin_off2;  // exact path
     const uint32_t* bin_cap2;  // exact path
     const uint32_t* bin_cnt;
     const int* thr;
-    const uint32_t* q_lab;
-    const uint32_t* db_lab;
     double* ap;
     uint32_t* ids;
     uint16_t* dist;
     int32_t* rel;
-    int* fail_list;  // fast path: queries to redo exactly
+    int* fail_list;  // queries to redo exactly (fast path only)
     int* n_fail;
+    int* wide_list;  // queries whose distance span does not fit the window (WINDOW only)
+    int* n_wide;
     int no_fallback;
 };
 
-__global__ void __launch_bounds__(kApWarps * 32) ap_kernel(ApParams p)
+template <bool WINDOW>
+__global__ void __launch_bounds__(128) ap_kernel(ApParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NTB = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int nb = p.b + 1;
-    uint32_t* A = smem + (size_t)warp * 4 * nb;  // count per distance -> exclusive prefix N[d]
-    uint32_t* B = A + nb;                        // relevant count per distance -> exclusive prefix M[d]
-    uint32_t* C = B + nb;                        // running count per distance (walk 2)
-    uint32_t* D = C + nb;                        // running relevant count per distance (walk 2)
-    const bool exact = p.qlist != nullptr;
-    const int64_t n_act = exact ? (int64_t)*p.n_active : p.nq;
-    const int64_t slot = (int64_t)blockIdx.x * kApWarps + warp;
-    if (slot >= n_act) return;
-    const int64_t q = exact ? (int64_t)p.qlist[slot] : slot;
-    const int64_t binbase = slot * p.P;
-    const int T = p.thr[q];
+    const int ncol = WINDOW ? 32 : nb;               // counters per thread and kind
+    uint32_t* cN = smem + tid;                        // cN[c * NTB]: count per distance  -> rank base
+    uint32_t* cM = smem + (size_t)ncol * NTB + tid;   // cM[c * NTB]: relevant per distance -> relevant base
+    const int G = p.G;
+    const bool exact = p.bins_by_slot != 0;
+    const int64_t n_act = p.qlist ? (int64_t)*p.n_active : p.nq;
+    const int64_t slot = ((int64_t)blockIdx.x * NTB + tid) / G;
+    const int g = tid % G;  // groups are aligned inside a warp because G divides 32
     const uint32_t FULL = 0xffffffffu;
+    if ((int64_t)blockIdx.x * NTB / G >= n_act) return;  // whole CTA beyond the active queries
+    bool live = slot < n_act;
+    const int64_t q = live ? (p.qlist ? (int64_t)p.qlist[slot] : slot) : 0;
+    const int64_t binbase = (exact ? slot : q) * p.P;
+    const int T = live ? p.thr[q] : -1;
+    const int s0 = (int)((int64_t)g * p.P / G), s1 = (int)((int64_t)(g + 1) * p.P / G);
 
-    for (int d = lane; d < nb; d += 32) { A[d] = 0; B[d] = 0; C[d] = 0; D[d] = 0; }
+    for (int c = 0; c < ncol; ++c) { cN[c * NTB] = 0; cM[c * NTB] = 0; }
 
-    // ---- totals / overflow ----------------------------------------------------------------
+    // ---- totals / overflow over the query's bins (group reduction) -------------------------
     unsigned long long total = 0;
     int ovf = 0;
-    for (int s = lane; s < p.P; s += 32) {
-        const uint32_t c = p.bin_cnt[binbase + s];
-        const uint32_t capb = exact ? p.bin_cap2[binbase + s] : p.cap;
-        ovf |= (c > capb);
-        total += c;
+    if (live) {
+        for (int s = s0; s < s1; ++s) {
+            const uint32_t c = p.bin_cnt[binbase + s];
+            const uint32_t capb = exact ? p.bin_cap2[binbase + s] : p.cap;
+            ovf |= (c > capb);
+            total += c;
+        }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
-    ovf = __any_sync(FULL, ovf);
-    if (ovf || total < (unsigned long long)p.R || T < 0) {
-        if (lane == 0) {
+    for (int o = 1; o < G; o <<= 1) {
+        total += __shfl_xor_sync(FULL, total, o);
+        ovf |= __shfl_xor_sync(FULL, ovf, o);
+    }
+    if (live && (ovf || total < (unsigned long long)p.R || T < 0)) {
+        if (g == 0) {
             if (p.fail_list != nullptr && !p.no_fallback) {
                 const int i = atomicAdd(p.n_fail, 1);
                 p.fail_list[i] = (int)q;
@@ -455,107 +556,111 @@ __global__ void __launch_bounds__(kApWarps * 32) ap_kernel(ApParams p)
                 if (p.n_fail) atomicAdd(p.n_fail, 1);
             }
         }
-        return;
+        live = false;
     }
-    __syncwarp();
 
-    uint32_t ql[4];
-    const uint32_t* qlp = p.q_lab + q * p.LW;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) ql[w] = (w < p.LW) ? qlp[w] : 0u;
-
-    auto bin_ptr = [&](int s) -> uint32_t* {
+    auto bin_ptr = [&](int s) -> const uint32_t* {
         return exact ? p.lists + slot * p.R + (int64_t)p.bin_off2[binbase + s] : p.lists + (binbase + s) * (int64_t)p.cap;
     };
+    auto col = [&](uint32_t d) -> uint32_t { return (WINDOW ? (d & 31u) : d) * (uint32_t)NTB; };
 
-    // ---- walk 1: relevance bit per candidate, histograms per distance ---------------------
-    for (int s = 0; s < p.P; ++s) {
-        const uint32_t c = p.bin_cnt[binbase + s];
-        uint32_t* lp = bin_ptr(s);
-        const int64_t row0 = (int64_t)s * p.SL;
-        for (uint32_t e = lane; e < c; e += 32) {
-            uint32_t ent = lp[e];
+    // walks my bins in row order; 32 bytes of entries in flight per thread while the previous 32 are consumed
+    auto walk = [&](auto&& fn) {
+        for (int s = s0; s < s1; ++s) {
+            const uint32_t c = p.bin_cnt[binbase + s];
+            const uint32_t* lp = bin_ptr(s);
+            const int64_t row0 = (int64_t)s * p.SL;
+            uint32_t e = 0;
+            if ((reinterpret_cast<uintptr_t>(lp) & 15) == 0 && c >= 8) {
+                const uint4* vp = reinterpret_cast<const uint4*>(lp);
+                uint4 a0 = __ldg(vp), a1 = __ldg(vp + 1);
+                for (; e + 8 <= c; e += 8) {
+                    uint4 n0 = a0, n1 = a1;
+                    if (e + 16 <= c) { n0 = __ldg(vp + (e >> 2) + 2); n1 = __ldg(vp + (e >> 2) + 3); }
+                    fn(a0.x, row0); fn(a0.y, row0); fn(a0.z, row0); fn(a0.w, row0);
+                    fn(a1.x, row0); fn(a1.y, row0); fn(a1.z, row0); fn(a1.w, row0);
+                    a0 = n0; a1 = n1;
+                }
+            }
+            for (; e < c; ++e) fn(__ldg(lp + e), row0);
+        }
+    };
+
+    // ---- phase A: private histograms (+ distance span for the window variant) -------------------
+    uint32_t dmin = 0xffffffffu, dmax = 0;
+    if (live) {
+        walk([&](uint32_t ent, int64_t) {
             const uint32_t d = (ent >> kIdxBits) & kDistMask;
-            const int64_t row = row0 + (ent & kIdxMask);
-            const uint32_t* dl = p.db_lab + row * p.LW;
-            uint32_t m = 0;
-            if (p.LW <= 4) {
-#pragma unroll
-                for (int w = 0; w < 4; ++w)
-                    if (w < p.LW) m |= ql[w] & __ldg(dl + w);
-            } else {
-                for (int w = 0; w < p.LW; ++w) m |= __ldg(qlp + w) & __ldg(dl + w);
-            }
-            if (m) {
-                lp[e] = ent | 0x80000000u;
-                atomicAdd(&B[d], 1u);
-            }
-            atomicAdd(&A[d], 1u);
-        }
+            const uint32_t c = col(d);
+            cN[c] += 1u;
+            cM[c] += ent >> 31;
+            if (WINDOW) { dmin = min(dmin, d); dmax = max(dmax, d); }
+        });
     }
-    __syncwarp();
+    if (WINDOW) {
+        for (int o = 1; o < G; o <<= 1) {
+            dmin = min(dmin, __shfl_xor_sync(FULL, dmin, o));
+            dmax = max(dmax, __shfl_xor_sync(FULL, dmax, o));
+        }
+        if (live && dmax - dmin >= 32u) {
+            if (g == 0) {
+                const int i = atomicAdd(p.n_wide, 1);
+                p.wide_list[i] = (int)q;
+            }
+            live = false;
+        }
+        if (!live) dmin = 0;
+    }
 
-    // ---- exclusive prefixes and the cut distance d* -----------------------------------------
-    int dstar = -1;
-    if (lane == 0) {
+    // ---- phase A2: rank bases, distances in ascending order (all 32 lanes take part in the shuffles) ----
+    {
         uint32_t cn = 0, cm = 0;
-        for (int d = 0; d <= T && d < nb; ++d) {
-            const uint32_t n = A[d], m = B[d];
-            A[d] = cn; B[d] = cm;
-            if (dstar < 0 && (unsigned long long)cn + n >= (unsigned long long)p.R) dstar = d;
-            cn += n; cm += m;
+        for (int i = 0; i < ncol; ++i) {
+            const uint32_t c = col(WINDOW ? dmin + (uint32_t)i : (uint32_t)i);
+            const uint32_t vN = cN[c], vM = cM[c];
+            uint32_t iN = vN, iM = vM;
+            for (int o = 1; o < G; o <<= 1) {
+                const uint32_t tN = __shfl_up_sync(FULL, iN, o, G);
+                const uint32_t tM = __shfl_up_sync(FULL, iM, o, G);
+                if (g >= o) { iN += tN; iM += tM; }
+            }
+            const uint32_t totN = __shfl_sync(FULL, iN, G - 1, G);
+            const uint32_t totM = __shfl_sync(FULL, iM, G - 1, G);
+            cN[c] = cn + (iN - vN);
+            cM[c] = cm + (iM - vM);
+            cn += totN; cm += totM;
         }
     }
-    dstar = __shfl_sync(FULL, dstar, 0);
-    __syncwarp();
-    const uint32_t quota = (uint32_t)(p.R - (int64_t)A[dstar]);
 
-    // ---- walk 2: rank and relevant-prefix of every candidate, in database-row order -------------
+    // ---- phase B: ranks, relevant prefix counts, AP ------------------------------------------------
     double acc = 0.0;
     int relc = 0;
-    for (int s = 0; s < p.P; ++s) {
-        const uint32_t c = p.bin_cnt[binbase + s];
-        const uint32_t* lp = bin_ptr(s);
-        const int64_t row0 = (int64_t)s * p.SL;
-        for (uint32_t base = 0; base < c; base += 32) {
-            const uint32_t e = base + lane;
-            const bool act = e < c;
-            const uint32_t ent = act ? lp[e] : 0u;
-            const int d = (int)((ent >> kIdxBits) & kDistMask);
-            const uint32_t match = ent >> 31;
-            const bool valid = act && d <= dstar;
-            const uint32_t key = valid ? (uint32_t)d : (1024u + lane);
-            const uint32_t peers = __match_any_sync(FULL, key);
-            const uint32_t mb = __ballot_sync(FULL, valid && match);
-            const uint32_t lt = peers & ((1u << lane) - 1u);
-            uint32_t rn = 0, rm = 0;
-            if (valid) { rn = C[d]; rm = D[d]; }
-            const uint32_t n = rn + __popc(lt) + 1u;
-            const uint32_t m = rm + __popc(lt & mb) + match;
-            const bool inc = valid && (d < dstar || n <= quota);
-            if (inc) {
-                const uint32_t pos = A[d] + n - 1u;
-                if (p.ids) p.ids[q * p.R + pos] = (uint32_t)(row0 + (ent & kIdxMask));
-                if (p.dist) p.dist[q * p.R + pos] = (uint16_t)d;
-                if (match) {
-                    acc += (double)(B[d] + m) / (double)(pos + 1u);
+    const uint32_t R32 = (uint32_t)p.R;
+    if (live) {
+        walk([&](uint32_t ent, int64_t row0) {
+            const uint32_t d = (ent >> kIdxBits) & kDistMask;
+            const uint32_t m = ent >> 31;
+            const uint32_t c = col(d);
+            const uint32_t rank = cN[c] + 1u;
+            const uint32_t cum = cM[c] + m;
+            cN[c] = rank;
+            cM[c] = cum;
+            if (rank <= R32) {
+                if (p.ids) p.ids[q * p.R + (rank - 1u)] = (uint32_t)(row0 + (ent & kIdxMask));
+                if (p.dist) p.dist[q * p.R + (rank - 1u)] = (uint16_t)d;
+                if (m) {
+                    acc += (double)cum / (double)rank;
                     relc += 1;
                 }
             }
-            __syncwarp();
-            if (valid && lane == 31 - __clz(peers)) {
-                C[d] = rn + __popc(peers);
-                D[d] = rm + __popc(peers & mb);
-            }
-            __syncwarp();
-        }
+        });
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    // fixed-order reduction over the G ranges of the query (deterministic)
+    for (int o = 1; o < G; o <<= 1) {
         acc += __shfl_xor_sync(FULL, acc, o);
         relc += __shfl_xor_sync(FULL, relc, o);
     }
-    if (lane == 0) {
+    if (live && g == 0) {
         p.ap[q] = relc ? acc / (double)relc : __longlong_as_double(0x7ff8000000000000LL);
         if (p.rel) p.rel[q] = relc;
     }
@@ -654,7 +759,7 @@ __global__ void __launch_bounds__(kApWarps * 32) exact_plan_kernel(ExactPlanPara
 template <int W>
 static int launch_hist(const HistParams& hp, int64_t n_slots_max, int n_chunks, cudaStream_t st)
 {
-    const size_t smem = sizeof(uint32_t) * ((size_t)(hp.b + 1) * kHistThreads + (size_t)hp.seg_rows * W);
+    const size_t smem = sizeof(uint32_t) * ((size_t)(hp.b + 1) * kHistThreads + (size_t)hp.seg_rows * hp.Wr);
     static thread_local size_t configured = 0;
     if (smem > configured) {
         HG_CUDA_TRY(cudaFuncSetAttribute(hist_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -667,37 +772,65 @@ static int launch_hist(const HistParams& hp, int64_t n_slots_max, int n_chunks, 
     return HG_OK;
 }
 
-template <int W, bool EXACT>
-static int launch_select_w(const SelectParams& sp, const Plan& pl, cudaStream_t st)
+template <int W, bool EXACT, bool LW1>
+static int launch_select_q(const SelectParams& sp, const Plan& pl, cudaStream_t st)
 {
     dim3 grid((unsigned)pl.nqt, (unsigned)pl.P);
+    // <= 16 KB of tiles (+ <= 8 KB of query label words in the generic-label variant): no opt-in needed
+    const size_t smem = sizeof(uint32_t) * (2 * (size_t)pl.TILE * pl.Wr + (LW1 ? 0 : (size_t)pl.LW * pl.TQ));
     switch (pl.QT) {
-        case 4: select_kernel<W, 4, EXACT><<<grid, kSelectThreads, 0, st>>>(sp); break;
-        case 2: select_kernel<W, 2, EXACT><<<grid, kSelectThreads, 0, st>>>(sp); break;
-        default: select_kernel<W, 1, EXACT><<<grid, kSelectThreads, 0, st>>>(sp); break;
+        case 4: select_kernel<W, 4, EXACT, LW1><<<grid, kSelectThreads, smem, st>>>(sp); break;
+        case 2: select_kernel<W, 2, EXACT, LW1><<<grid, kSelectThreads, smem, st>>>(sp); break;
+        default: select_kernel<W, 1, EXACT, LW1><<<grid, kSelectThreads, smem, st>>>(sp); break;
     }
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     return HG_OK;
 }
 
-static int launch_ap(const ApParams& ap, int64_t n_slots_max, cudaStream_t st)
+template <int W, bool EXACT>
+static int launch_select_w(const SelectParams& sp, const Plan& pl, cudaStream_t st)
 {
-    const size_t smem = sizeof(uint32_t) * 4 * (size_t)(ap.b + 1) * kApWarps;
-    ap_kernel<<<(unsigned)ceil_div(n_slots_max, kApWarps), kApWarps * 32, smem, st>>>(ap);
+    return pl.LW == 1 ? launch_select_q<W, EXACT, true>(sp, pl, st) : launch_select_q<W, EXACT, false>(sp, pl, st);
+}
+
+template <bool WINDOW>
+static int launch_ap(ApParams ap, int64_t n_slots_max, cudaStream_t st)
+{
+    const int ncol = WINDOW ? 32 : ap.b + 1;
+    // one shared-memory column of 2*ncol counters per thread
+    int threads = 128;
+    while (threads > 32 && (size_t)threads * 2 * ncol * sizeof(uint32_t) > 200 * 1024) threads >>= 1;
+    const size_t smem = (size_t)threads * 2 * ncol * sizeof(uint32_t);
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        HG_CUDA_TRY(cudaFuncSetAttribute(ap_kernel<WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    // threads per query: enough threads to fill the GPU (resident CTAs limited by shared memory), power of two <= 32, <= P
+    const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024) / (smem + 1024)));
+    const int64_t want_threads = (int64_t)sms * ctas_per_sm * threads * 2;
+    int G = 1;
+    while (G < 32 && G * 2 <= ap.P && (int64_t)n_slots_max * G < want_threads) G <<= 1;
+    G = env_int("HG_AP_G", G);
+    if (G < 1 || G > 32 || (G & (G - 1)) || G > ap.P) G = 1;
+    ap.G = G;
+    const int64_t blocks = ceil_div(n_slots_max * G, threads);
+    ap_kernel<WINDOW><<<(unsigned)blocks, threads, smem, st>>>(ap);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     return HG_OK;
 }
 
 template <int W>
-static int run_map(const Plan& pl, const uint32_t* q_codes, const uint32_t* q_lab, const uint32_t* db_codes, const uint32_t* db_lab,
-                   unsigned flags, double* d_ap, uint32_t* d_ids, uint16_t* d_dist, int32_t* d_rel, char* ws, cudaStream_t st)
+static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_rows, unsigned flags, double* d_ap, uint32_t* d_ids, uint16_t* d_dist, int32_t* d_rel, char* ws, cudaStream_t st)
 {
     int* ctrl = reinterpret_cast<int*>(ws + pl.off_ctrl);
     int* thr = reinterpret_cast<int*>(ws + pl.off_thr);
     int* thr2 = reinterpret_cast<int*>(ws + pl.off_thr2);
     int* fail_list = reinterpret_cast<int*>(ws + pl.off_fail);
+    int* wide_list = reinterpret_cast<int*>(ws + pl.off_wide);
     uint32_t* hist_s = reinterpret_cast<uint32_t*>(ws + pl.off_hist_s);
     uint32_t* bin_cnt = reinterpret_cast<uint32_t*>(ws + pl.off_bin_cnt);
     uint32_t* bin_cnt2 = reinterpret_cast<uint32_t*>(ws + pl.off_bin_cnt2);
@@ -725,7 +858,7 @@ static int run_map(const Plan& pl, const uint32_t* q_codes, const uint32_t* q_la
         // 1. sampled histogram
         HG_CUDA_TRY(cudaMemsetAsync(hist_s, 0, sizeof(uint32_t) * (size_t)pl.nq * nb, st));
         HistParams hp{};
-        hp.q_codes = q_codes; hp.db_codes = db_codes; hp.nq = pl.nq; hp.ndb = pl.ndb; hp.b = pl.b;
+        hp.q_rows = q_rows; hp.db_rows = db_rows; hp.nq = pl.nq; hp.ndb = pl.ndb; hp.b = pl.b; hp.Wr = pl.Wr;
         hp.n_active = nullptr; hp.qlist = nullptr;
         hp.seg_stride = pl.seg_stride; hp.n_seg = pl.n_seg; hp.seg_rows = pl.TILE; hp.seg_per_chunk = pl.seg_per_chunk;
         hp.out = hist_s; hp.out_chunks = 1;
@@ -741,7 +874,7 @@ static int run_map(const Plan& pl, const uint32_t* q_codes, const uint32_t* q_la
     if (!force_exact) {
         // 3. single-pass select
         SelectParams sp{};
-        sp.q_codes = q_codes; sp.db_codes = db_codes; sp.nq = pl.nq; sp.ndb = pl.ndb; sp.thr = thr;
+        sp.q_rows = q_rows; sp.db_rows = db_rows; sp.nq = pl.nq; sp.ndb = pl.ndb; sp.Wr = pl.Wr; sp.LW = pl.LW; sp.TILE = pl.TILE; sp.thr = thr;
         sp.n_active = nullptr; sp.qlist = nullptr; sp.P = pl.P; sp.SL = pl.SL; sp.R = pl.R;
         sp.lists = lists; sp.cap = pl.cap; sp.bin_off2 = nullptr; sp.bin_cap2 = nullptr; sp.quota2 = nullptr;
         sp.bin_cnt = bin_cnt;
@@ -753,11 +886,15 @@ static int run_map(const Plan& pl, const uint32_t* q_codes, const uint32_t* q_la
     timer.mark(kPhaseAp, st);
     {
         ApParams ap{};
-        ap.nq = pl.nq; ap.n_active = nullptr; ap.qlist = nullptr; ap.P = pl.P; ap.b = pl.b; ap.LW = pl.LW; ap.SL = pl.SL; ap.R = pl.R;
+        ap.nq = pl.nq; ap.n_active = nullptr; ap.qlist = nullptr; ap.bins_by_slot = 0; ap.P = pl.P; ap.b = pl.b; ap.SL = pl.SL; ap.R = pl.R;
         ap.lists = lists; ap.cap = pl.cap; ap.bin_off2 = nullptr; ap.bin_cap2 = nullptr; ap.bin_cnt = bin_cnt; ap.thr = thr;
-        ap.q_lab = q_lab; ap.db_lab = db_lab; ap.ap = d_ap; ap.ids = d_ids; ap.dist = d_dist; ap.rel = d_rel;
+        ap.ap = d_ap; ap.ids = d_ids; ap.dist = d_dist; ap.rel = d_rel;
         ap.fail_list = fail_list; ap.n_fail = n_fail; ap.no_fallback = no_fallback ? 1 : 0;
-        if ((rc = launch_ap(ap, pl.nq, st)) != HG_OK) return rc;
+        ap.wide_list = wide_list; ap.n_wide = ctrl + 2;
+        if ((rc = launch_ap<true>(ap, pl.nq, st)) != HG_OK) return rc;
+        // queries whose candidate distances span >= 32 values: same bins, full-width counters
+        ap.n_active = ctrl + 2; ap.qlist = wide_list; ap.wide_list = nullptr; ap.n_wide = nullptr;
+        if ((rc = launch_ap<false>(ap, pl.nq, st)) != HG_OK) return rc;
     }
     timer.mark(kPhaseExact, st);
     if (no_fallback) { timer.mark(kNumPhases, st); return HG_OK; }
@@ -768,7 +905,7 @@ static int run_map(const Plan& pl, const uint32_t* q_codes, const uint32_t* q_la
         count_launch();
         HG_CUDA_TRY(cudaGetLastError());
         HistParams hp{};
-        hp.q_codes = q_codes; hp.db_codes = db_codes; hp.nq = pl.nq; hp.ndb = pl.ndb; hp.b = pl.b;
+        hp.q_rows = q_rows; hp.db_rows = db_rows; hp.nq = pl.nq; hp.ndb = pl.ndb; hp.b = pl.b; hp.Wr = pl.Wr;
         hp.n_active = n_fail; hp.qlist = fail_list;
         hp.seg_stride = pl.TILE; hp.n_seg = ceil_div(pl.ndb, pl.TILE); hp.seg_rows = pl.TILE; hp.seg_per_chunk = (int)(pl.SL / pl.TILE);
         hp.out = hist2; hp.out_chunks = pl.P;
@@ -783,18 +920,18 @@ static int run_map(const Plan& pl, const uint32_t* q_codes, const uint32_t* q_la
         HG_CUDA_TRY(cudaGetLastError());
 
         SelectParams sp{};
-        sp.q_codes = q_codes; sp.db_codes = db_codes; sp.nq = pl.nq; sp.ndb = pl.ndb; sp.thr = thr2;
+        sp.q_rows = q_rows; sp.db_rows = db_rows; sp.nq = pl.nq; sp.ndb = pl.ndb; sp.Wr = pl.Wr; sp.LW = pl.LW; sp.TILE = pl.TILE; sp.thr = thr2;
         sp.n_active = n_fail; sp.qlist = fail_list; sp.P = pl.P; sp.SL = pl.SL; sp.R = pl.R;
         sp.lists = lists; sp.cap = 0; sp.bin_off2 = bin_off2; sp.bin_cap2 = bin_cap2; sp.quota2 = quota2;
         sp.bin_cnt = bin_cnt2;
         if ((rc = launch_select_w<W, true>(sp, pl, st)) != HG_OK) return rc;
 
         ApParams ap{};
-        ap.nq = pl.nq; ap.n_active = n_fail; ap.qlist = fail_list; ap.P = pl.P; ap.b = pl.b; ap.LW = pl.LW; ap.SL = pl.SL; ap.R = pl.R;
+        ap.nq = pl.nq; ap.n_active = n_fail; ap.qlist = fail_list; ap.bins_by_slot = 1; ap.P = pl.P; ap.b = pl.b; ap.SL = pl.SL; ap.R = pl.R;
         ap.lists = lists; ap.cap = 0; ap.bin_off2 = bin_off2; ap.bin_cap2 = bin_cap2; ap.bin_cnt = bin_cnt2; ap.thr = thr2;
-        ap.q_lab = q_lab; ap.db_lab = db_lab; ap.ap = d_ap; ap.ids = d_ids; ap.dist = d_dist; ap.rel = d_rel;
-        ap.fail_list = nullptr; ap.n_fail = ctrl + 1; ap.no_fallback = 0;
-        if ((rc = launch_ap(ap, pl.nq, st)) != HG_OK) return rc;
+        ap.ap = d_ap; ap.ids = d_ids; ap.dist = d_dist; ap.rel = d_rel;
+        ap.fail_list = nullptr; ap.n_fail = ctrl + 1; ap.no_fallback = 0; ap.wide_list = nullptr; ap.n_wide = nullptr;
+        if ((rc = launch_ap<false>(ap, pl.nq, st)) != HG_OK) return rc;
     }
     timer.mark(kNumPhases, st);
     return HG_OK;
@@ -811,20 +948,19 @@ extern "C" size_t hg_hamming_map_workspace_bytes(int64_t nq, int64_t ndb, int b,
     return pl.ok ? pl.total : 0;
 }
 
-extern "C" int hg_hamming_map(const uint32_t* d_q_codes, const uint32_t* d_q_lab, int64_t nq, const uint32_t* d_db_codes,
-                              const uint32_t* d_db_lab, int64_t ndb, int b, int L, int64_t R, unsigned flags, double* d_ap,
-                              uint32_t* d_ids, uint16_t* d_dist, int32_t* d_rel, void* d_workspace, size_t workspace_bytes, void* stream)
+extern "C" int hg_hamming_map(const uint32_t* d_q_rows, int64_t nq, const uint32_t* d_db_rows, int64_t ndb, int b, int L, int64_t R,
+                              unsigned flags, double* d_ap, uint32_t* d_ids, uint16_t* d_dist, int32_t* d_rel, void* d_workspace,
+                              size_t workspace_bytes, void* stream)
 {
     if (nq == 0) return HG_OK;
     if (nq < 0 || ndb < 0) return hg::fail(HG_EINVAL, "hg_hamming_map: negative size");
     if (R <= 0) return hg::fail(HG_EINVAL, "hg_hamming_map: R must be positive (got %lld)", (long long)R);
     if (R > ndb) return hg::fail(HG_ERANGE, "hg_hamming_map: R=%lld exceeds the database size %lld", (long long)R, (long long)ndb);
     if (hg_code_words(b) == 0) return hg::fail(HG_EINVAL, "hg_hamming_map: unsupported hash length b=%d (1..%d)", b, HG_MAX_BITS);
-    if (hg_label_words(L) == 0) return hg::fail(HG_EINVAL, "hg_hamming_map: unsupported label width L=%d", L);
-    if (!d_q_codes || !d_q_lab || !d_db_codes || !d_db_lab || !d_ap || !d_workspace)
-        return hg::fail(HG_EINVAL, "hg_hamming_map: NULL pointer");
-    if ((reinterpret_cast<uintptr_t>(d_db_codes) & 15) || (reinterpret_cast<uintptr_t>(d_workspace) & 255))
-        return hg::fail(HG_EINVAL, "hg_hamming_map: d_db_codes must be 16-byte and the workspace 256-byte aligned");
+    if (hg_label_words(L) == 0) return hg::fail(HG_EINVAL, "hg_hamming_map: unsupported label width L=%d (1..%d)", L, HG_MAX_LABELS);
+    if (!d_q_rows || !d_db_rows || !d_ap || !d_workspace) return hg::fail(HG_EINVAL, "hg_hamming_map: NULL pointer");
+    if ((reinterpret_cast<uintptr_t>(d_db_rows) & 15) || (reinterpret_cast<uintptr_t>(d_workspace) & 255))
+        return hg::fail(HG_EINVAL, "hg_hamming_map: d_db_rows must be 16-byte and the workspace 256-byte aligned");
     if (!hg::device_facts().ok) return hg::fail(HG_ECUDA, "hg_hamming_map: no CUDA device");
     const hg::Plan pl = hg::make_plan(nq, ndb, b, L, R);
     if (!pl.ok) return hg::fail(HG_EINVAL, "hg_hamming_map: sizes out of range (nq=%lld ndb=%lld)", (long long)nq, (long long)ndb);
@@ -833,11 +969,11 @@ extern "C" int hg_hamming_map(const uint32_t* d_q_codes, const uint32_t* d_q_lab
     char* ws = static_cast<char*>(d_workspace);
     cudaStream_t st = (cudaStream_t)stream;
     switch (pl.W) {
-        case 1: return hg::run_map<1>(pl, d_q_codes, d_q_lab, d_db_codes, d_db_lab, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
-        case 2: return hg::run_map<2>(pl, d_q_codes, d_q_lab, d_db_codes, d_db_lab, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
-        case 3: return hg::run_map<3>(pl, d_q_codes, d_q_lab, d_db_codes, d_db_lab, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
-        case 4: return hg::run_map<4>(pl, d_q_codes, d_q_lab, d_db_codes, d_db_lab, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
-        case 8: return hg::run_map<8>(pl, d_q_codes, d_q_lab, d_db_codes, d_db_lab, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
+        case 1: return hg::run_map<1>(pl, d_q_rows, d_db_rows, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
+        case 2: return hg::run_map<2>(pl, d_q_rows, d_db_rows, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
+        case 3: return hg::run_map<3>(pl, d_q_rows, d_db_rows, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
+        case 4: return hg::run_map<4>(pl, d_q_rows, d_db_rows, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
+        case 8: return hg::run_map<8>(pl, d_q_rows, d_db_rows, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
         default: return hg::fail(HG_EINVAL, "hg_hamming_map: unsupported word count %d", pl.W);
     }
 }
@@ -858,6 +994,6 @@ extern "C" int hg_hamming_map_stats(const void* d_workspace, size_t workspace_by
     out[4] = pl.TQ;
     out[5] = pl.sample_rows;
     out[6] = ctrl[1];
-    out[7] = pl.nqt;
+    out[7] = ctrl[2];
     return HG_OK;
 }

@@ -1,7 +1,7 @@
 """mAP@R by Hamming ranking -- the drop-in for the reference's ``lib/metric.py``.
 
 Reference surface kept (thuml/HashGAN):
-    lib/metric.py:4-6    class MAPs: __init__(self, r) -> self.R
+    lib/metric.py:4-6    MAPs.__init__(self, r) -> self.R
     lib/metric.py:8-10   MAPs.distance(a, b)            (dead code in the reference; kept)
     lib/metric.py:12-24  MAPs.get_maps_by_feature(database, query) -> numpy.float64
     main.py:164          MAPs(cfg.DATA.MAP_R).get_maps_by_feature(db, test)
@@ -22,13 +22,13 @@ Semantics relative to the reference:
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Optional
 
 import numpy as np
 
 from . import _native
 
-__all__ = ["MAPs", "MAPs_CQ", "pack_codes", "pack_labels", "hamming_map_device"]
+__all__ = ["MAPs", "MAPs_CQ", "pack_rows", "hamming_map_device"]
 
 # One call of hg_hamming_map handles a query chunk whose workspace stays under this many bytes.
 DEFAULT_WORKSPACE_LIMIT = 24 << 30
@@ -76,9 +76,6 @@ def _features_to_device(torch, x, device):
     return t.contiguous()
 
 
-_LABEL_BYTES = {}
-
-
 def _labels_to_device(torch, x, device):
     """[N, L] 0/1 labels -> contiguous CUDA tensor of int64 / int32 / int8 (as given) and its item size."""
     if isinstance(x, torch.Tensor):
@@ -112,69 +109,69 @@ def _labels_to_device(torch, x, device):
     return t, t.element_size()
 
 
-def pack_codes(feat, device=None):
-    """sign + bit-pack [N, b] float features on the GPU -> uint32 words as an int32 CUDA tensor
-    [N, hg_code_words(b)] (C ABI: hg_pack_sign_f32)."""
+def pack_rows(feat, lab=None, device=None, bad_flag=None, L: Optional[int] = None):
+    """sign + bit-pack [N, b] features and (optionally) [N, L] 0/1 labels on the GPU into packed rows
+    [ code words | label words | pad ] -- an int32 CUDA tensor [N, hg_row_words(b, L)] (C ABI: hg_pack_rows).
+    ``bad_flag`` (int32 CUDA tensor [1]) is OR-ed with 1 when a label is not 0/1."""
     torch = _torch()
     device = _require_cuda(torch, device)
     lib = _native.lib()
     with torch.cuda.device(device):
         f = _features_to_device(torch, feat, device)
         n, b = f.shape
-        W = _native.code_words(b)
-        codes = torch.empty((n, W), dtype=torch.int32, device=device)
-        _native.check(lib.hg_pack_sign_f32(f.data_ptr(), n, b, b, codes.data_ptr(), _stream_ptr(torch, device)))
-        f.record_stream(torch.cuda.current_stream(device))
-    return codes
-
-
-def pack_labels(lab, device=None, bad_flag=None):
-    """0/1 label matrix [N, L] -> bit rows, int32 CUDA tensor [N, ceil(L/32)] (C ABI: hg_pack_labels).
-    ``bad_flag`` (int32 CUDA tensor [1]) is OR-ed with 1 when a label is not 0/1."""
-    torch = _torch()
-    device = _require_cuda(torch, device)
-    lib = _native.lib()
-    with torch.cuda.device(device):
-        t, nbytes = _labels_to_device(torch, lab, device)
-        n, L = t.shape
-        LW = _native.label_words(L)
-        packed = torch.empty((n, LW), dtype=torch.int32, device=device)
-        _native.check(lib.hg_pack_labels(t.data_ptr(), nbytes, n, L, packed.data_ptr(),
-                                         bad_flag.data_ptr() if bad_flag is not None else None,
-                                         _stream_ptr(torch, device)))
-        t.record_stream(torch.cuda.current_stream(device))
-    return packed
+        if lab is not None:
+            t, nbytes = _labels_to_device(torch, lab, device)
+            if t.shape[0] != n:
+                raise ValueError(f"output has {n} rows but label has {t.shape[0]}")
+            L = int(t.shape[1])
+        else:
+            t, nbytes, L = None, 8, int(L or 1)
+        Wr = _native.row_words(b, L)
+        rows = torch.empty((n, Wr), dtype=torch.int32, device=device)
+        stream = torch.cuda.current_stream(device)
+        _native.check(lib.hg_pack_rows(f.data_ptr(), b, t.data_ptr() if t is not None else None, nbytes, n, b, L, rows.data_ptr(),
+                                       bad_flag.data_ptr() if bad_flag is not None else None, int(stream.cuda_stream)))
+        f.record_stream(stream)
+        if t is not None:
+            t.record_stream(stream)
+    return rows
 
 
 def _query_chunk(nq: int, ndb: int, b: int, L: int, R: int, limit: int) -> int:
     """Largest query count whose hg_hamming_map workspace fits in `limit` bytes."""
     lib = _native.lib()
-    need = lib.hg_hamming_map_workspace_bytes(nq, ndb, b, L, R)
-    if need == 0:
-        raise ValueError(f"sizes out of range for the Hamming kernel: nq={nq} ndb={ndb} b={b} L={L} R={R}")
-    if need <= limit:
+    def fits(n):  # 0 = the plan refuses the batch (list area beyond 32-bit offsets): treat as "too big"
+        need = lib.hg_hamming_map_workspace_bytes(n, ndb, b, L, R)
+        return 0 < need <= limit
+
+    if lib.hg_hamming_map_workspace_bytes(1, ndb, b, L, R) == 0:
+        raise ValueError(f"sizes out of range for the Hamming kernel: ndb={ndb} b={b} L={L} R={R}")
+    if fits(nq):
         return nq
     lo, hi = 1, nq
-    while lo < hi:  # workspace is monotone in nq
+    while lo < hi:  # the workspace grows with nq
         mid = (lo + hi + 1) // 2
-        if lib.hg_hamming_map_workspace_bytes(mid, ndb, b, L, R) <= limit:
+        if fits(mid):
             lo = mid
         else:
             hi = mid - 1
-    if lib.hg_hamming_map_workspace_bytes(lo, ndb, b, L, R) > limit:
+    if not fits(lo):
         raise MemoryError(f"workspace limit {limit} B is too small for a single query against ndb={ndb}")
     return lo
 
 
-def hamming_map_device(q_codes, q_lab, db_codes, db_lab, b: int, L: int, R: int, *, flags: int = 0,
+def hamming_map_device(q_rows, db_rows, b: int, L: int, R: int, *, flags: int = 0,
                        want_ids: bool = False, want_rel: bool = False,
                        workspace_limit: int = DEFAULT_WORKSPACE_LIMIT, stats: Optional[dict] = None):
-    """Per-query AP@R from packed device tensors (C ABI: hg_hamming_map).  Returns (ap, ids, dist, rel);
+    """Per-query AP@R from packed-row device tensors (C ABI: hg_hamming_map).  Returns (ap, ids, dist, rel);
     ids/dist/rel are None unless requested.  Everything stays on the device and on the current stream."""
     torch = _torch()
     lib = _native.lib()
-    device = db_codes.device
-    nq, ndb = int(q_codes.shape[0]), int(db_codes.shape[0])
+    device = db_rows.device
+    nq, ndb = int(q_rows.shape[0]), int(db_rows.shape[0])
+    Wr = _native.row_words(b, L)
+    if q_rows.shape[1] != Wr or db_rows.shape[1] != Wr or not q_rows.is_contiguous() or not db_rows.is_contiguous():
+        raise ValueError(f"packed rows must be contiguous [N, {Wr}] for b={b}, L={L}")
     if R > ndb:
         raise ValueError(f"operands could not be broadcast together: R={R} exceeds the database size {ndb}")
     if R <= 0:
@@ -193,8 +190,7 @@ def hamming_map_device(q_codes, q_lab, db_codes, db_lab, b: int, L: int, R: int,
         for s in range(0, nq, chunk):
             n = min(chunk, nq - s)
             _native.check(lib.hg_hamming_map(
-                q_codes[s:s + n].data_ptr(), q_lab[s:s + n].data_ptr(), n,
-                db_codes.data_ptr(), db_lab.data_ptr(), ndb, b, L, R, flags,
+                q_rows[s:s + n].data_ptr(), n, db_rows.data_ptr(), ndb, b, L, R, flags,
                 ap[s:s + n].data_ptr(),
                 ids[s:s + n].data_ptr() if ids is not None else None,
                 dist[s:s + n].data_ptr() if dist is not None else None,
@@ -206,8 +202,27 @@ def hamming_map_device(q_codes, q_lab, db_codes, db_lab, b: int, L: int, R: int,
                 stats.setdefault("chunks", []).append(
                     dict(exact_queries=int(out[0]), splits=int(out[1]), rows_per_split=int(out[2]), bin_entries=int(out[3]),
                          queries_per_cta=int(out[4]), sample_rows=int(out[5]), exact_failures=int(out[6]),
-                         query_tiles=int(out[7]), nq=n))
+                         wide_queries=int(out[7]), nq=n))
     return ap, ids, dist, rel
+
+
+class _Record:
+    __slots__ = ("output", "label")
+
+    def __init__(self, output, label):
+        self.output, self.label = output, label
+
+
+def _as_record(x):
+    """Accepts the reference's EasyDict / any object with .output and .label; list-like fields become arrays."""
+    out, lab = x.output, x.label
+    if not hasattr(out, "shape"):
+        out = np.asarray(out)
+    if not hasattr(lab, "shape"):
+        lab = np.asarray(lab)
+    if len(out.shape) != 2 or len(lab.shape) != 2:
+        raise ValueError("output must be [N, b] and label [N, L]")
+    return _Record(out, lab)
 
 
 class MAPs:
@@ -218,45 +233,38 @@ class MAPs:
         self.device = device
         self.flags = flags
         self.workspace_limit = workspace_limit
-        self.last_stats: dict = {}
+        self.collect_stats = False
+        self.last_stats = None
 
     @staticmethod
     def distance(a, b):
         # lib/metric.py:8-10 (unused by the reference itself)
         return np.dot(a, b)
 
-    # -- device-side pipeline ---------------------------------------------------------------------
     def _pack_all(self, database, query):
         torch = _torch()
         device = _require_cuda(torch, self.device)
         with torch.cuda.device(device):
             bad = torch.zeros((1,), dtype=torch.int32, device=device)
-            db_f = _features_to_device(torch, database.output, device)
-            q_f = _features_to_device(torch, query.output, device)
-            if db_f.shape[1] != q_f.shape[1]:
-                raise ValueError(f"shapes {tuple(q_f.shape)} and {tuple(db_f.shape)} not aligned: hash lengths differ")
-            db_codes = pack_codes(db_f, device)
-            q_codes = pack_codes(q_f, device)
-            db_lab = pack_labels(database.label, device, bad)
-            q_lab = pack_labels(query.label, device, bad)
-            b = int(db_f.shape[1])
-            L = int(np.shape(database.label)[1]) if not hasattr(database.label, "shape") else int(database.label.shape[1])
-            Lq = int(query.label.shape[1]) if hasattr(query.label, "shape") else int(np.shape(query.label)[1])
+            b, bq = int(database.output.shape[1]), int(query.output.shape[1])
+            L, Lq = int(database.label.shape[1]), int(query.label.shape[1])
+            if b != bq:
+                raise ValueError(f"shapes {tuple(query.output.shape)} and {tuple(database.output.shape)} not aligned: hash lengths differ")
             if L != Lq:
                 raise ValueError(f"label widths differ: database {L}, query {Lq}")
-            if db_codes.shape[0] != db_lab.shape[0] or q_codes.shape[0] != q_lab.shape[0]:
-                raise ValueError("output and label row counts differ")
-        return device, bad, db_codes, db_lab, q_codes, q_lab, b, L
+            db_rows = pack_rows(database.output, database.label, device, bad)
+            q_rows = pack_rows(query.output, query.label, device, bad)
+        return device, bad, db_rows, q_rows, b, L
 
     def per_query_ap(self, database, query, *, want_ids: bool = False):
         """Per-query AP@R as a NumPy float64 vector (NaN where the reference would skip the query).
         With ``want_ids`` also returns (ids [Nq, R] int64, dist [Nq, R] int32) in rank order."""
-        torch = _torch()
-        device, bad, db_codes, db_lab, q_codes, q_lab, b, L = self._pack_all(database, query)
+        database, query = _as_record(database), _as_record(query)
+        device, bad, db_rows, q_rows, b, L = self._pack_all(database, query)
         R = int(self.R)
-        self.last_stats = {}
-        ap, ids, dist, _ = hamming_map_device(q_codes, q_lab, db_codes, db_lab, b, L, R, flags=self.flags, want_ids=want_ids,
-                                              workspace_limit=self.workspace_limit, stats=None)
+        self.last_stats = {} if self.collect_stats else None
+        ap, ids, dist, _ = hamming_map_device(q_rows, db_rows, b, L, R, flags=self.flags, want_ids=want_ids,
+                                              workspace_limit=self.workspace_limit, stats=self.last_stats)
         ap_h = ap.cpu().numpy()
         if int(bad.item()) != 0:
             raise ValueError("labels must be 0/1 integers (lib/metric.py:17-19 is only defined for 0/1 labels)")

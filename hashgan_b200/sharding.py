@@ -3,8 +3,8 @@ CUDA_VISIBLE_DEVICES), so this layer is new.
 
 One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch; gloo on CPU for the tests):
   1. the database is row-sharded: rank g holds rows [start_g, start_g + n_g) and packs them locally;
-  2. ONE all-gather of the packed code words (and the packed label words) -- rank order is the global
-     database row order, which preserves the (distance, row) tie rule;
+  2. ONE all-gather of the packed rows (code words + label words in one tensor) -- rank order is the
+     global database row order, which preserves the (distance, row) tie rule;
   3. queries are row-sharded: each rank ranks its own queries against the full packed database;
   4. the per-query APs are all-gathered so every rank computes the same mean in the same order
      (lib/metric.py:24).
@@ -77,44 +77,39 @@ class ShardedMAPs:
     contiguous row blocks (rank order == global row order) and returns the global mAP on every rank."""
 
     def __init__(self, r: int, group=None, *, device=None, flags: int = 0,
-                 pack_codes: Optional[Callable] = None, pack_labels: Optional[Callable] = None, rank_fn: Optional[Callable] = None):
+                 pack_rows: Optional[Callable] = None, rank_fn: Optional[Callable] = None):
         self.R = r
         self.group = group
         self.device = device
         self.flags = flags
-        self._pack_codes = pack_codes
-        self._pack_labels = pack_labels
+        self._pack_rows = pack_rows
         self._rank_fn = rank_fn
         self.last_counts: Sequence[int] = ()
 
-    def _native_hooks(self):
+    def _hooks(self):
         from . import metric
 
-        pc = self._pack_codes or (lambda x: metric.pack_codes(x, self.device))
-        pl = self._pack_labels or (lambda x: metric.pack_labels(x, self.device))
+        pack = self._pack_rows or (lambda out, lab: metric.pack_rows(out, lab, self.device))
 
-        def rank(qc, ql, dbc, dbl, b, L, R):
-            ap, _, _, _ = metric.hamming_map_device(qc, ql, dbc, dbl, b, L, R, flags=self.flags)
+        def rank(q_rows, db_rows, b, L, R):
+            ap, _, _, _ = metric.hamming_map_device(q_rows, db_rows, b, L, R, flags=self.flags)
             return ap
 
-        return pc, pl, (self._rank_fn or rank)
+        return pack, (self._rank_fn or rank)
 
     def per_query_ap_device(self, database, query):
         """Global per-query AP vector (rank order) as a tensor on the compute device."""
-        pack_codes, pack_labels, rank = self._native_hooks()
+        pack, rank = self._hooks()
         b = int(database.output.shape[1])
         L = int(database.label.shape[1])
-        db_codes_local = pack_codes(database.output)
-        db_lab_local = pack_labels(database.label)
-        q_codes = pack_codes(query.output)
-        q_lab = pack_labels(query.label)
-        db_codes, counts = gather_rows(db_codes_local, self.group)   # the one exchange step of the path
-        db_lab, _ = gather_rows(db_lab_local, self.group)
+        db_rows_local = pack(database.output, database.label)
+        q_rows = pack(query.output, query.label)
+        db_rows, counts = gather_rows(db_rows_local, self.group)   # the ONE exchange step: packed code + label words
         self.last_counts = counts
-        ndb = int(db_codes.shape[0])
+        ndb = int(db_rows.shape[0])
         if self.R > ndb:
             raise ValueError(f"operands could not be broadcast together: R={self.R} exceeds the database size {ndb}")
-        ap_local = rank(q_codes, q_lab, db_codes, db_lab, b, L, int(self.R))
+        ap_local = rank(q_rows, db_rows, b, L, int(self.R))
         return gather_vector(ap_local, self.group)
 
     def get_maps_by_feature(self, database, query):

@@ -27,7 +27,7 @@ extern "C" {
 #define HG_ELABEL 5      /* a label was not 0/1 (lib/metric.py:17-19 is only defined for 0/1 labels) */
 
 #define HG_MAX_BITS 256  /* hash length b supported by the kernels (reference default 64, lib/config.py:10) */
-#define HG_MAX_LABELS 4096
+#define HG_MAX_LABELS 128  /* label width L (CIFAR-10: 10, NUS-WIDE: 81, COCO: 80) */
 
 /* flags for hg_hamming_map */
 #define HG_FLAG_FORCE_EXACT 1u  /* skip the sampled-threshold fast pass; every query takes the two-pass exact path */
@@ -40,25 +40,26 @@ const char* hg_last_error(void);
 /* Device facts used for grid sizing (multiples of the SM count). */
 int hg_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes);
 
-/* Number of uint32 words per packed code row as the kernels lay them out: ceil(b/32) for b<=128,
- * 8 for 128<b<=256 (zero pad words).  Returns 0 for unsupported b. */
+/* Packed-row layout shared by queries and database:
+ *     row = [ W code words | LW label words | zero pad ]   (uint32, row stride hg_row_words(b, L))
+ * W  = hg_code_words(b)  = ceil(b/32) for b <= 128, 8 for 128 < b <= 256 (zero pad words); 0 if unsupported.
+ * LW = hg_label_words(L) = ceil(L/32), L <= HG_MAX_LABELS; 0 if unsupported.
+ * The stride rounds W+LW up so that the code words can be fetched with one 64/128-bit load. */
 int hg_code_words(int b);
-/* Words per packed label row: ceil(L/32). */
 int hg_label_words(int L);
+int hg_row_words(int b, int L);
 
-/* sign + bit-pack.  New in the build: the reference never binarises (main.py:155-157 hands tanh
- * outputs straight to lib/metric.py:13); on {-1,+1} inputs ip = b - 2*d_H, so ranking by inner
- * product (lib/metric.py:13-14) == ranking by Hamming distance of these words.
- * d_feat: [n, ld] float32 row-major, first b columns used.  d_codes: [n, hg_code_words(b)] uint32,
- * bit j of word w = (feat[i, 32w+j] > 0); pad bits/words are zero. */
-int hg_pack_sign_f32(const float* d_feat, int64_t n, int b, int64_t ld, uint32_t* d_codes, void* stream);
-
-/* 0/1 label matrix -> bit rows.  Replaces the per-query gather/compare of lib/metric.py:17-19:
- * imatch = any_l(db.label[l] == label[l]) with query zeros rewritten to -1  <=>  (q_bits & db_bits) != 0.
- * d_lab: [n, L] int64 (the dtype np.array(list-of-int) gives, lib/dataloader.py:45,74) or int32/uint8
- * (elem_bytes = 8, 4 or 1).  d_packed: [n, hg_label_words(L)] uint32.  d_bad (optional, int32[1]) is
- * OR-ed with 1 if any label is not 0/1. */
-int hg_pack_labels(const void* d_lab, int elem_bytes, int64_t n, int L, uint32_t* d_packed, int* d_bad, void* stream);
+/* sign + bit-pack of features and 0/1 labels into packed rows (d_rows: [n, hg_row_words(b, L)] uint32).
+ * New in the build: the reference never binarises (main.py:155-157 hands tanh outputs straight to
+ * lib/metric.py:13); on {-1,+1} inputs ip = b - 2*d_H, so ranking by inner product (lib/metric.py:13-14) ==
+ * ranking by Hamming distance of these words.  Code bit j of word w = (feat[i, 32w+j] > 0).
+ * The label bits replace the per-query gather/compare of lib/metric.py:17-19: imatch = any_l(db.label[l] ==
+ * label[l]) with the query's zeros rewritten to -1  <=>  (q_label_bits & db_label_bits) != 0 for 0/1 labels.
+ * d_feat: [n, ld] float32 row-major, first b columns used.  d_lab: [n, L] int64 (the dtype np.array(list-of-int)
+ * gives, lib/dataloader.py:45,74), int32 or int8/uint8 (lab_elem_bytes = 8, 4, 1); may be NULL (label bits zero).
+ * d_bad (optional, int32[1]) is OR-ed with 1 if any label is not 0/1. */
+int hg_pack_rows(const float* d_feat, int64_t ld, const void* d_lab, int lab_elem_bytes, int64_t n, int b, int L,
+                 uint32_t* d_rows, int* d_bad, void* stream);
 
 /* Workspace (bytes) hg_hamming_map needs for these sizes; 0 on invalid arguments. */
 size_t hg_hamming_map_workspace_bytes(int64_t nq, int64_t ndb, int b, int L, int64_t R);
@@ -70,17 +71,18 @@ size_t hg_hamming_map_workspace_bytes(int64_t nq, int64_t ndb, int b, int L, int
  * d_ap[q] = AP@R of query q, NaN where the top-R holds no relevant row (the reference skips those
  * queries, lib/metric.py:22-23).  Optional outputs (may be NULL): d_ids [nq, R] uint32 database rows in
  * rank order, d_dist [nq, R] uint16 their Hamming distances, d_rel [nq] int32 relevant count in top-R.
- * Codes/labels as produced by hg_pack_sign_f32 / hg_pack_labels; d_db_codes must be 16-byte aligned.
+ * d_q_rows / d_db_rows are packed rows as produced by hg_pack_rows; d_db_rows must be 16-byte aligned.
  * Asynchronous on `stream`; the workspace must stay alive until the stream has drained. */
-int hg_hamming_map(const uint32_t* d_q_codes, const uint32_t* d_q_lab, int64_t nq,
-                   const uint32_t* d_db_codes, const uint32_t* d_db_lab, int64_t ndb,
+int hg_hamming_map(const uint32_t* d_q_rows, int64_t nq, const uint32_t* d_db_rows, int64_t ndb,
                    int b, int L, int64_t R, unsigned flags,
                    double* d_ap, uint32_t* d_ids, uint16_t* d_dist, int32_t* d_rel,
                    void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Diagnostics of the last hg_hamming_map run on this workspace (host copy, synchronises `stream`):
  * out[0] = queries that needed the exact two-pass path, out[1] = db splits P, out[2] = rows per split,
- * out[3] = entries per candidate bin, out[4] = queries per CTA tile, out[5] = sample rows used. */
+ * out[3] = entries per candidate bin, out[4] = queries per CTA tile, out[5] = sample rows used,
+ * out[6] = queries the exact path could not answer (always 0), out[7] = queries whose candidate distances
+ * spanned >= 32 values (redone by the full-width AP kernel). */
 int hg_hamming_map_stats(const void* d_workspace, size_t workspace_bytes, int64_t nq, int64_t ndb, int b, int L,
                          int64_t R, int64_t out[8], void* stream);
 

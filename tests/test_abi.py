@@ -31,7 +31,10 @@ def test_version_and_word_counts():
     assert lib.hg_version() >= 100
     assert [lib.hg_code_words(b) for b in (1, 32, 33, 48, 64, 96, 128, 129, 256)] == [1, 1, 2, 2, 2, 3, 4, 8, 8]
     assert lib.hg_code_words(0) == 0 and lib.hg_code_words(257) == 0
-    assert [lib.hg_label_words(L) for L in (1, 10, 32, 33, 81)] == [1, 1, 1, 2, 3]
+    assert [lib.hg_label_words(L) for L in (1, 10, 32, 33, 81, 128)] == [1, 1, 1, 2, 3, 4]
+    assert lib.hg_label_words(129) == 0
+    # row stride: code words + label words, rounded so the code words stay 8/16-byte aligned
+    assert [lib.hg_row_words(b, L) for b, L in ((32, 10), (48, 10), (64, 10), (96, 10), (128, 81), (256, 10))] == [2, 4, 4, 4, 8, 12]
     with pytest.raises(ValueError):
         _native.code_words(300)
 
@@ -41,9 +44,9 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.hg_hamming_map_workspace_bytes(10, 100, 64, 10, 101) == 0  # R > ndb
     assert lib.hg_hamming_map_workspace_bytes(10, 100, 300, 10, 10) == 0  # unsupported b
     assert lib.hg_hamming_map_workspace_bytes(10000, 1000000, 64, 10, 5000) > 0
-    rc = lib.hg_hamming_map(None, None, 4, None, None, 10, 64, 10, 11, 0, None, None, None, None, None, 0, None)
+    rc = lib.hg_hamming_map(None, 4, None, 10, 64, 10, 11, 0, None, None, None, None, None, 0, None)
     assert rc == _native.HG_ERANGE and b"exceeds" in lib.hg_last_error()
-    rc = lib.hg_pack_sign_f32(None, 4, 999, 999, None, None)
+    rc = lib.hg_pack_rows(None, 999, None, 8, 4, 999, 10, None, None, None)
     assert rc == _native.HG_EINVAL
     with pytest.raises(_native.HgError):
         _native.check(rc)

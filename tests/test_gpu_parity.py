@@ -51,28 +51,36 @@ def _check_against_c_oracle(hb, c_oracle, db, q, R, flags=0, ids=True, device=No
 # packers
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("b", [1, 31, 32, 33, 48, 64, 96, 100, 128, 129, 200, 256])
-def test_pack_sign_bit_exact(hb, b):
+def test_pack_rows_code_words_bit_exact(hb, b):
     from hashgan_b200 import _native
 
     rng = np.random.default_rng(b)
-    for n in (1, 7, 1000, 4099):
+    for n, L in ((1, 10), (7, 81), (1000, 10), (4099, 33)):
         feat = rng.normal(size=(n, b)).astype(np.float32)
         feat[rng.random((n, b)) < 0.05] = 0.0  # zero is "not positive" -> bit 0
-        got = hb.pack_codes(feat).cpu().numpy().view(np.uint32)
+        lab = (rng.random((n, L)) < 0.2).astype(np.int64)
+        got = hb.pack_rows(feat, lab).cpu().numpy().view(np.uint32)
         want = maps_oracle.pack_sign_bits(feat)
-        W = _native.code_words(b)
-        assert got.shape == (n, W)
+        want_l = maps_oracle.pack_label_bits(lab)
+        W, LW, Wr = _native.code_words(b), _native.label_words(L), _native.row_words(b, L)
+        assert got.shape == (n, Wr) and Wr >= W + LW
         assert np.array_equal(got[:, : want.shape[1]], want)
-        assert not got[:, want.shape[1]:].any()  # pad words are zero
+        assert not got[:, want.shape[1]:W].any()          # pad code words are zero
+        assert np.array_equal(got[:, W:W + LW], want_l)   # label words follow the code words
+        assert not got[:, W + LW:].any()                  # row padding is zero
 
 
-@pytest.mark.parametrize("L,dtype", [(1, np.int64), (10, np.int64), (10, np.int32), (32, np.int8), (33, np.uint8), (81, np.int64), (80, bool)])
-def test_pack_labels_bit_exact(hb, L, dtype):
+@pytest.mark.parametrize("L,dtype", [(1, np.int64), (10, np.int64), (10, np.int32), (32, np.int8), (33, np.uint8), (81, np.int64), (80, bool), (128, np.int64)])
+def test_pack_rows_label_words_bit_exact(hb, L, dtype):
+    from hashgan_b200 import _native
+
     rng = np.random.default_rng(L)
     for n in (1, 5, 1237):
         lab = (rng.random((n, L)) < 0.2).astype(dtype)
-        got = hb.pack_labels(lab).cpu().numpy().view(np.uint32)
-        assert np.array_equal(got, maps_oracle.pack_label_bits(lab.astype(np.int64)))
+        feat = rng.normal(size=(n, 64)).astype(np.float32)
+        got = hb.pack_rows(feat, lab).cpu().numpy().view(np.uint32)
+        W, LW = _native.code_words(64), _native.label_words(L)
+        assert np.array_equal(got[:, W:W + LW], maps_oracle.pack_label_bits(lab.astype(np.int64)))
 
 
 def test_bad_labels_are_rejected(hb):
@@ -190,6 +198,32 @@ def test_clustered_database_order(hb, c_oracle):
     _check_against_c_oracle(hb, c_oracle, db, q, 5000)
 
 
+def test_wide_distance_span_uses_full_width_counters(hb, c_oracle):
+    """Near-duplicates of the queries planted in a 128-bit database: candidate distances span 0..~50, more than the
+    32-value window of the fast AP kernel -> those queries are redone by the full-width variant."""
+    from hashgan_b200.synthetic import make_workload
+
+    wl, db, q = make_workload("C5", nq=200, ndb=150000)
+    rng = np.random.default_rng(77)
+    out = db.output.copy()
+    for i in range(0, 200, 2):  # every other query gets 6 planted neighbours at distances 0..5
+        for k in range(6):
+            row = int(rng.integers(0, len(out)))
+            out[row] = q.output[i]
+            flip = rng.choice(wl.b, size=k, replace=False)
+            out[row, flip] *= -1
+    db = NS(output=out, label=db.label)
+    m = hb.MAPs(2000)
+    m.collect_stats = True
+    ap, ids, dist = m.per_query_ap(db, q, want_ids=True)
+    ref_ap, _, ref_ids, ref_dist = c_oracle.hamming_map(db, q, 2000, want_ids=True)
+    assert np.array_equal(dist, ref_dist.astype(np.int32))
+    assert np.array_equal(ids, ref_ids.astype(np.int64))
+    assert np.array_equal(np.isnan(ap), np.isnan(ref_ap))
+    assert np.nanmax(np.abs(ap - ref_ap)) <= AP_TOL
+    assert m.last_stats["chunks"][0]["wide_queries"] >= 90
+
+
 @pytest.mark.parametrize("flags", [0, 1])
 def test_force_exact_equals_fast(hb, c_oracle, flags):
     from hashgan_b200.synthetic import make_workload
@@ -221,8 +255,10 @@ def test_reference_error_and_nan_behaviour(hb):
     before = q.label.copy()
     hb.MAPs(10).get_maps_by_feature(db, q)
     assert np.array_equal(before, q.label)
-    with pytest.raises(ValueError):
+    with pytest.raises(ValueError):  # hash length beyond HG_MAX_BITS
         hb.MAPs(10).get_maps_by_feature(NS(output=np.ones((50, 300), np.float32), label=db.label), NS(output=np.ones((4, 300), np.float32), label=q.label))
+    with pytest.raises(ValueError):  # label width beyond HG_MAX_LABELS
+        hb.MAPs(10).get_maps_by_feature(NS(output=db.output, label=np.ones((50, 200), np.int64)), NS(output=q.output, label=np.ones((4, 200), np.int64)))
 
 
 def test_inputs_may_be_torch_cuda_tensors(hb, c_oracle):
@@ -267,13 +303,15 @@ def test_c4_full_size_properties(hb, c_oracle):
     sampled bit-exact check against the C oracle."""
     import torch
     from hashgan_b200.synthetic import make_workload
-    from hashgan_b200.metric import hamming_map_device, pack_codes, pack_labels
+    from hashgan_b200 import _native
+    from hashgan_b200.metric import hamming_map_device, pack_rows
 
     wl, db, q = make_workload("C4")
-    dbc, dbl = pack_codes(db.output), pack_labels(db.label)
-    qc, ql = pack_codes(q.output), pack_labels(q.label)
+    dbr, qr = pack_rows(db.output, db.label), pack_rows(q.output, q.label)
+    W = _native.code_words(wl.b)
+    dbc, qc = dbr[:, :W], qr[:, :W]
     stats = {}
-    ap, ids, dist, rel = hamming_map_device(qc, ql, dbc, dbl, wl.b, wl.L, wl.R, want_ids=True, want_rel=True, stats=stats)
+    ap, ids, dist, rel = hamming_map_device(qr, dbr, wl.b, wl.L, wl.R, want_ids=True, want_rel=True, stats=stats)
     torch.cuda.synchronize()
     ids64 = ids.to(torch.int64) & 0xFFFFFFFF
     d32 = dist.to(torch.int32) & 0xFFFF
@@ -293,7 +331,7 @@ def test_c4_full_size_properties(hb, c_oracle):
     assert bool((pop == d32[sel]).all())
     # (4) the answer of a query does not depend on which other queries share its launch
     perm = torch.randperm(wl.nq, device=qc.device, generator=torch.Generator(device=qc.device).manual_seed(3))
-    ap_p, _, _, _ = hamming_map_device(qc[perm].contiguous(), ql[perm].contiguous(), dbc, dbl, wl.b, wl.L, wl.R)
+    ap_p, _, _, _ = hamming_map_device(qr[perm].contiguous(), dbr, wl.b, wl.L, wl.R)
     assert bool((ap_p == ap[perm]).all())
     # (5) sampled queries bit-exact against the C oracle
     pick = np.arange(0, wl.nq, 157)

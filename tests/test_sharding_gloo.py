@@ -44,23 +44,23 @@ def _worker(rank, world, port, ndb, nq, b, L, R, seed, out_dir):
         lo, hi = row_shard(ndb, rank, world)
         qlo, qhi = row_shard(nq, rank, world)
 
-        def pack_codes(x):
-            return torch.from_numpy(maps_oracle.pack_sign_bits(np.asarray(x)).view(np.int32))
+        W, LW = (b + 31) // 32, (L + 31) // 32
 
-        def pack_labels(x):
-            return torch.from_numpy(maps_oracle.pack_label_bits(np.asarray(x)).view(np.int32))
+        def pack_rows(out, lab):  # [code words | label words], the layout the device path all-gathers
+            rows = np.concatenate([maps_oracle.pack_sign_bits(np.asarray(out)), maps_oracle.pack_label_bits(np.asarray(lab))], 1)
+            return torch.from_numpy(np.ascontiguousarray(rows).view(np.int32))
 
-        def rank_fn(q_codes, q_lab, db_codes, db_lab, b_, L_, R_):
-            qn, dn = q_codes.numpy().view(np.uint32), db_codes.numpy().view(np.uint32)
-            qln, dln = q_lab.numpy().view(np.uint32), db_lab.numpy().view(np.uint32)
+        def rank_fn(q_rows, db_rows, b_, L_, R_):
+            qn, dn = q_rows.numpy().view(np.uint32), db_rows.numpy().view(np.uint32)
+            qc, ql = np.ascontiguousarray(qn[:, :W]), np.ascontiguousarray(qn[:, W:W + LW])
+            dc, dl_ = np.ascontiguousarray(dn[:, :W]), np.ascontiguousarray(dn[:, W:W + LW])
             ap = np.empty(len(qn), dtype=np.float64)
-            rc = co.lib.hgo_hamming_map(np.ascontiguousarray(qn).ctypes.data, np.ascontiguousarray(qln).ctypes.data, len(qn),
-                                        np.ascontiguousarray(dn).ctypes.data, np.ascontiguousarray(dln).ctypes.data, len(dn),
+            rc = co.lib.hgo_hamming_map(qc.ctypes.data, ql.ctypes.data, len(qn), dc.ctypes.data, dl_.ctypes.data, len(dn),
                                         b_, L_, R_, ap.ctypes.data, None, None, None, 1)
             assert rc == 0
             return torch.from_numpy(ap)
 
-        m = ShardedMAPs(R, pack_codes=pack_codes, pack_labels=pack_labels, rank_fn=rank_fn)
+        m = ShardedMAPs(R, pack_rows=pack_rows, rank_fn=rank_fn)
         ap = m.per_query_ap_device(NS(output=dbc[lo:hi], label=dl[lo:hi]), NS(output=qc[qlo:qhi], label=ql[qlo:qhi])).numpy()
         val = m.get_maps_by_feature(NS(output=dbc[lo:hi], label=dl[lo:hi]), NS(output=qc[qlo:qhi], label=ql[qlo:qhi]))
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ap=ap, val=val, counts=np.array(m.last_counts))
