@@ -48,7 +48,7 @@ def _peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
 
-    def __init__(self, index: int, period: float = 0.1):
+    def __init__(self, index: int, period: float = 0.01):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
