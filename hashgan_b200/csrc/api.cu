@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -113,7 +114,10 @@ struct Arena {
     size_t bytes = 0;
     double* pinned_ap = nullptr;
     size_t pinned_n = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t copy_stream = nullptr;  // H2D of the database chunks, overlapped with packing + ranking
+    cudaEvent_t chunk_ev[MapChunks::kMax] = {};
+    bool events = false;
     int device = -1;
 };
 static Arena g_arena;
@@ -127,10 +131,17 @@ static int arena_reserve(Arena& a, size_t bytes, size_t n_ap)
         if (a.ptr) cudaFree(a.ptr);
         if (a.pinned_ap) cudaFreeHost(a.pinned_ap);
         if (a.stream) cudaStreamDestroy(a.stream);
+        if (a.copy_stream) cudaStreamDestroy(a.copy_stream);
+        if (a.events) for (auto& e : a.chunk_ev) cudaEventDestroy(e);
         a = Arena();
         a.device = dev;
     }
     if (!a.stream) HG_CUDA_TRY(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+    if (!a.copy_stream) HG_CUDA_TRY(cudaStreamCreateWithFlags(&a.copy_stream, cudaStreamNonBlocking));
+    if (!a.events) {
+        for (auto& e : a.chunk_ev) HG_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        a.events = true;
+    }
     if (bytes > a.bytes) {
         if (a.ptr) HG_CUDA_TRY(cudaFree(a.ptr));
         a.ptr = nullptr; a.bytes = 0;
@@ -245,6 +256,8 @@ extern "C" int hg_release_cached(void)
     if (a.ptr) cudaFree(a.ptr);
     if (a.pinned_ap) cudaFreeHost(a.pinned_ap);
     if (a.stream) cudaStreamDestroy(a.stream);
+    if (a.copy_stream) cudaStreamDestroy(a.copy_stream);
+    if (a.events) for (auto& e : a.chunk_ev) cudaEventDestroy(e);
     a = hg::Arena();
     (void)cudaGetLastError();
     return HG_OK;
@@ -265,8 +278,11 @@ extern "C" int hg_maps_by_feature_host(const float* h_db_feat, const void* h_db_
     if (lab_elem_bytes != 8 && lab_elem_bytes != 4 && lab_elem_bytes != 1)
         return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: lab_elem_bytes must be 8, 4 or 1");
     if (!h_db_feat || !h_db_lab || !h_q_feat || !h_q_lab) return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: NULL pointer");
-    const size_t ws_bytes = hg_hamming_map_workspace_bytes(nq, ndb, b, L, R);
-    if (ws_bytes == 0) return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: sizes out of range");
+    hg::MapChunks chunks;
+    size_t ws_bytes = 0;
+    const char* kenv = getenv("HG_HOST_CHUNKS");
+    if (hg::plan_chunks(nq, ndb, b, L, R, (kenv && *kenv) ? atoi(kenv) : 6, &chunks, &ws_bytes) != HG_OK || ws_bytes == 0)
+        return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: sizes out of range (split the query batch)");
 
     std::lock_guard<std::mutex> lock(hg::g_arena_mu);
     hg::Arena& a = hg::g_arena;
@@ -296,10 +312,50 @@ extern "C" int hg_maps_by_feature_host(const float* h_db_feat, const void* h_db_
     HG_CUDA_TRY(cudaMemcpyAsync(d_qf, h_q_feat, sizeof(float) * (size_t)nq * b, cudaMemcpyHostToDevice, st));
     HG_CUDA_TRY(cudaMemcpyAsync(base + o_ql, h_q_lab, (size_t)lab_elem_bytes * nq * L, cudaMemcpyHostToDevice, st));
     if ((rc = hg_pack_rows(d_qf, b, base + o_ql, lab_elem_bytes, nq, b, L, d_qr, d_bad, st)) != HG_OK) return rc;
-    HG_CUDA_TRY(cudaMemcpyAsync(d_dbf, h_db_feat, sizeof(float) * (size_t)ndb * b, cudaMemcpyHostToDevice, st));
-    HG_CUDA_TRY(cudaMemcpyAsync(base + o_dbl, h_db_lab, (size_t)lab_elem_bytes * ndb * L, cudaMemcpyHostToDevice, st));
-    if ((rc = hg_pack_rows(d_dbf, b, base + o_dbl, lab_elem_bytes, ndb, b, L, d_dbr, d_bad, st)) != HG_OK) return rc;
-    if ((rc = hg_hamming_map(d_qr, nq, d_dbr, ndb, b, L, R, flags, d_ap, nullptr, nullptr, nullptr, base + o_ws, ws_bytes, st)) != HG_OK)
+
+    // Database: chunked H2D on the copy stream, each chunk packed and ranked on the compute stream as soon as it
+    // has landed, so the PCIe transfer (339 MB at C4) overlaps the select kernel instead of preceding it.
+    struct Pipe {
+        hg::Arena* a; hg::MapChunks ch; bool issued[hg::MapChunks::kMax]; bool pinned;
+        const float* h_feat; const char* h_lab; float* d_feat; char* d_lab; uint32_t* d_rows; int* d_bad;
+        int b, L, Wr, lab_bytes;
+        int issue(int k) {
+            if (issued[k]) return HG_OK;
+            const int64_t lo = ch.row_lo[k], n = ch.row_hi[k] - lo;
+            HG_CUDA_TRY(cudaMemcpyAsync(d_feat + lo * b, h_feat + lo * b, sizeof(float) * (size_t)n * b, cudaMemcpyHostToDevice, a->copy_stream));
+            HG_CUDA_TRY(cudaMemcpyAsync(d_lab + (size_t)lo * L * lab_bytes, h_lab + (size_t)lo * L * lab_bytes, (size_t)lab_bytes * n * L,
+                                        cudaMemcpyHostToDevice, a->copy_stream));
+            HG_CUDA_TRY(cudaEventRecord(a->chunk_ev[k], a->copy_stream));
+            issued[k] = true;
+            return HG_OK;
+        }
+        static int prepare(void* user, int k, int64_t lo, int64_t hi, cudaStream_t cst) {
+            Pipe* p = static_cast<Pipe*>(user);
+            int prc = p->issue(k);
+            if (prc != HG_OK) return prc;
+            // pageable host memory makes cudaMemcpyAsync block the host: issue one chunk ahead at most, after the
+            // previous chunk's kernels are queued; pinned memory was queued up front
+            HG_CUDA_TRY(cudaStreamWaitEvent(cst, p->a->chunk_ev[k], 0));
+            return hg_pack_rows(p->d_feat + lo * p->b, p->b, p->d_lab + (size_t)lo * p->L * p->lab_bytes, p->lab_bytes, hi - lo, p->b, p->L,
+                                p->d_rows + lo * p->Wr, p->d_bad, cst);
+        }
+    } pipe;
+    pipe.a = &a; pipe.h_feat = h_db_feat; pipe.h_lab = static_cast<const char*>(h_db_lab); pipe.d_feat = d_dbf; pipe.d_lab = base + o_dbl;
+    pipe.d_rows = d_dbr; pipe.d_bad = d_bad; pipe.b = b; pipe.L = L; pipe.Wr = Wr; pipe.lab_bytes = lab_elem_bytes;
+    for (bool& f : pipe.issued) f = false;
+    pipe.ch = chunks;
+    {
+        cudaPointerAttributes pa{}, pb{};
+        const bool ok = cudaPointerGetAttributes(&pa, h_db_feat) == cudaSuccess && cudaPointerGetAttributes(&pb, h_db_lab) == cudaSuccess;
+        (void)cudaGetLastError();
+        pipe.pinned = ok && pa.type == cudaMemoryTypeHost && pb.type == cudaMemoryTypeHost;
+    }
+    // the copy stream must not overtake the previous call's reads of these buffers: both streams were drained by
+    // the synchronize at the end of that call
+    if (pipe.pinned)
+        for (int k = 0; k < pipe.ch.K; ++k)
+            if ((rc = pipe.issue(k)) != HG_OK) return rc;
+    if ((rc = hg::hamming_map_chunked(d_qr, nq, d_dbr, ndb, b, L, R, flags, d_ap, base + o_ws, ws_bytes, st, &pipe.ch, &Pipe::prepare, &pipe)) != HG_OK)
         return rc;
     HG_CUDA_TRY(cudaMemcpyAsync(a.pinned_ap, d_ap, sizeof(double) * (size_t)nq, cudaMemcpyDeviceToHost, st));
     int* h_bad = reinterpret_cast<int*>(a.pinned_ap + nq);

@@ -39,6 +39,17 @@ struct PhaseTimer {
 };
 PhaseTimer& phase_timer();
 
+// chunked host pipeline (api.cu <-> rank.cu): database rows arrive chunk by chunk (whole splits per chunk)
+struct MapChunks {
+    static constexpr int kMax = 64;
+    int K = 0;
+    int64_t row_lo[kMax], row_hi[kMax];
+};
+typedef int (*PrepareRowsFn)(void* user, int chunk, int64_t row_lo, int64_t row_hi, cudaStream_t st);
+int plan_chunks(int64_t nq, int64_t ndb, int b, int L, int64_t R, int k_req, MapChunks* out, size_t* ws_bytes);
+int hamming_map_chunked(const uint32_t* q_rows, int64_t nq, const uint32_t* db_rows, int64_t ndb, int b, int L, int64_t R, unsigned flags,
+                        double* d_ap, void* ws, size_t ws_bytes, cudaStream_t st, const MapChunks* chunks, PrepareRowsFn prepare, void* user);
+
 struct DeviceFacts {
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     size_t l2_bytes = 0;

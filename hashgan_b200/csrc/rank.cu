@@ -60,7 +60,7 @@ static int env_int(const char* name, int fallback)
     return (v && *v) ? atoi(v) : fallback;
 }
 
-static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R)
+static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas_mult = 1)
 {
     Plan p;
     p.W = hg_code_words(b);
@@ -80,7 +80,7 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R)
     p.TILE = tile_rows_for(p.Wr);
     // db splits: one wave of CTAs that are all resident (grid ~ SMs x CTAs/SM), split length a multiple of the
     // tile, at most 2^21 rows
-    const int64_t target_ctas = (int64_t)sms * env_int("HG_SELECT_CTAS_PER_SM", kSelectCtasPerSm);
+    const int64_t target_ctas = (int64_t)sms * env_int("HG_SELECT_CTAS_PER_SM", kSelectCtasPerSm) * ctas_mult;
     int64_t P0 = std::max<int64_t>(1, ceil_div(target_ctas, p.nqt));
     int64_t SL = round_up(ceil_div(ndb, P0), p.TILE);
     SL = std::min<int64_t>(SL, kMaxSplitRows);
@@ -280,6 +280,7 @@ struct SelectParams {
     const int* n_active;  // EXACT: fail count
     const int* qlist;     // EXACT: fail list
     int P, Wr, LW, TILE;
+    int split0;  // first database split of this launch (chunked host pipeline), grid.y splits from here
     int64_t SL, R;
     uint32_t* lists;
     uint32_t cap;              // fast path: bin = q*P + s at lists + bin*cap
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams p)
     uint32_t* s_qlab = smem + 2 * tile_words;  // only used when !LW1
 
     const int tid = threadIdx.x;
-    const int split = blockIdx.y;
+    const int split = p.split0 + (int)blockIdx.y;
     const int64_t n_act = EXACT ? (int64_t)*p.n_active : p.nq;
     const int64_t slot0 = (int64_t)blockIdx.x * TQ;
     if (slot0 >= n_act) return;
@@ -773,9 +774,9 @@ static int launch_hist(const HistParams& hp, int64_t n_slots_max, int n_chunks, 
 }
 
 template <int W, bool EXACT, bool LW1>
-static int launch_select_q(const SelectParams& sp, const Plan& pl, cudaStream_t st)
+static int launch_select_q(const SelectParams& sp, const Plan& pl, int n_splits, cudaStream_t st)
 {
-    dim3 grid((unsigned)pl.nqt, (unsigned)pl.P);
+    dim3 grid((unsigned)pl.nqt, (unsigned)n_splits);
     // <= 16 KB of tiles (+ <= 8 KB of query label words in the generic-label variant): no opt-in needed
     const size_t smem = sizeof(uint32_t) * (2 * (size_t)pl.TILE * pl.Wr + (LW1 ? 0 : (size_t)pl.LW * pl.TQ));
     switch (pl.QT) {
@@ -789,9 +790,9 @@ static int launch_select_q(const SelectParams& sp, const Plan& pl, cudaStream_t 
 }
 
 template <int W, bool EXACT>
-static int launch_select_w(const SelectParams& sp, const Plan& pl, cudaStream_t st)
+static int launch_select_w(const SelectParams& sp, const Plan& pl, int n_splits, cudaStream_t st)
 {
-    return pl.LW == 1 ? launch_select_q<W, EXACT, true>(sp, pl, st) : launch_select_q<W, EXACT, false>(sp, pl, st);
+    return pl.LW == 1 ? launch_select_q<W, EXACT, true>(sp, pl, n_splits, st) : launch_select_q<W, EXACT, false>(sp, pl, n_splits, st);
 }
 
 template <bool WINDOW>
@@ -824,8 +825,42 @@ static int launch_ap(ApParams ap, int64_t n_slots_max, cudaStream_t st)
 }
 
 template <int W>
-static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_rows, unsigned flags, double* d_ap, uint32_t* d_ids, uint16_t* d_dist, int32_t* d_rel, char* ws, cudaStream_t st)
+static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_rows, unsigned flags, double* d_ap, uint32_t* d_ids, uint16_t* d_dist, int32_t* d_rel, char* ws, cudaStream_t st,
+                   const MapChunks* chunks = nullptr, PrepareRowsFn prepare = nullptr, void* user = nullptr)
 {
+    // Chunked mode (host pipeline): the database rows of chunk k become valid when prepare(k) has been enqueued
+    // on `st`; thresholds are estimated from a sample of chunk 0, select runs chunk by chunk behind the copies.
+    int K = (chunks && prepare) ? chunks->K : 1;
+    int64_t sample_stride = pl.seg_stride, sample_nseg = pl.n_seg, sample_rows = pl.sample_rows;
+    int sample_spc = pl.seg_per_chunk, sample_chunks = pl.n_chunks;
+    int prepared = 0;
+    auto prepare_upto = [&](int k_end) -> int {
+        for (; prepared < k_end; ++prepared) {
+            int prc = prepare(user, prepared, chunks->row_lo[prepared], chunks->row_hi[prepared], st);
+            if (prc != HG_OK) return prc;
+        }
+        return HG_OK;
+    };
+    if (K > 1) {
+        if (pl.sample_rows >= pl.ndb || (flags & HG_FLAG_FORCE_EXACT)) {
+            int prc = prepare_upto(K);  // the estimate needs the whole database: no overlap possible
+            if (prc != HG_OK) return prc;
+            K = 1;
+        } else {
+            const int64_t avail_tiles = (chunks->row_hi[0] - chunks->row_lo[0]) / pl.TILE;  // chunk 0 = whole splits = whole tiles
+            sample_nseg = std::min<int64_t>(pl.n_seg, std::max<int64_t>(1, avail_tiles));
+            sample_stride = std::max<int64_t>(1, avail_tiles / sample_nseg) * pl.TILE;
+            sample_rows = sample_nseg * pl.TILE;
+            sample_spc = (int)ceil_div(sample_nseg, std::max<int64_t>(1, std::min<int64_t>(sample_nseg, pl.n_chunks)));
+            sample_chunks = (int)ceil_div(sample_nseg, sample_spc);
+            int prc = prepare_upto(1);
+            if (prc != HG_OK) return prc;
+        }
+    } else if (chunks && prepare) {
+        int prc = prepare_upto(chunks->K);
+        if (prc != HG_OK) return prc;
+    }
+
     int* ctrl = reinterpret_cast<int*>(ws + pl.off_ctrl);
     int* thr = reinterpret_cast<int*>(ws + pl.off_thr);
     int* thr2 = reinterpret_cast<int*>(ws + pl.off_thr2);
@@ -860,13 +895,13 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
         HistParams hp{};
         hp.q_rows = q_rows; hp.db_rows = db_rows; hp.nq = pl.nq; hp.ndb = pl.ndb; hp.b = pl.b; hp.Wr = pl.Wr;
         hp.n_active = nullptr; hp.qlist = nullptr;
-        hp.seg_stride = pl.seg_stride; hp.n_seg = pl.n_seg; hp.seg_rows = pl.TILE; hp.seg_per_chunk = pl.seg_per_chunk;
+        hp.seg_stride = sample_stride; hp.n_seg = sample_nseg; hp.seg_rows = pl.TILE; hp.seg_per_chunk = sample_spc;
         hp.out = hist_s; hp.out_chunks = 1;
-        if ((rc = launch_hist<W>(hp, pl.nq, pl.n_chunks, st)) != HG_OK) return rc;
+        if ((rc = launch_hist<W>(hp, pl.nq, sample_chunks, st)) != HG_OK) return rc;
     }
     // 2. thresholds
     timer.mark(kPhaseThreshold, st);
-    thr_kernel<<<(unsigned)ceil_div(pl.nq, 256), 256, 0, st>>>(hist_s, pl.nq, pl.b, pl.sample_rows, pl.ndb, pl.R, kSampleZ,
+    thr_kernel<<<(unsigned)ceil_div(pl.nq, 256), 256, 0, st>>>(hist_s, pl.nq, pl.b, sample_rows, pl.ndb, pl.R, kSampleZ,
                                                                force_exact ? 1 : 0, thr);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
@@ -878,7 +913,17 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
         sp.n_active = nullptr; sp.qlist = nullptr; sp.P = pl.P; sp.SL = pl.SL; sp.R = pl.R;
         sp.lists = lists; sp.cap = pl.cap; sp.bin_off2 = nullptr; sp.bin_cap2 = nullptr; sp.quota2 = nullptr;
         sp.bin_cnt = bin_cnt;
-        if ((rc = launch_select_w<W, false>(sp, pl, st)) != HG_OK) return rc;
+        if (K > 1) {
+            for (int k = 0; k < K; ++k) {
+                if ((rc = prepare_upto(k + 1)) != HG_OK) return rc;
+                sp.split0 = (int)(chunks->row_lo[k] / pl.SL);
+                const int n_splits = (int)ceil_div(chunks->row_hi[k] - chunks->row_lo[k], pl.SL);
+                if ((rc = launch_select_w<W, false>(sp, pl, n_splits, st)) != HG_OK) return rc;
+            }
+        } else {
+            sp.split0 = 0;
+            if ((rc = launch_select_w<W, false>(sp, pl, pl.P, st)) != HG_OK) return rc;
+        }
     } else {
         HG_CUDA_TRY(cudaMemsetAsync(bin_cnt, 0, sizeof(uint32_t) * (size_t)pl.nq * pl.P, st));
     }
@@ -923,8 +968,8 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
         sp.q_rows = q_rows; sp.db_rows = db_rows; sp.nq = pl.nq; sp.ndb = pl.ndb; sp.Wr = pl.Wr; sp.LW = pl.LW; sp.TILE = pl.TILE; sp.thr = thr2;
         sp.n_active = n_fail; sp.qlist = fail_list; sp.P = pl.P; sp.SL = pl.SL; sp.R = pl.R;
         sp.lists = lists; sp.cap = 0; sp.bin_off2 = bin_off2; sp.bin_cap2 = bin_cap2; sp.quota2 = quota2;
-        sp.bin_cnt = bin_cnt2;
-        if ((rc = launch_select_w<W, true>(sp, pl, st)) != HG_OK) return rc;
+        sp.bin_cnt = bin_cnt2; sp.split0 = 0;
+        if ((rc = launch_select_w<W, true>(sp, pl, pl.P, st)) != HG_OK) return rc;
 
         ApParams ap{};
         ap.nq = pl.nq; ap.n_active = n_fail; ap.qlist = fail_list; ap.bins_by_slot = 1; ap.P = pl.P; ap.b = pl.b; ap.SL = pl.SL; ap.R = pl.R;
@@ -935,6 +980,43 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
     }
     timer.mark(kNumPhases, st);
     return HG_OK;
+}
+
+// ---- internal entry points used by the pipelined host path (api.cu) ---------------------------------------
+// The chunked path launches select once per chunk: it uses kChunkCtasMult x more (smaller) splits so that every
+// launch still fills the SMs.
+constexpr int kChunkCtasMult = 4;
+
+int plan_chunks(int64_t nq, int64_t ndb, int b, int L, int64_t R, int k_req, MapChunks* out, size_t* ws_bytes)
+{
+    const Plan pl = make_plan(nq, ndb, b, L, R, kChunkCtasMult);
+    if (!pl.ok || !out) return fail(HG_EINVAL, "plan_chunks: sizes out of range");
+    if (ws_bytes) *ws_bytes = pl.total;
+    int K = std::max(1, std::min(std::min(k_req, pl.P), MapChunks::kMax));
+    out->K = K;
+    for (int k = 0; k < K; ++k) {
+        const int64_t s_lo = (int64_t)k * pl.P / K, s_hi = (int64_t)(k + 1) * pl.P / K;
+        out->row_lo[k] = s_lo * pl.SL;
+        out->row_hi[k] = std::min<int64_t>(s_hi * pl.SL, ndb);
+    }
+    return HG_OK;
+}
+
+int hamming_map_chunked(const uint32_t* q_rows, int64_t nq, const uint32_t* db_rows, int64_t ndb, int b, int L, int64_t R, unsigned flags,
+                        double* d_ap, void* ws, size_t ws_bytes, cudaStream_t st, const MapChunks* chunks, PrepareRowsFn prepare, void* user)
+{
+    const Plan pl = make_plan(nq, ndb, b, L, R, kChunkCtasMult);
+    if (!pl.ok) return fail(HG_EINVAL, "hamming_map_chunked: sizes out of range");
+    if (ws_bytes < pl.total) return fail(HG_ENOMEM, "hamming_map_chunked: workspace %zu B < required %zu B", ws_bytes, pl.total);
+    char* w = static_cast<char*>(ws);
+    switch (pl.W) {
+        case 1: return run_map<1>(pl, q_rows, db_rows, flags, d_ap, nullptr, nullptr, nullptr, w, st, chunks, prepare, user);
+        case 2: return run_map<2>(pl, q_rows, db_rows, flags, d_ap, nullptr, nullptr, nullptr, w, st, chunks, prepare, user);
+        case 3: return run_map<3>(pl, q_rows, db_rows, flags, d_ap, nullptr, nullptr, nullptr, w, st, chunks, prepare, user);
+        case 4: return run_map<4>(pl, q_rows, db_rows, flags, d_ap, nullptr, nullptr, nullptr, w, st, chunks, prepare, user);
+        case 8: return run_map<8>(pl, q_rows, db_rows, flags, d_ap, nullptr, nullptr, nullptr, w, st, chunks, prepare, user);
+        default: return fail(HG_EINVAL, "hamming_map_chunked: unsupported word count %d", pl.W);
+    }
 }
 
 }  // namespace hg

@@ -256,10 +256,75 @@ class MAPs:
             q_rows = pack_rows(query.output, query.label, device, bad)
         return device, bad, db_rows, q_rows, b, L
 
+    def _host_call(self, database, query):
+        """Host arrays in -> per-query AP out through ONE C call (hg_maps_by_feature_host): chunked H2D on a copy
+        stream overlapped with packing and ranking.  Returns None when the inputs are not plain host buffers (CUDA
+        tensors) or the batch needs query chunking; the caller then takes the device path."""
+        torch = _torch()
+        device = _require_cuda(torch, self.device)
+
+        def host_view(x, kinds):
+            if isinstance(x, torch.Tensor):
+                if x.device.type != "cpu" or not x.is_contiguous():
+                    return None
+                x = x.numpy()  # shares memory (pinned stays pinned)
+            a = np.asarray(x)
+            if "f4" not in kinds and a.dtype.kind not in "iub":
+                raise TypeError(f"labels must be an integer 0/1 matrix, got dtype {a.dtype}")
+            if a.dtype == np.bool_:
+                a = a.view(np.int8)
+            elif a.dtype == np.uint8 and "u1" in kinds:
+                a = a.view(np.int8)
+            if a.dtype.str[1:] not in kinds:
+                a = a.astype(np.float32 if "f4" in kinds else np.int64)
+            return np.ascontiguousarray(a)
+
+        arrs = [host_view(database.output, ("f4",)), host_view(database.label, ("i8", "i4", "i1", "u1")),
+                host_view(query.output, ("f4",)), host_view(query.label, ("i8", "i4", "i1", "u1"))]
+        if any(a is None for a in arrs):
+            return None
+        db_f, db_l, q_f, q_l = arrs
+        if db_f.ndim != 2 or q_f.ndim != 2 or db_l.ndim != 2 or q_l.ndim != 2:
+            raise ValueError("output must be [N, b] and label [N, L]")
+        if db_f.shape[1] != q_f.shape[1]:
+            raise ValueError(f"shapes {q_f.shape} and {db_f.shape} not aligned: hash lengths differ")
+        if db_l.shape[1] != q_l.shape[1]:
+            raise ValueError(f"label widths differ: database {db_l.shape[1]}, query {q_l.shape[1]}")
+        if db_f.shape[0] != db_l.shape[0] or q_f.shape[0] != q_l.shape[0]:
+            raise ValueError("output and label row counts differ")
+        if q_l.dtype != db_l.dtype:
+            q_l, db_l = q_l.astype(np.int64), db_l.astype(np.int64)
+        nq, ndb, b, L, R = q_f.shape[0], db_f.shape[0], db_f.shape[1], db_l.shape[1], int(self.R)
+        _native.code_words(b)
+        _native.label_words(L)
+        if R > ndb:
+            raise ValueError(f"operands could not be broadcast together: R={R} exceeds the database size {ndb}")
+        if R <= 0:
+            raise ValueError("R must be positive")
+        lib = _native.lib()
+        if nq == 0:
+            return np.empty((0,), dtype=np.float64)
+        need = lib.hg_hamming_map_workspace_bytes(nq, ndb, b, L, R)
+        if need == 0 or 2 * need > self.workspace_limit:
+            return None  # needs query chunking: device path
+        out = C.c_double(0.0)
+        ap = np.empty((nq,), dtype=np.float64)
+        with torch.cuda.device(device):
+            rc = lib.hg_maps_by_feature_host(db_f.ctypes.data, db_l.ctypes.data, ndb, q_f.ctypes.data, q_l.ctypes.data, nq,
+                                             b, L, db_l.dtype.itemsize, R, self.flags, C.byref(out), ap.ctypes.data)
+        if rc == _native.HG_ELABEL:
+            raise ValueError("labels must be 0/1 integers (lib/metric.py:17-19 is only defined for 0/1 labels)")
+        _native.check(rc)
+        return ap
+
     def per_query_ap(self, database, query, *, want_ids: bool = False):
         """Per-query AP@R as a NumPy float64 vector (NaN where the reference would skip the query).
         With ``want_ids`` also returns (ids [Nq, R] int64, dist [Nq, R] int32) in rank order."""
         database, query = _as_record(database), _as_record(query)
+        if not want_ids and not self.collect_stats:
+            host = self._host_call(database, query)
+            if host is not None:
+                return host
         device, bad, db_rows, q_rows, b, L = self._pack_all(database, query)
         R = int(self.R)
         self.last_stats = {} if self.collect_stats else None
