@@ -38,6 +38,7 @@ SIGNATURES = {
     "hg_maps_by_feature_host": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _int, _i64, _u32,
                                        C.POINTER(C.c_double), _vp]),
     "hg_release_cached": (_int, []),
+    "hg_gemm_tf32": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _int, _int, _int, _int, _vp]),
     "hg_popc_peak": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), _int, _vp]),
 }
 

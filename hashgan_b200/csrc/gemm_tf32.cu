@@ -1,0 +1,248 @@
+// Dense layer GEMM on the 5th-generation tensor cores:  C[M,N] = act(A[M,K] * Bt[N,K]^T + bias[N])
+//
+// Used for the fully connected layers of the AlexNet hash head (lib/architecture.py:363-382: fc6 9216->4096,
+// fc7 4096->4096, fc8 = lib/ops.py:287-302 `linear` 4096->HASH_DIM).  fp32 operands are consumed as TF32 by
+// tcgen05.mma (kind::tf32), accumulated in fp32 in tensor memory.
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0      : TMA producer  -- cp.async.bulk.tensor.2d of a 128x32 A tile and a BNx32 B tile (128-byte rows,
+//                 SWIZZLE_128B) into a 4-stage shared-memory ring, completion on mbarriers
+//   warp 1      : allocates BN TMEM columns, issues tcgen05.mma (one elected thread; 4 MMAs of K=8 per stage),
+//                 tcgen05.commit releases the stage / signals the epilogue
+//   warps 2..5  : epilogue -- tcgen05.ld 32 lanes x 32 columns, + bias, ReLU, float4 stores
+#include "common.cuh"
+
+#include <cuda.h>
+
+namespace hg {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 32;  // fp32 elements = 128 bytes = one swizzle atom row
+constexpr int kGemmStages = 4;
+constexpr int kGemmThreads = 192;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t mbar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// shared-memory matrix descriptor: K-major operand, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell), bits [46,48)
+    d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B, bits [61,64)
+    return d;
+}
+
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = BN
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_c),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, bool RELU>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const float* __restrict__ bias,
+                 float* __restrict__ C, int M, int N, int K, int ldc)
+{
+    extern __shared__ __align__(1024) uint8_t gsm[];
+    constexpr uint32_t A_BYTES = kGemmBM * kGemmBK * 4;  // 16 KB
+    constexpr uint32_t B_BYTES = BN * kGemmBK * 4;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    // the dynamic shared memory base is only 16-byte aligned by contract: round up to the 1024 bytes SWIZZLE_128B needs
+    const uint32_t base = (smem_u32(gsm) + 1023u) & ~1023u;
+    __shared__ __align__(8) uint64_t full_bar[kGemmStages], empty_bar[kGemmStages], tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * kGemmBM, n0 = blockIdx.x * BN;
+    const int nkb = K / kGemmBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {  // TMEM allocation: one warp, power-of-two column count >= 32
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kGemmStages;
+                mbar_wait(&empty_bar[s], (uint32_t)(((kb / kGemmStages) & 1) ^ 1));
+                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+                tma_load_2d(sa, &tmap_a, smem_u32(&full_bar[s]), kb * kGemmBK, m0);
+                tma_load_2d(sb, &tmap_b, smem_u32(&full_bar[s]), kb * kGemmBK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(kGemmBM, BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kGemmStages;
+                mbar_wait(&full_bar[s], (uint32_t)((kb / kGemmStages) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+                const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sb);
+#pragma unroll
+                for (int k = 0; k < kGemmBK / 8; ++k)  // UMMA_K = 8 tf32 = 32 bytes: advance the start address by 2 (x16 B)
+                    umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                umma_commit(&empty_bar[s]);  // the stage may be refilled once these MMAs have read it
+            }
+            umma_commit(&tmem_full_bar);     // accumulator complete
+        }
+    } else {
+        // epilogue warps 2..5: TMEM lane quarter = warp % 4
+        const int quarter = warp & 3;
+        mbar_wait(&tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + quarter * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+                float* crow = C + (size_t)row * ldc + n0 + c0;
+                const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (n0 + c0 + 32 <= N);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float v[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int n = n0 + c0 + j + t;
+                        float x = __uint_as_float(r[j + t]) + ((bias != nullptr && n < N) ? __ldg(bias + n) : 0.0f);
+                        v[t] = RELU ? fmaxf(x, 0.0f) : x;
+                    }
+                    if (vec) {
+                        *reinterpret_cast<float4*>(crow + j) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (n0 + c0 + j + t < N) crow[j + t] = v[t];
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// [rows, K] fp32 row-major (row stride ld elements) -> 2-D tensor map, box = 32 x box_rows, 128-byte swizzle, OOB -> 0
+static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t K, int64_t ld, int box_rows)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(HG_ECUDA, "gemm_tf32: cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HG_ECUDA, "gemm_tf32: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return HG_OK;
+}
+
+template <int BN, bool RELU>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, float* C, int M, int N, int K, int ldc, cudaStream_t st)
+{
+    const size_t smem = (size_t)kGemmStages * (kGemmBM + BN) * kGemmBK * 4 + 1024;
+    static thread_local bool configured = false;
+    if (!configured) {
+        HG_CUDA_TRY(cudaFuncSetAttribute(gemm_tf32_kernel<BN, RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, kGemmBM));
+    gemm_tf32_kernel<BN, RELU><<<grid, kGemmThreads, smem, st>>>(ta, tb, bias, C, M, N, K, ldc);
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    return HG_OK;
+}
+
+int gemm_tf32(const float* A, int64_t lda, const float* Bt, int64_t ldb, const float* bias, float* C, int64_t ldc, int M, int N, int K, int relu,
+              cudaStream_t st)
+{
+    if (M <= 0 || N <= 0) return HG_OK;
+    if (K <= 0 || (K % kGemmBK) != 0) return fail(HG_EINVAL, "gemm_tf32: K=%d must be a positive multiple of %d", K, kGemmBK);
+    if (!A || !Bt || !C) return fail(HG_EINVAL, "gemm_tf32: NULL pointer");
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(Bt) & 15) || (lda % 4) || (ldb % 4))
+        return fail(HG_EINVAL, "gemm_tf32: A / Bt must be 16-byte aligned with row strides that are multiples of 4 floats");
+    const int BN = N <= 64 ? 64 : 128;
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_map(&ta, A, M, K, lda, kGemmBM)) != HG_OK) return rc;
+    if ((rc = make_map(&tb, Bt, N, K, ldb, BN)) != HG_OK) return rc;
+    if (BN == 64) return relu ? launch_gemm<64, true>(ta, tb, bias, C, M, N, K, (int)ldc, st) : launch_gemm<64, false>(ta, tb, bias, C, M, N, K, (int)ldc, st);
+    return relu ? launch_gemm<128, true>(ta, tb, bias, C, M, N, K, (int)ldc, st) : launch_gemm<128, false>(ta, tb, bias, C, M, N, K, (int)ldc, st);
+}
+
+}  // namespace hg
+
+extern "C" int hg_gemm_tf32(const float* d_a, int64_t lda, const float* d_bt, int64_t ldb, const float* d_bias, float* d_c, int64_t ldc, int M,
+                            int N, int K, int relu, void* stream)
+{
+    if (!hg::device_facts().ok) return hg::fail(HG_ECUDA, "hg_gemm_tf32: no CUDA device");
+    return hg::gemm_tf32(d_a, lda, d_bt, ldb, d_bias, d_c, ldc, M, N, K, relu, (cudaStream_t)stream);
+}

@@ -109,6 +109,15 @@ int hg_maps_by_feature_host(const float* h_db_feat, const void* h_db_lab, int64_
                             double* map_out, double* h_ap_out);
 int hg_release_cached(void);
 
+/* Dense layer on the tensor cores (tcgen05.mma kind::tf32, fp32 accumulation in TMEM):
+ *     C[M,N] = act(A[M,K] * Bt[N,K]^T + bias[N]),  act = ReLU when relu != 0
+ * Replaces tf.matmul + tf.nn.bias_add (+ tf.nn.relu) of the fully connected layers, lib/architecture.py:363-377
+ * (fc6, fc7) and lib/ops.py:287-302 (`linear`, fc8).  A and Bt are fp32 row-major with row strides lda / ldb
+ * (elements, multiples of 4; 16-byte aligned bases); Bt is the weight matrix TRANSPOSED to [N, K].  K % 32 == 0.
+ * d_bias may be NULL.  Asynchronous on `stream`. */
+int hg_gemm_tf32(const float* d_a, int64_t lda, const float* d_bt, int64_t ldb, const float* d_bias, float* d_c, int64_t ldc,
+                 int M, int N, int K, int relu, void* stream);
+
 /* Integer-pipe microbenchmark: measured XOR+POPC word-ops per second of this GPU (the binding roofline
  * of the Hamming kernel).  Runs `iters` dependent-free popc chains on every SM. */
 int hg_popc_peak(double* wordops_per_s, double* ms, int iters, void* stream);
