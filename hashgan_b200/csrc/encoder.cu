@@ -1,0 +1,365 @@
+// AlexNet hash-head forward (stage='val'): uint8 images -> [n, HASH_DIM] float32 in (-1, 1).
+//
+// Restates, as hand-written CUDA, the evaluation graph of the reference:
+//   main.py:144-148               normalize: 2*x/256 - 1   (de-quantisation noise off: deterministic mode)
+//   lib/util.py:12-21             (x+1)*255.99/2, NCHW -> NHWC, tf.image.resize_bilinear -> 256x256 (TF1 legacy sampling)
+//   lib/architecture.py:215-249   10 crops 227x227 (5 of the left-right flipped image, 5 plain), minus the channel mean
+//   lib/architecture.py:253-359   conv1..conv5 (+bias, ReLU), 3x3/2 max pools, LRN when TRAIN.WGAN_SCALE == 0
+//   lib/architecture.py:363-382   fc6, fc7 (+bias, ReLU; eval-time dropout off in deterministic mode), fc8 = lib/ops.py:183-304
+//   lib/architecture.py:386-389   tanh, mean over the 10 crops
+// Layout: activations NHWC fp32 (as in the reference), conv weights HWIO (as stored by the reference's .npy / ckpt),
+// fc weights transposed to [N, K] once so that the tensor-core GEMM reads both operands K-major.
+// fc6-8 run on tcgen05 (gemm_tf32.cu); conv1-5 are fp32 implicit-GEMM kernels on the CUDA cores (tensor-core conv
+// is a "next" row).
+#include "common.cuh"
+
+namespace hg {
+
+int gemm_tf32(const float* A, int64_t lda, const float* Bt, int64_t ldb, const float* bias, float* C, int64_t ldc, int M, int N, int K, int relu,
+              cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------------
+// K0-K4: normalize + scale + legacy bilinear resize to 256x256 + 10-crop (+flip) + mean subtraction, fused.
+// in : uint8 [n, 3, wh, wh] (RGB planes, the loader's flattened layout, lib/dataloader.py:110-113)
+// out: float [10n, 227, 227, 3]; crop block k holds rows k*n .. (k+1)*n (lib/architecture.py:242-244)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float scaled_pixel(unsigned char v)
+{
+    const float x = 2.0f * (float)v / 256.0f - 1.0f;  // main.py:146
+    return (x + 1.0f) * 255.99f / 2.0f;               // lib/util.py:13
+}
+
+__global__ void __launch_bounds__(256) prep_crops_kernel(const unsigned char* __restrict__ img, int n, int wh, float* __restrict__ out)
+{
+    const int64_t total = (int64_t)10 * n * 227 * 227;
+    const float scale = (float)wh / 256.0f;  // tf.image.resize_bilinear, align_corners=False, no half-pixel centres
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % 227);
+        const int y = (int)((i / 227) % 227);
+        const int64_t nn = i / (227 * 227);
+        const int k = (int)(nn / n), b = (int)(nn % n);
+        const int kk = k % 5;
+        const int oy = (kk == 1 || kk == 2) ? 28 : (kk == 4 ? 14 : 0);  // (0,0) (28,28) (28,0) (0,28) (14,14)
+        const int ox = (kk == 1 || kk == 3) ? 28 : (kk == 4 ? 14 : 0);
+        const int Y = oy + y;
+        const int X = (k < 5) ? 255 - (ox + x) : ox + x;  // crops 0..4 are taken from the left-right flipped image
+        const float fy = (float)Y * scale, fx = (float)X * scale;
+        const int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
+        const int y1 = min((int)ceilf(fy), wh - 1), x1 = min((int)ceilf(fx), wh - 1);
+        const float ly = fy - (float)y0, lx = fx - (float)x0;
+        const float mean[3] = {103.939f, 116.779f, 123.68f};
+        float* o = out + i * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const unsigned char* p = img + ((int64_t)b * 3 + c) * wh * wh;
+            const float tl = scaled_pixel(p[y0 * wh + x0]), tr = scaled_pixel(p[y0 * wh + x1]);
+            const float bl = scaled_pixel(p[y1 * wh + x0]), br = scaled_pixel(p[y1 * wh + x1]);
+            const float top = tl + (tr - tl) * lx;
+            const float bot = bl + (br - bl) * lx;
+            o[c] = (top + (bot - top) * ly) - mean[c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5/K8/K10-12: convolution as an implicit GEMM on the CUDA cores, fused bias + ReLU.
+//   in  [N, H, W, C]  (NHWC), weights [KH, KW, C/groups, Cout] (HWIO), out [N, Ho, Wo, Cout]
+//   tile: 64 output pixels x BN output channels of one group, K chunks of 16; 256 threads, 4 x (BN/16) outputs each.
+// ---------------------------------------------------------------------------------------------------------
+struct ConvParams {
+    const float* in;
+    const float* w;
+    const float* bias;
+    float* out;
+    int N, H, W, C, KH, KW, stride, pad, Ho, Wo, Cout, groups;
+};
+
+template <int BN, bool VEC>
+__global__ void __launch_bounds__(256) conv_relu_kernel(ConvParams p)
+{
+    constexpr int BM = 64, BK = 16, TN = BN / 16;
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN];
+    const int tid = threadIdx.x;
+    const int g = blockIdx.z;
+    const int Cg = p.C / p.groups, Cog = p.Cout / p.groups;
+    const int K = p.KH * p.KW * Cg;
+    const int64_t M = (int64_t)p.N * p.Ho * p.Wo;
+    const int64_t m0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int tm = tid / 16, tn = tid % 16;  // 16 x 16 threads: 4 pixels x TN channels each
+
+    // A-tile loader: thread -> pixel (tid / 4), 4 consecutive k starting at (tid % 4) * 4
+    const int a_m = tid >> 2, a_k = (tid & 3) * 4;
+    const int64_t am = m0 + a_m;
+    const bool a_valid = am < M;
+    int a_n = 0, a_oy = 0, a_ox = 0;
+    if (a_valid) {
+        a_ox = (int)(am % p.Wo);
+        a_oy = (int)((am / p.Wo) % p.Ho);
+        a_n = (int)(am / ((int64_t)p.Wo * p.Ho));
+    }
+    const float* in_n = p.in + (int64_t)a_n * p.H * p.W * p.C + g * Cg;
+    // B-tile loader: thread -> k row (tid / 16), 4 * (BN/64) ... handled as TN floats at column tn*TN
+    const int b_k = tid >> 4, b_n = (tid & 15) * TN;
+
+    float acc[4][TN];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        // ---- gather A ----
+        float av[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a_valid) {
+            const int k = k0 + a_k;
+            if (VEC) {  // Cg % 4 == 0: the 4 values share (ky, kx) and are contiguous in memory
+                if (k < K) {
+                    const int ci = k % Cg, kx = (k / Cg) % p.KW, ky = k / (Cg * p.KW);
+                    const int iy = a_oy * p.stride + ky - p.pad, ix = a_ox * p.stride + kx - p.pad;
+                    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(in_n + ((int64_t)iy * p.W + ix) * p.C + ci));
+                        av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int kk = k + t;
+                    if (kk < K) {
+                        const int ci = kk % Cg, kx = (kk / Cg) % p.KW, ky = kk / (Cg * p.KW);
+                        const int iy = a_oy * p.stride + ky - p.pad, ix = a_ox * p.stride + kx - p.pad;
+                        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) av[t] = __ldg(in_n + ((int64_t)iy * p.W + ix) * p.C + ci);
+                    }
+                }
+            }
+        }
+        // ---- load B ----
+        float bv[TN];
+        {
+            const int k = k0 + b_k;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int n = n0 + b_n + j;
+                bv[j] = (k < K && n < Cog) ? __ldg(p.w + (int64_t)k * p.Cout + g * Cog + n) : 0.0f;
+            }
+        }
+        __syncthreads();  // previous chunk consumed
+#pragma unroll
+        for (int t = 0; t < 4; ++t) As[a_k + t][a_m] = av[t];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) Bs[b_k][b_n + j] = bv[j];
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][tm * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            float b[TN];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tn * TN + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+    }
+    // ---- epilogue: bias + ReLU, NHWC store ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t m = m0 + tm * 4 + i;
+        if (m >= M) continue;
+        float* o = p.out + m * p.Cout + g * Cog;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tn * TN + j;
+            if (n < Cog) o[n] = fmaxf(acc[i][j] + __ldg(p.bias + g * Cog + n), 0.0f);
+        }
+    }
+}
+
+// K6/K9: 3x3 stride-2 VALID max pool, NHWC
+__global__ void __launch_bounds__(256) maxpool3s2_kernel(const float* __restrict__ in, int N, int H, int W, int C, int Ho, int Wo, float* __restrict__ out)
+{
+    const int64_t total = (int64_t)N * Ho * Wo * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int ox = (int)((i / C) % Wo);
+        const int oy = (int)((i / ((int64_t)C * Wo)) % Ho);
+        const int64_t n = i / ((int64_t)C * Wo * Ho);
+        const float* p = in + ((n * H + oy * 2) * W + ox * 2) * C + c;
+        float m = -3.402823466e38f;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) m = fmaxf(m, __ldg(p + ((int64_t)dy * W + dx) * C));
+        out[i] = m;
+    }
+}
+
+// K7: tf.nn.local_response_normalization(depth_radius=2, bias=1, alpha=2e-5, beta=0.75) over the channel axis
+__global__ void __launch_bounds__(256) lrn_kernel(const float* __restrict__ in, int64_t pixels, int C, float* __restrict__ out)
+{
+    const int64_t total = pixels * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const float* p = in + (i - c);
+        float s = 0.0f;
+#pragma unroll
+        for (int d = -2; d <= 2; ++d) {
+            const int cc = c + d;
+            if (cc >= 0 && cc < C) { const float v = __ldg(p + cc); s = fmaf(v, v, s); }
+        }
+        out[i] = __ldg(p + c) * powf(1.0f + 2e-5f * s, -0.75f);
+    }
+}
+
+// K16: tanh, then the mean over the 10 crop blocks (lib/architecture.py:386-389)
+__global__ void __launch_bounds__(256) tanh_crop_mean_kernel(const float* __restrict__ fc8, int n, int b, float* __restrict__ out)
+{
+    const int total = n * b;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) s += tanhf(__ldg(fc8 + (size_t)k * total + i));
+        out[i] = s / 10.0f;
+    }
+}
+
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out)
+{
+    __shared__ float tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int r = by + j, c = bx + tx;
+        tile[j][tx] = (r < rows && c < cols) ? in[(size_t)r * cols + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = bx + j, r = by + tx;  // out[c][r]
+        if (c < cols && r < rows) out[(size_t)c * rows + r] = tile[tx][j];
+    }
+}
+
+static unsigned grid_1d(int64_t total, int threads)
+{
+    const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
+    const int64_t want = ceil_div(total, threads);
+    const int64_t cap = (int64_t)sms * 16;
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, cap));
+}
+
+static int launch_conv(const float* in, const float* w, const float* bias, float* out, int N, int H, int W, int C, int KH, int KW, int stride,
+                       int pad, int Cout, int groups, cudaStream_t st)
+{
+    ConvParams p;
+    p.in = in; p.w = w; p.bias = bias; p.out = out; p.N = N; p.H = H; p.W = W; p.C = C; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
+    p.Ho = (H + 2 * pad - KH) / stride + 1; p.Wo = (W + 2 * pad - KW) / stride + 1; p.Cout = Cout; p.groups = groups;
+    const int Cog = Cout / groups, Cg = C / groups;
+    const int64_t M = (int64_t)N * p.Ho * p.Wo;
+    const bool vec = (Cg % 4 == 0) && (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+    const int BN = (Cog % 128 == 0) ? 128 : ((Cog % 96 == 0) ? 96 : 64);
+    dim3 grid((unsigned)ceil_div(M, 64), (unsigned)ceil_div(Cog, BN), (unsigned)groups);
+    if (BN == 128) { if (vec) conv_relu_kernel<128, true><<<grid, 256, 0, st>>>(p); else conv_relu_kernel<128, false><<<grid, 256, 0, st>>>(p); }
+    else if (BN == 96) { if (vec) conv_relu_kernel<96, true><<<grid, 256, 0, st>>>(p); else conv_relu_kernel<96, false><<<grid, 256, 0, st>>>(p); }
+    else { if (vec) conv_relu_kernel<64, true><<<grid, 256, 0, st>>>(p); else conv_relu_kernel<64, false><<<grid, 256, 0, st>>>(p); }
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    return HG_OK;
+}
+
+// bytes of ONE of the two ping-pong activation buffers: the largest activation, conv1's output [10n,55,55,96]
+// (crops [10n,227,227,3] and conv2's output [10n,27,27,256] are smaller)
+static size_t buf_bytes(int n) { return (((size_t)n * 10 * 55 * 55 * 96 * sizeof(float)) + 255) & ~size_t(255); }
+
+}  // namespace hg
+
+extern "C" size_t hg_alexnet_workspace_bytes(int n)
+{
+    if (n <= 0) return 0;
+    return 2 * hg::buf_bytes(n);
+}
+
+extern "C" int hg_transpose_f32(const float* d_in, int rows, int cols, float* d_out, void* stream)
+{
+    if (rows <= 0 || cols <= 0 || !d_in || !d_out) return hg::fail(HG_EINVAL, "hg_transpose_f32: bad arguments");
+    dim3 grid((unsigned)hg::ceil_div(cols, 32), (unsigned)hg::ceil_div(rows, 32));
+    hg::transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, rows, cols, d_out);
+    hg::count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    return HG_OK;
+}
+
+extern "C" int hg_alexnet_encode(const uint8_t* d_images, int n, int wh, const HgAlexNetWeights* w, int hash_dim, unsigned flags, float* d_out,
+                                 void* d_workspace, size_t workspace_bytes, void* stream)
+{
+    using namespace hg;
+    if (n == 0) return HG_OK;
+    if (n < 0 || wh <= 0 || wh > 256) return fail(HG_EINVAL, "hg_alexnet_encode: bad n=%d / wh=%d", n, wh);
+    if (hash_dim <= 0 || hash_dim > 256) return fail(HG_EINVAL, "hg_alexnet_encode: unsupported HASH_DIM=%d (1..256)", hash_dim);
+    if (!d_images || !w || !d_out || !d_workspace) return fail(HG_EINVAL, "hg_alexnet_encode: NULL pointer");
+    if (workspace_bytes < hg_alexnet_workspace_bytes(n)) return fail(HG_ENOMEM, "hg_alexnet_encode: workspace too small");
+    for (int i = 0; i < 5; ++i)
+        if (!w->conv_w[i] || !w->conv_b[i]) return fail(HG_EINVAL, "hg_alexnet_encode: conv%d weights missing", i + 1);
+    if (!w->fc6_wt || !w->fc6_b || !w->fc7_wt || !w->fc7_b || !w->fc8_wt || !w->fc8_b) return fail(HG_EINVAL, "hg_alexnet_encode: fc weights missing");
+    if (flags & ~(unsigned)HG_ENC_LRN) return fail(HG_EINVAL, "hg_alexnet_encode: only the deterministic mode is implemented (flags = HG_ENC_LRN or 0)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool lrn = (flags & HG_ENC_LRN) != 0;
+    float* A = static_cast<float*>(d_workspace);
+    float* B = reinterpret_cast<float*>(static_cast<char*>(d_workspace) + buf_bytes(n));
+    const int N = 10 * n;
+    int rc;
+    // crops -> A
+    prep_crops_kernel<<<grid_1d((int64_t)N * 227 * 227, 256), 256, 0, st>>>(d_images, n, wh, A);
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    // conv1 11x11/4 VALID 3->96 : A -> B [N,55,55,96]
+    if ((rc = launch_conv(A, w->conv_w[0], w->conv_b[0], B, N, 227, 227, 3, 11, 11, 4, 0, 96, 1, st)) != HG_OK) return rc;
+    // pool1 : B -> A [N,27,27,96]
+    maxpool3s2_kernel<<<grid_1d((int64_t)N * 27 * 27 * 96, 256), 256, 0, st>>>(B, N, 55, 55, 96, 27, 27, A);
+    count_launch();
+    float* cur = A;
+    float* other = B;
+    if (lrn) {
+        lrn_kernel<<<grid_1d((int64_t)N * 27 * 27 * 96, 256), 256, 0, st>>>(cur, (int64_t)N * 27 * 27, 96, other);
+        count_launch();
+        std::swap(cur, other);
+    }
+    HG_CUDA_TRY(cudaGetLastError());
+    // conv2 5x5 SAME, 2 groups 48->128 : -> [N,27,27,256]
+    if ((rc = launch_conv(cur, w->conv_w[1], w->conv_b[1], other, N, 27, 27, 96, 5, 5, 1, 2, 256, 2, st)) != HG_OK) return rc;
+    std::swap(cur, other);
+    maxpool3s2_kernel<<<grid_1d((int64_t)N * 13 * 13 * 256, 256), 256, 0, st>>>(cur, N, 27, 27, 256, 13, 13, other);
+    count_launch();
+    std::swap(cur, other);
+    if (lrn) {
+        lrn_kernel<<<grid_1d((int64_t)N * 13 * 13 * 256, 256), 256, 0, st>>>(cur, (int64_t)N * 13 * 13, 256, other);
+        count_launch();
+        std::swap(cur, other);
+    }
+    HG_CUDA_TRY(cudaGetLastError());
+    // conv3 3x3 SAME 256->384, conv4 3x3 SAME 2 groups 192->192, conv5 3x3 SAME 2 groups 192->128
+    if ((rc = launch_conv(cur, w->conv_w[2], w->conv_b[2], other, N, 13, 13, 256, 3, 3, 1, 1, 384, 1, st)) != HG_OK) return rc;
+    std::swap(cur, other);
+    if ((rc = launch_conv(cur, w->conv_w[3], w->conv_b[3], other, N, 13, 13, 384, 3, 3, 1, 1, 384, 2, st)) != HG_OK) return rc;
+    std::swap(cur, other);
+    if ((rc = launch_conv(cur, w->conv_w[4], w->conv_b[4], other, N, 13, 13, 384, 3, 3, 1, 1, 256, 2, st)) != HG_OK) return rc;
+    std::swap(cur, other);
+    // pool5 -> [N,6,6,256] == [N, 9216] in (h, w, c) order, the row order of the fc6 weights
+    maxpool3s2_kernel<<<grid_1d((int64_t)N * 6 * 6 * 256, 256), 256, 0, st>>>(cur, N, 13, 13, 256, 6, 6, other);
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    std::swap(cur, other);
+    // fc6, fc7 (+ReLU), fc8 on the tensor cores
+    if ((rc = gemm_tf32(cur, 9216, w->fc6_wt, 9216, w->fc6_b, other, 4096, N, 4096, 9216, 1, st)) != HG_OK) return rc;
+    std::swap(cur, other);
+    if ((rc = gemm_tf32(cur, 4096, w->fc7_wt, 4096, w->fc7_b, other, 4096, N, 4096, 4096, 1, st)) != HG_OK) return rc;
+    std::swap(cur, other);
+    if ((rc = gemm_tf32(cur, 4096, w->fc8_wt, 4096, w->fc8_b, other, hash_dim, N, hash_dim, 4096, 0, st)) != HG_OK) return rc;
+    std::swap(cur, other);
+    tanh_crop_mean_kernel<<<grid_1d((int64_t)n * hash_dim, 256), 256, 0, st>>>(cur, n, hash_dim, d_out);
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    return HG_OK;
+}

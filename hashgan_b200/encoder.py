@@ -1,0 +1,156 @@
+"""AlexNet hash-head encoder (stage='val') -- host mirror of the reference's encode operator.
+
+Reference: the per-batch operator `session.run(model.disc_real_acgan, {labeled_real_data_holder: image, ...})`
+(main.py:154-155) = Model.normalize (main.py:144-148) -> discriminator(stage='val') = alexnet_discriminator
+(lib/architecture.py:196-392).  Weights keep the reference's registry names (lib/params.py:11-35):
+    discriminator.conv{1..5}.{weights,biases}   HWIO, shapes of lib/architecture.py:253-341
+    discriminator.fc{6,7}.{weights,biases}
+    discriminator.ACGANOutput.{W,b}             lib/ops.py:264-266,296-301 (fc8, [4096, HASH_DIM])
+The numeric work is libhashgan_b200's hg_alexnet_encode (conv1-5 CUDA kernels, fc6-8 on tcgen05 tensor cores).
+Deterministic mode only (EVAL.DETERMINISTIC): no de-quantisation noise, no eval-time dropout.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _native
+
+__all__ = ["AlexNetWeights", "AlexNetHashEncoder", "CONV_SHAPES", "WEIGHT_NAMES"]
+
+CONV_SHAPES = {"conv1": (11, 11, 3, 96), "conv2": (5, 5, 48, 256), "conv3": (3, 3, 256, 384), "conv4": (3, 3, 192, 384),
+               "conv5": (3, 3, 192, 256)}
+FC_SHAPES = {"fc6": (9216, 4096), "fc7": (4096, 4096)}
+
+
+def WEIGHT_NAMES(hash_dim: int) -> Dict[str, tuple]:
+    names = {}
+    for k, s in CONV_SHAPES.items():
+        names[f"discriminator.{k}.weights"] = s
+        names[f"discriminator.{k}.biases"] = (s[3],)
+    for k, s in FC_SHAPES.items():
+        names[f"discriminator.{k}.weights"] = s
+        names[f"discriminator.{k}.biases"] = (s[1],)
+    names["discriminator.ACGANOutput.W"] = (4096, hash_dim)
+    names["discriminator.ACGANOutput.b"] = (hash_dim,)
+    return names
+
+
+class AlexNetWeights:
+    """name -> float32 array, validated against the reference's shapes."""
+
+    def __init__(self, tensors: Dict[str, np.ndarray], hash_dim: int):
+        want = WEIGHT_NAMES(hash_dim)
+        self.hash_dim = hash_dim
+        self.tensors = {}
+        for name, shape in want.items():
+            if name not in tensors:
+                raise KeyError(f"missing weight {name}")
+            a = np.ascontiguousarray(np.asarray(tensors[name], dtype=np.float32))
+            if tuple(a.shape) != tuple(shape):
+                raise ValueError(f"{name}: expected shape {shape}, got {tuple(a.shape)}")
+            self.tensors[name] = a
+
+    @classmethod
+    def synthetic(cls, hash_dim: int, seed: int = 0) -> "AlexNetWeights":
+        """Seeded He-normal conv/fc weights, Glorot-uniform fc8 like lib/ops.py:213-218, small biases."""
+        rng = np.random.default_rng(seed)
+        t = {}
+        for name, shape in WEIGHT_NAMES(hash_dim).items():
+            if name.endswith(".W"):
+                lim = np.sqrt(2.0 / (shape[0] + shape[1])) * np.sqrt(3.0)
+                t[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+            elif len(shape) > 1:
+                fan_in = int(np.prod(shape[:-1]))
+                gain = np.sqrt(2.0 / fan_in)
+                if name == "discriminator.conv1.weights":
+                    gain /= 200.0  # mean-subtracted pixels are O(100): bring activations (and fc8) to O(1) so tanh is not saturated
+                t[name] = (rng.standard_normal(size=shape, dtype=np.float32) * gain).astype(np.float32)
+            else:
+                t[name] = (rng.standard_normal(size=shape, dtype=np.float32) * 0.01).astype(np.float32)
+        return cls(t, hash_dim)
+
+    @classmethod
+    def from_alexnet_npy(cls, path: str, hash_dim: int, seed: int = 0) -> "AlexNetWeights":
+        """The reference's ImageNet initialisation: a pickled dict net_data[layer][0|1] (lib/architecture.py:199);
+        fc8 (ACGANOutput) is not in that file and gets the reference's Glorot-uniform init (lib/ops.py:213-218)."""
+        net = dict(np.load(path, encoding="latin1", allow_pickle=True).item())
+        t = cls.synthetic(hash_dim, seed).tensors
+        for layer in ("conv1", "conv2", "conv3", "conv4", "conv5", "fc6", "fc7"):
+            t[f"discriminator.{layer}.weights"] = np.asarray(net[layer][0], dtype=np.float32)
+            t[f"discriminator.{layer}.biases"] = np.asarray(net[layer][1], dtype=np.float32)
+        t["discriminator.ACGANOutput.b"] = np.zeros((hash_dim,), dtype=np.float32)
+        return cls(t, hash_dim)
+
+
+class AlexNetHashEncoder:
+    """images (uint8, [B, 3*wh*wh] as the loader yields them, lib/dataloader.py:110-113) -> CUDA float32 [B, HASH_DIM]."""
+
+    def __init__(self, weights: AlexNetWeights, *, lrn: bool = True, device=None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise _native.NativeLibraryError("hashgan_b200 needs a CUDA device (sm_100a); there is no CPU fallback for the encoder")
+        self.torch = torch
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.hash_dim = weights.hash_dim
+        self.lrn = lrn
+        self.lib = _native.lib()
+        dev = self.device
+        t = {k: torch.from_numpy(v).to(dev) for k, v in weights.tensors.items()}
+        self._keep = t
+        st = _native.AlexNetWeightsStruct()
+        for i in range(5):
+            st.conv_w[i] = t[f"discriminator.conv{i + 1}.weights"].data_ptr()
+            st.conv_b[i] = t[f"discriminator.conv{i + 1}.biases"].data_ptr()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            self._wt = {}
+            for key, name in (("fc6", "discriminator.fc6.weights"), ("fc7", "discriminator.fc7.weights"), ("fc8", "discriminator.ACGANOutput.W")):
+                src = t[name]
+                dst = torch.empty((src.shape[1], src.shape[0]), dtype=torch.float32, device=dev)
+                _native.check(self.lib.hg_transpose_f32(src.data_ptr(), src.shape[0], src.shape[1], dst.data_ptr(), stream))
+                self._wt[key] = dst
+            torch.cuda.synchronize(dev)
+        st.fc6_wt, st.fc6_b = self._wt["fc6"].data_ptr(), t["discriminator.fc6.biases"].data_ptr()
+        st.fc7_wt, st.fc7_b = self._wt["fc7"].data_ptr(), t["discriminator.fc7.biases"].data_ptr()
+        st.fc8_wt, st.fc8_b = self._wt["fc8"].data_ptr(), t["discriminator.ACGANOutput.b"].data_ptr()
+        self._struct = st
+        self._ws = None
+
+    def encode(self, images, wh: Optional[int] = None):
+        torch = self.torch
+        if isinstance(images, torch.Tensor):
+            x = images
+        else:
+            a = np.asarray(images)
+            if a.dtype != np.uint8:
+                if a.size and (a.min() < 0 or a.max() > 255):
+                    raise ValueError("image values must be 0..255 (the loader yields uint8-valued pixels)")
+                a = a.astype(np.uint8)
+            x = torch.from_numpy(np.ascontiguousarray(a))
+        n = int(x.shape[0])
+        x = x.reshape(n, -1)
+        if wh is None:
+            wh = int(round((x.shape[1] / 3) ** 0.5))
+        if 3 * wh * wh != x.shape[1]:
+            raise ValueError(f"each image must have 3*wh*wh values, got {x.shape[1]}")
+        if x.dtype != torch.uint8:
+            x = x.to(torch.uint8)
+        dev = self.device
+        with torch.cuda.device(dev):
+            x = x.to(dev, non_blocking=True).contiguous()
+            out = torch.empty((n, self.hash_dim), dtype=torch.float32, device=dev)
+            need = self.lib.hg_alexnet_workspace_bytes(n)
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _native.check(self.lib.hg_alexnet_encode(x.data_ptr(), n, wh, C.byref(self._struct), self.hash_dim,
+                                                     _native.ENC_LRN if self.lrn else 0, out.data_ptr(), self._ws.data_ptr(),
+                                                     self._ws.numel(), stream))
+            x.record_stream(torch.cuda.current_stream(dev))
+        return out
+
+    __call__ = encode

@@ -118,6 +118,37 @@ int hg_release_cached(void);
 int hg_gemm_tf32(const float* d_a, int64_t lda, const float* d_bt, int64_t ldb, const float* d_bias, float* d_c, int64_t ldc,
                  int M, int N, int K, int relu, void* stream);
 
+/* AlexNet hash head, stage='val' (lib/architecture.py:196-392 with main.py:144-148 and lib/util.py:12-21 in front):
+ * uint8 images -> crop-averaged tanh outputs in (-1, 1), the `.output` that main.py:155-157 hands to the metric.
+ * Weight tensors are fp32 device pointers in the reference's own layouts and names (lib/params.py registry):
+ *   conv_w[i] HWIO: discriminator.conv1..5.weights = [11,11,3,96] [5,5,48,256] [3,3,256,384] [3,3,192,384] [3,3,192,256]
+ *   conv_b[i]     : discriminator.conv1..5.biases
+ *   fc6_wt / fc7_wt / fc8_wt: discriminator.fc6.weights [9216,4096], discriminator.fc7.weights [4096,4096],
+ *                   discriminator.ACGANOutput.W [4096,HASH_DIM] -- each TRANSPOSED to [N, K] (hg_transpose_f32), so the
+ *                   tensor-core GEMM reads both operands K-major; fc6 rows are in (h, w, c) order as in the reference
+ *   fc6_b / fc7_b / fc8_b: discriminator.fc6.biases, discriminator.fc7.biases, discriminator.ACGANOutput.b */
+typedef struct HgAlexNetWeights {
+    const float* conv_w[5];
+    const float* conv_b[5];
+    const float* fc6_wt; const float* fc6_b;
+    const float* fc7_wt; const float* fc7_b;
+    const float* fc8_wt; const float* fc8_b;
+} HgAlexNetWeights;
+
+#define HG_ENC_LRN 1u  /* local response normalisation after pool1/pool2: on iff TRAIN.WGAN_SCALE == 0 (architecture.py:268,294) */
+
+/* Workspace bytes for a batch of n images (10 n crops). */
+size_t hg_alexnet_workspace_bytes(int n);
+
+/* d_images: uint8 [n, 3, wh, wh], RGB planes -- the loader's flattened batch (lib/dataloader.py:110-113), wh <= 256.
+ * d_out: float32 [n, hash_dim].  Deterministic mode only: no de-quantisation noise (main.py:147) and no eval-time
+ * dropout (architecture.py:369,377).  fc6-8 run on tcgen05 tensor cores (TF32), conv1-5 on the CUDA cores (fp32). */
+int hg_alexnet_encode(const uint8_t* d_images, int n, int wh, const HgAlexNetWeights* w, int hash_dim, unsigned flags,
+                      float* d_out, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* out[c][r] = in[r][c] (fp32, [rows, cols] -> [cols, rows]); used once per model to transpose the fc weights. */
+int hg_transpose_f32(const float* d_in, int rows, int cols, float* d_out, void* stream);
+
 /* Integer-pipe microbenchmark: measured XOR+POPC word-ops per second of this GPU (the binding roofline
  * of the Hamming kernel).  Runs `iters` dependent-free popc chains on every SM. */
 int hg_popc_peak(double* wordops_per_s, double* ms, int iters, void* stream);

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""CLI of the evaluation path -- same surface as the reference's main.py:253-270:
+
+    python main.py --cfg config/cifar_evaluation.yaml --gpus 0
+
+prints the merged config, writes it to OUTPUT_DIR/config.txt, evaluates and prints `map_val: <float>`
+(main.py:197-199).  Only TRAIN.EVALUATE_MODE: True is in scope (training is not part of this build).
+Weights: MODEL.ALEXNET_PRETRAINED_MODEL_PATH (.npy dict, lib/architecture.py:199) when present; with
+EVAL.SYNTHETIC: True seeded synthetic weights and images stand in for missing files.
+"""
+import argparse
+import os
+import sys
+from pprint import pprint
+
+
+def main(cfg):
+    from hashgan_b200.dataloader import Dataloader, SyntheticDataloader
+    from hashgan_b200.encoder import AlexNetHashEncoder, AlexNetWeights
+    from hashgan_b200.evaluate import evaluate
+
+    if not cfg.TRAIN.EVALUATE_MODE:
+        raise SystemExit("hashgan_b200 implements the evaluation path only: set TRAIN.EVALUATE_MODE: True")
+    if cfg.MODEL.D_ARCHITECTURE != "ALEXNET":
+        raise SystemExit("only MODEL.D_ARCHITECTURE: ALEXNET is in scope (cifar_evaluation.yaml:3)")
+    npy = cfg.MODEL.ALEXNET_PRETRAINED_MODEL_PATH
+    if os.path.exists(npy):
+        weights = AlexNetWeights.from_alexnet_npy(npy, cfg.MODEL.HASH_DIM, cfg.EVAL.SEED)
+        print("AlexNet weights loaded: {}".format(npy))
+    elif cfg.EVAL.SYNTHETIC:
+        weights = AlexNetWeights.synthetic(cfg.MODEL.HASH_DIM, cfg.EVAL.SEED)
+        print("synthetic AlexNet weights (seed {})".format(cfg.EVAL.SEED))
+    else:
+        raise SystemExit("{} not found (set EVAL.SYNTHETIC: True for seeded synthetic weights)".format(npy))
+    if len(cfg.MODEL.D_PRETRAINED_MODEL_PATH) > 0 and not cfg.EVAL.SYNTHETIC:
+        raise SystemExit("TensorFlow checkpoints (MODEL.D_PRETRAINED_MODEL_PATH) cannot be read yet: export the discriminator "
+                         "variables to the .npy dict format or set EVAL.SYNTHETIC: True")
+    encoder = AlexNetHashEncoder(weights, lrn=(cfg.TRAIN.WGAN_SCALE == 0))
+    if os.path.isdir(cfg.DATA.DATA_ROOT) and os.path.isdir(cfg.DATA.LIST_ROOT):
+        dataloader = Dataloader(cfg.TRAIN.BATCH_SIZE, cfg.DATA.WIDTH_HEIGHT, cfg.DATA.LIST_ROOT, cfg.DATA.DATA_ROOT)
+    elif cfg.EVAL.SYNTHETIC:
+        dataloader = SyntheticDataloader(cfg.TRAIN.BATCH_SIZE, cfg.DATA.WIDTH_HEIGHT, cfg.DATA.LABEL_DIM,
+                                         {"database": cfg.DATA.DB_SIZE, "test": cfg.DATA.TEST_SIZE}, cfg.EVAL.SEED)
+    else:
+        raise SystemExit("{} / {} not found (set EVAL.SYNTHETIC: True for seeded synthetic images)".format(cfg.DATA.DATA_ROOT, cfg.DATA.LIST_ROOT))
+    map_val = evaluate(encoder, dataloader, cfg)
+    print('map_val: {}'.format(map_val))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.path.append(os.getcwd())
+    parser = argparse.ArgumentParser(description='HashGAN evaluation on B200')
+    parser.add_argument('--cfg', '--config', required=True, type=str, metavar="FILE", help="path to yaml config")
+    parser.add_argument('--gpus', default='0', type=str)
+    parser.add_argument('opts', nargs=argparse.REMAINDER, help="KEY VALUE overrides, e.g. EVAL.SYNTHETIC True DATA.DB_SIZE 2048")
+    args = parser.parse_args()
+    os.environ["CUDA_VISIBLE_DEVICES"] = args.gpus
+
+    from hashgan_b200.config import config, update_and_inference_config
+
+    if args.opts:
+        config.merge_from_list(args.opts)
+    config = update_and_inference_config(args.cfg)
+    pprint(config)
+    with open(os.path.join(config.DATA.OUTPUT_DIR, 'config.txt'), 'w') as fh:
+        pprint(config, fh)
+    sys.exit(main(config))

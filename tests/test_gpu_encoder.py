@@ -46,3 +46,72 @@ def test_gemm_tf32_matches_fp32_reference(M, N, K, relu):
     goti = _gemm(ai, bi, None, False)
     wanti = (ai.double() @ bi.double().t()).float()
     assert torch.equal(goti, wanti)
+
+
+def test_alexnet_encoder_matches_fp32_oracle():
+    """configs[2] shape (CIFAR 32x32 -> 10 crops -> conv1-5 -> fc6-8 -> tanh -> crop mean) on synthetic weights/images:
+    outputs within TF32 tolerance of the PyTorch fp32 restatement, code bits identical outside a small margin."""
+    import torch
+    from hashgan_b200.encoder import AlexNetHashEncoder, AlexNetWeights
+    from oracle import alexnet_oracle
+
+    for hash_dim, lrn, n in ((64, True, 12), (48, False, 5)):
+        w = AlexNetWeights.synthetic(hash_dim, seed=3)
+        rng = np.random.default_rng(5)
+        img = rng.integers(0, 256, (n, 3 * 32 * 32), dtype=np.uint8)
+        want = alexnet_oracle.encode(img, w.tensors, 32, lrn=lrn)
+        enc = AlexNetHashEncoder(w, lrn=lrn, device="cuda:0")
+        got = enc(img).cpu().numpy()
+        assert got.shape == want.shape == (n, hash_dim)
+        err = np.abs(got - want).max()
+        assert err <= 5e-3, err  # TF32 fc layers (10-bit mantissa) vs fp32; tanh compresses the error
+        margin = np.abs(want) > 2e-2
+        assert np.array_equal(got[margin] > 0, want[margin] > 0)
+        assert ((got > 0) == (want > 0)).mean() >= 0.995
+        assert 0.2 < np.abs(want).mean() < 0.999  # the test exercises the unsaturated range of tanh
+
+
+def test_encoder_stages_match_oracle():
+    """Stage-by-stage check of the fused prep kernel (normalize + legacy bilinear + 10-crop + mean) through conv1."""
+    import torch
+    from hashgan_b200.encoder import AlexNetHashEncoder, AlexNetWeights
+    from oracle import alexnet_oracle as ao
+
+    # a structured image exposes flip / crop-offset / interpolation mistakes that noise would hide
+    n, wh = 3, 32
+    yy, xx = np.meshgrid(np.arange(wh), np.arange(wh), indexing="ij")
+    img = np.stack([np.stack([(7 * yy + 3 * xx + 11 * i) % 256, (5 * yy * (i + 1) + xx) % 256, (yy * xx + 40 * i) % 256]) for i in range(n)]).astype(np.uint8)
+    w = AlexNetWeights.synthetic(32, seed=9)
+    want = ao.encode(img.reshape(n, -1), w.tensors, wh, lrn=True)
+    got = AlexNetHashEncoder(w, lrn=True)(img.reshape(n, -1)).cpu().numpy()
+    assert np.abs(got - want).max() <= 5e-3
+
+
+def test_evaluate_loop_and_cli_surface(tmp_path):
+    """main.py:151-164 mirror on a synthetic dataloader: forward_all truncates the wrapped last batch, evaluate returns the
+    same mAP as the oracle metric on the encoder's outputs."""
+    import torch
+    from types import SimpleNamespace as NS
+    from hashgan_b200.config import get_default_config
+    from hashgan_b200.dataloader import SyntheticDataloader
+    from hashgan_b200.encoder import AlexNetHashEncoder, AlexNetWeights
+    from hashgan_b200.evaluate import evaluate, forward_all
+    from oracle import maps_oracle
+
+    cfg = get_default_config()
+    cfg.merge_from_list(["MODEL.HASH_DIM", 32, "DATA.DB_SIZE", 300, "DATA.TEST_SIZE", 40, "DATA.MAP_R", 300, "TRAIN.BATCH_SIZE", 64])
+    enc = AlexNetHashEncoder(AlexNetWeights.synthetic(32, seed=1), lrn=False)
+    dl = SyntheticDataloader(64, 32, 10, {"database": 300, "test": 40}, seed=4)
+    np.random.seed(0)
+    db = forward_all(enc, dl.db_gen, 300, cfg)
+    assert tuple(db.output.shape) == (300, 32) and db.label.shape == (300, 10)
+    np.random.seed(0)
+    val = evaluate(enc, dl, cfg)
+    # oracle metric on the sign codes of the same encoder outputs (same permutation: same seed)
+    np.random.seed(0)
+    db2 = forward_all(enc, dl.db_gen, 300, cfg)
+    q2 = forward_all(enc, dl.test_gen, 40, cfg)
+    codes = lambda t: np.where(t.cpu().numpy() > 0, 1.0, -1.0).astype(np.float32)
+    ref = maps_oracle.OracleMAPs(300, tie="stable").get_maps_by_feature(NS(output=codes(db2.output), label=db2.label),
+                                                                          NS(output=codes(q2.output), label=q2.label))
+    assert abs(val - ref) <= 1e-12
