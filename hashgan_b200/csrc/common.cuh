@@ -50,6 +50,25 @@ int plan_chunks(int64_t nq, int64_t ndb, int b, int L, int64_t R, int k_req, Map
 int hamming_map_chunked(const uint32_t* q_rows, int64_t nq, const uint32_t* db_rows, int64_t ndb, int b, int L, int64_t R, unsigned flags,
                         double* d_ap, void* ws, size_t ws_bytes, cudaStream_t st, const MapChunks* chunks, PrepareRowsFn prepare, void* user);
 
+// tensor-core select (select_umma.cu), driven from rank.cu
+struct UmmaSelectArgs {
+    const uint32_t* q_rows;
+    const uint32_t* db_rows;
+    int64_t nq, ndb;
+    int b, W, LW, Wr, KP;
+    const int* thr;
+    int P, split0, n_splits;
+    int64_t SL;
+    uint32_t* lists;
+    uint32_t cap;
+    uint32_t* bin_cnt;
+    const uint8_t* q8;   // [nq, KP] int8 codes
+    const uint8_t* db8;  // [ndb, KP]
+};
+int umma_select_kp(int b, int Wr);  // int8 row bytes (64 / 128), 0 = shape not supported by the tensor-core path
+int umma_expand(const uint32_t* rows, int64_t n, int b, int Wr, int KP, uint8_t* out, cudaStream_t st);
+int umma_select_launch(const UmmaSelectArgs& a, cudaStream_t st);
+
 struct DeviceFacts {
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     size_t l2_bytes = 0;

@@ -10,9 +10,7 @@
 //   warp 1      : allocates BN TMEM columns, issues tcgen05.mma (one elected thread; 4 MMAs of K=8 per stage),
 //                 tcgen05.commit releases the stage / signals the epilogue
 //   warps 2..5  : epilogue -- tcgen05.ld 32 lanes x 32 columns, + bias, ReLU, float4 stores
-#include "common.cuh"
-
-#include <cuda.h>
+#include "umma.cuh"
 
 namespace hg {
 
@@ -20,25 +18,6 @@ constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 32;  // fp32 elements = 128 bytes = one swizzle atom row
 constexpr int kGemmStages = 4;
 constexpr int kGemmThreads = 192;
-
-__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t mbar, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
-                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar), "r"(c0), "r"(c1)
-                 : "memory");
-}
-
-// shared-memory matrix descriptor: K-major operand, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 bytes apart
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
-    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major), bits [16,30)
-    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell), bits [46,48)
-    d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B, bits [61,64)
-    return d;
-}
 
 // instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = BN
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
@@ -56,11 +35,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint6
         "}\n" ::"r"(tmem_c),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 template <int BN, bool RELU>
@@ -174,10 +148,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn()
+EncodeTiledFn encode_tiled_fn()
 {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {

@@ -33,6 +33,7 @@ namespace hg {
 // ================================================================================================
 struct Plan {
     int b = 0, L = 0, W = 0, LW = 0, Wr = 0, QT = 0, TQ = 0, TILE = 0, P = 0, nqt = 0;
+    int umma_kp = 0;  // > 0: the fast-path select runs on the tensor cores (select_umma.cu), int8 rows of this many bytes
     int64_t nq = 0, ndb = 0, R = 0, SL = 0;
     uint32_t cap = 0;
     // sample pass
@@ -40,12 +41,13 @@ struct Plan {
     int seg_per_chunk = 0, n_chunks = 0;
     // workspace byte offsets
     size_t off_ctrl = 0, off_thr = 0, off_thr2 = 0, off_fail = 0, off_wide = 0, off_hist_s = 0, off_bin_cnt = 0, off_bin_cnt2 = 0,
-           off_bin_off2 = 0, off_bin_cap2 = 0, off_quota2 = 0, off_hist2 = 0, off_lists = 0, total = 0;
+           off_bin_off2 = 0, off_bin_cap2 = 0, off_quota2 = 0, off_hist2 = 0, off_lists = 0, off_q8 = 0, off_db8 = 0, total = 0;
     bool ok = false;
 };
 
 constexpr int kSelectThreads = 128;
 constexpr int kSelectCtasPerSm = 16;
+constexpr int kUmmaWaves = 8;
 constexpr int kHistThreads = 128;
 constexpr int kApWarps = 8;  // exact_plan_kernel: warps per CTA
 constexpr int64_t kSampleTarget = 16384;
@@ -80,8 +82,17 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
     p.TILE = tile_rows_for(p.Wr);
     // db splits: one wave of CTAs that are all resident (grid ~ SMs x CTAs/SM), split length a multiple of the
     // tile, at most 2^21 rows
-    const int64_t target_ctas = (int64_t)sms * env_int("HG_SELECT_CTAS_PER_SM", kSelectCtasPerSm) * ctas_mult;
-    int64_t P0 = std::max<int64_t>(1, ceil_div(target_ctas, p.nqt));
+    {
+        const char* be = getenv("HG_SELECT_BACKEND");
+        if (!(be && be[0] == 'p')) p.umma_kp = umma_select_kp(b, p.Wr);  // "popc" forces the POPC kernel
+    }
+    int64_t target_ctas = (int64_t)sms * env_int("HG_SELECT_CTAS_PER_SM", kSelectCtasPerSm) * ctas_mult;
+    int64_t units = p.nqt;
+    if (p.umma_kp) {  // one 320-thread CTA per SM holds all 512 TMEM columns: size the grid in waves of 148
+        target_ctas = (int64_t)sms * env_int("HG_UMMA_WAVES", kUmmaWaves) * ctas_mult;
+        units = ceil_div(nq, 256);
+    }
+    int64_t P0 = std::max<int64_t>(1, ceil_div(target_ctas, units));
     int64_t SL = round_up(ceil_div(ndb, P0), p.TILE);
     SL = std::min<int64_t>(SL, kMaxSplitRows);
     SL = std::max<int64_t>(SL, p.TILE);
@@ -131,6 +142,10 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
     p.off_quota2 = take(sizeof(uint32_t) * bins);
     p.off_hist2 = take(sizeof(uint32_t) * bins * (b + 1));
     p.off_lists = take(sizeof(uint32_t) * bins * p.cap);
+    if (p.umma_kp) {
+        p.off_q8 = take((size_t)nq * p.umma_kp);
+        p.off_db8 = take((size_t)ndb * p.umma_kp);
+    }
     p.total = off;
     p.ok = true;
     return p;
@@ -913,16 +928,31 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
         sp.n_active = nullptr; sp.qlist = nullptr; sp.P = pl.P; sp.SL = pl.SL; sp.R = pl.R;
         sp.lists = lists; sp.cap = pl.cap; sp.bin_off2 = nullptr; sp.bin_cap2 = nullptr; sp.quota2 = nullptr;
         sp.bin_cnt = bin_cnt;
-        if (K > 1) {
-            for (int k = 0; k < K; ++k) {
+        UmmaSelectArgs ua{};
+        uint8_t* q8 = reinterpret_cast<uint8_t*>(ws + pl.off_q8);
+        uint8_t* db8 = reinterpret_cast<uint8_t*>(ws + pl.off_db8);
+        if (pl.umma_kp) {
+            ua.q_rows = q_rows; ua.db_rows = db_rows; ua.nq = pl.nq; ua.ndb = pl.ndb; ua.b = pl.b; ua.W = pl.W; ua.LW = pl.LW; ua.Wr = pl.Wr;
+            ua.KP = pl.umma_kp; ua.thr = thr; ua.P = pl.P; ua.SL = pl.SL; ua.lists = lists; ua.cap = pl.cap; ua.bin_cnt = bin_cnt;
+            ua.q8 = q8; ua.db8 = db8;
+            if ((rc = umma_expand(q_rows, pl.nq, pl.b, pl.Wr, pl.umma_kp, q8, st)) != HG_OK) return rc;
+        }
+        // one launch per chunk of whole splits (a single chunk unless the host pipeline feeds the database piecewise)
+        for (int k = 0; k < K; ++k) {
+            int64_t lo = 0, hi = pl.ndb;
+            if (K > 1) {
                 if ((rc = prepare_upto(k + 1)) != HG_OK) return rc;
-                sp.split0 = (int)(chunks->row_lo[k] / pl.SL);
-                const int n_splits = (int)ceil_div(chunks->row_hi[k] - chunks->row_lo[k], pl.SL);
+                lo = chunks->row_lo[k]; hi = chunks->row_hi[k];
+            }
+            const int split0 = (int)(lo / pl.SL), n_splits = (int)ceil_div(hi - lo, pl.SL);
+            if (pl.umma_kp) {
+                if ((rc = umma_expand(db_rows + lo * pl.Wr, hi - lo, pl.b, pl.Wr, pl.umma_kp, db8 + lo * pl.umma_kp, st)) != HG_OK) return rc;
+                ua.split0 = split0; ua.n_splits = n_splits;
+                if ((rc = umma_select_launch(ua, st)) != HG_OK) return rc;
+            } else {
+                sp.split0 = split0;
                 if ((rc = launch_select_w<W, false>(sp, pl, n_splits, st)) != HG_OK) return rc;
             }
-        } else {
-            sp.split0 = 0;
-            if ((rc = launch_select_w<W, false>(sp, pl, pl.P, st)) != HG_OK) return rc;
         }
     } else {
         HG_CUDA_TRY(cudaMemsetAsync(bin_cnt, 0, sizeof(uint32_t) * (size_t)pl.nq * pl.P, st));
