@@ -197,8 +197,8 @@ def main():
     stream = torch.cuda.current_stream(device)
     ap_host = torch.empty((wl.nq,), dtype=torch.float64).pin_memory()
     timing_flag = _native.FLAG_TIMING
-    phase = (C.c_float * 5)()
-    phase_acc = np.zeros(5)
+    phase = (C.c_float * 6)()
+    phase_acc = np.zeros(6)
 
     def step(timed: bool):
         db_rows = pack_rows(db_f, db_l, device)
@@ -279,35 +279,50 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (select_kernel: all-pairs XOR/POPC + threshold select) --
+    # ---- roofline of the dominant kernel: the all-pairs select ------------------------------------------------
     hbm_peak, peak_src = _peaks()
-    sel_ms = phase_acc[2] / args.steps
+    sel_ms = phase_acc[3] / args.steps
     W = lib.hg_code_words(wl.b)
+    kp = int(lib.hg_select_backend(wl.b, wl.L))
     pairs = float(wl.nq) * float(wl.ndb)
     eff_bytes = pairs * 1.0  # 1 byte per (query, db row) pair = the uint8 distance matrix a non-fused design writes
     achieved = eff_bytes / (sel_ms * 1e-3) / 1e9
-    popc_ops, popc_ms = C.c_double(), C.c_double()
-    _native.check(lib.hg_popc_peak(C.byref(popc_ops), C.byref(popc_ms), 1 << 14, None))
-    word_ops = pairs * W
-    popc_achieved = word_ops / (sel_ms * 1e-3)
     traffic = None
     prof = os.path.join(ROOT, "profiles", "select_kernel_dram_bytes.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get(wl.name)
+            traffic = json.load(open(prof)).get(f"{wl.name}_{'umma' if kp > 0 else 'popc'}")
         except Exception:
             traffic = None
+    phases = {"sample_hist": phase_acc[0] / args.steps, "threshold": phase_acc[1] / args.steps, "expand_int8": phase_acc[2] / args.steps,
+              "select": sel_ms, "ap": phase_acc[4] / args.steps, "exact_path": phase_acc[5] / args.steps}
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-        "peak_source": peak_src, "kernel": "select_kernel", "kernel_ms": sel_ms,
-        "algorithmic_bytes_per_launch": eff_bytes,
-        "note": ("fused kernel: the distance matrix is never written, so 'achieved' is the distance-matrix-equivalent rate "
-                 "(1 B/pair, SURVEY 8(d)); the binding resource is the integer POPC pipe, see 'popc'"),
-        "popc": {"achieved_wordops_per_s": popc_achieved, "peak_wordops_per_s": popc_ops.value,
-                 "frac": popc_achieved / popc_ops.value, "peak_source": "hg_popc_peak microbenchmark, same process"},
-        "phases_ms": {"sample_hist": phase_acc[0] / args.steps, "threshold": phase_acc[1] / args.steps, "select": sel_ms,
-                      "ap": phase_acc[3] / args.steps, "exact_path": phase_acc[4] / args.steps},
+        "peak_source": peak_src, "kernel_ms": sel_ms, "algorithmic_bytes_per_launch": eff_bytes, "phases_ms": phases,
     }
+    if kp > 0:
+        tops = 2.0 * pairs * kp / (sel_ms * 1e-3) / 1e12
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        bf16 = float(json.load(open(peaks_path))["bf16_tflops"]) if os.path.exists(peaks_path) else 1590.0
+        roofline.update({
+            "kernel": f"select_umma_kernel<{kp}>",
+            "note": ("fused kernel: the distance matrix is never written, 'achieved' is the distance-matrix-equivalent rate (1 B/pair, "
+                     "SURVEY 8(d)). The contraction is an exact int8 tcgen05.mma; the kernel is bound by its CUDA-core threshold "
+                     "epilogue (ALU pipe), see 'tensor' for the tensor-pipe view"),
+            "tensor": {"achieved_tops_int8": tops, "peak_tops_int8": 2.0 * bf16, "frac": tops / (2.0 * bf16),
+                       "peak_source": "2 x measured bf16 cuBLAS burst (MEASURED_PEAKS.json); int8 dense = 2 x bf16 on B200"},
+        })
+    else:
+        popc_ops, popc_ms = C.c_double(), C.c_double()
+        _native.check(lib.hg_popc_peak(C.byref(popc_ops), C.byref(popc_ms), 1 << 14, None))
+        popc_achieved = pairs * W / (sel_ms * 1e-3)
+        roofline.update({
+            "kernel": "select_kernel",
+            "note": ("fused kernel: the distance matrix is never written, so 'achieved' is the distance-matrix-equivalent rate "
+                     "(1 B/pair, SURVEY 8(d)); the binding resource is the integer POPC pipe, see 'popc'"),
+            "popc": {"achieved_wordops_per_s": popc_achieved, "peak_wordops_per_s": popc_ops.value,
+                     "frac": popc_achieved / popc_ops.value, "peak_source": "hg_popc_peak microbenchmark, same process"},
+        })
 
     cpu_baseline = None
     if args.cpu_sample > 0:
@@ -323,7 +338,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": f"{wl.name}: {wl.nq} queries/GPU x {wl.ndb} db, {wl.b}-bit, L={wl.L}, mAP@{wl.R}",
-                   "queries_total": total_queries, "db_rows": wl.ndb, "bits": wl.b, "R": wl.R,
+                   "queries_total": total_queries, "db_rows": wl.ndb, "bits": wl.b, "R": wl.R, "select_backend": ("tcgen05 int8 (select_umma_kernel)" if kp > 0 else "popc (select_kernel)"),
                    "l2": "no flush: every step re-reads the float32 feature matrix (256 MB at C4) which exceeds the 126 MB L2",
                    "parallelism": f"query-sharded x{world}, db row-sharded for packing + 1 all-gather" if world > 1 else "1 GPU"},
         "mAP": map_val, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

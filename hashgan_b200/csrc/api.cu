@@ -173,7 +173,7 @@ extern "C" int64_t hg_launch_count(int reset)
     return (int64_t)v;
 }
 
-extern "C" int hg_hamming_map_phase_ms(float out[5])
+extern "C" int hg_hamming_map_phase_ms(float out[6])
 {
     hg::PhaseTimer& t = hg::phase_timer();
     if (!out || !t.created || !t.armed) return hg::fail(HG_EINVAL, "hg_hamming_map_phase_ms: no timed hg_hamming_map call on this thread");

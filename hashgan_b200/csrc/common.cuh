@@ -30,7 +30,7 @@ inline int fail(int code, const char* fmt, ...) {
 void count_launch(int n = 1);
 
 // optional per-phase CUDA-event timing of hg_hamming_map (flag HG_FLAG_TIMING)
-enum Phase { kPhaseSample = 0, kPhaseThreshold, kPhaseSelect, kPhaseAp, kPhaseExact, kNumPhases };
+enum Phase { kPhaseSample = 0, kPhaseThreshold, kPhaseExpand, kPhaseSelect, kPhaseAp, kPhaseExact, kNumPhases };
 struct PhaseTimer {
     cudaEvent_t ev[kNumPhases + 1] = {};
     bool created = false, armed = false;

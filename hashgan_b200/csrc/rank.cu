@@ -920,7 +920,8 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
                                                                force_exact ? 1 : 0, thr);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
-    timer.mark(kPhaseSelect, st);
+    timer.mark(kPhaseExpand, st);
+    bool select_marked = false;
     if (!force_exact) {
         // 3. single-pass select
         SelectParams sp{};
@@ -937,6 +938,7 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
             ua.q8 = q8; ua.db8 = db8;
             if ((rc = umma_expand(q_rows, pl.nq, pl.b, pl.Wr, pl.umma_kp, q8, st)) != HG_OK) return rc;
         }
+        if (K > 1 || !pl.umma_kp) { timer.mark(kPhaseSelect, st); select_marked = true; }  // chunked: expansion is interleaved with select
         // one launch per chunk of whole splits (a single chunk unless the host pipeline feeds the database piecewise)
         for (int k = 0; k < K; ++k) {
             int64_t lo = 0, hi = pl.ndb;
@@ -947,6 +949,7 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
             const int split0 = (int)(lo / pl.SL), n_splits = (int)ceil_div(hi - lo, pl.SL);
             if (pl.umma_kp) {
                 if ((rc = umma_expand(db_rows + lo * pl.Wr, hi - lo, pl.b, pl.Wr, pl.umma_kp, db8 + lo * pl.umma_kp, st)) != HG_OK) return rc;
+                if (!select_marked) { timer.mark(kPhaseSelect, st); select_marked = true; }
                 ua.split0 = split0; ua.n_splits = n_splits;
                 if ((rc = umma_select_launch(ua, st)) != HG_OK) return rc;
             } else {
@@ -957,6 +960,7 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
     } else {
         HG_CUDA_TRY(cudaMemsetAsync(bin_cnt, 0, sizeof(uint32_t) * (size_t)pl.nq * pl.P, st));
     }
+    if (!select_marked) timer.mark(kPhaseSelect, st);
     // 4. AP (queries that cannot be answered exactly from their bins go to the fail list)
     timer.mark(kPhaseAp, st);
     {
@@ -1088,6 +1092,15 @@ extern "C" int hg_hamming_map(const uint32_t* d_q_rows, int64_t nq, const uint32
         case 8: return hg::run_map<8>(pl, d_q_rows, d_db_rows, flags, d_ap, d_ids, d_dist, d_rel, ws, st);
         default: return hg::fail(HG_EINVAL, "hg_hamming_map: unsupported word count %d", pl.W);
     }
+}
+
+extern "C" int hg_select_backend(int b, int L)
+{
+    const int Wr = hg_row_words(b, L);
+    if (Wr == 0) return -1;
+    const char* be = getenv("HG_SELECT_BACKEND");
+    if (be && be[0] == 'p') return 0;
+    return hg::umma_select_kp(b, Wr);
 }
 
 extern "C" int hg_hamming_map_stats(const void* d_workspace, size_t workspace_bytes, int64_t nq, int64_t ndb, int b, int L, int64_t R,

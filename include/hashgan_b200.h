@@ -87,9 +87,15 @@ int hg_hamming_map_stats(const void* d_workspace, size_t workspace_bytes, int64_
                          int64_t R, int64_t out[8], void* stream);
 
 /* Device time (ms, CUDA events on the call's stream) of the phases of the last hg_hamming_map call made by this
- * thread with HG_FLAG_TIMING: out[0] sampled histogram, out[1] thresholds, out[2] select (the all-pairs XOR/POPC
- * kernel), out[3] AP, out[4] exact-path chain.  Synchronises on the last event. */
-int hg_hamming_map_phase_ms(float out[5]);
+ * thread with HG_FLAG_TIMING: out[0] sampled histogram, out[1] thresholds, out[2] int8 expansion of the codes
+ * (tensor-core backend only), out[3] select (the all-pairs kernel), out[4] AP, out[5] exact-path chain.
+ * Synchronises on the last event. */
+int hg_hamming_map_phase_ms(float out[6]);
+
+/* Which all-pairs kernel hg_hamming_map uses for this shape: 0 = select_kernel (XOR/POPC on the integer pipe),
+ * 64 / 128 = select_umma_kernel (exact int8 tcgen05.mma, int8 row bytes); -1 = unsupported shape.
+ * The environment variable HG_SELECT_BACKEND=popc forces 0. */
+int hg_select_backend(int b, int L);
 
 /* Number of kernels this library has launched in this process so far (reset != 0 zeroes the counter). */
 int64_t hg_launch_count(int reset);

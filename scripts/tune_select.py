@@ -33,8 +33,8 @@ def main():
                 os.environ.pop("HG_AP_G", None)
             os.environ["HG_SELECT_QT"] = str(qt)
             os.environ["HG_SELECT_CTAS_PER_SM"] = str(c)
-            acc = np.zeros(5)
-            phase = (C.c_float * 5)()
+            acc = np.zeros(6)
+            phase = (C.c_float * 6)()
             stats = {}
             n = 4
             for i in range(n + 1):
@@ -50,7 +50,7 @@ def main():
             same = bool(np.array_equal(np.isnan(a), np.isnan(ref)) and np.nanmax(np.abs(a - ref)) <= 1e-12)
             st = stats["chunks"][0]
             rec = dict(wl=name, G=ilp, qt=qt, ctas_per_sm=c, P=st["splits"], SL=st["rows_per_split"], cap=st["bin_entries"], exact=st["exact_queries"],
-                       sample=round(acc[0], 4), select=round(acc[2], 4), ap=round(acc[3], 4), exact_ms=round(acc[4], 4),
+                       sample=round(acc[0], 4), expand=round(acc[2], 4), select=round(acc[3], 4), ap=round(acc[4], 4), exact_ms=round(acc[5], 4),
                        total=round(acc.sum(), 4), same_ap=same)
             print(json.dumps(rec), flush=True)
             out.append(rec)
