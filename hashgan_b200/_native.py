@@ -16,6 +16,7 @@ FLAG_FORCE_EXACT = 1
 FLAG_NO_FALLBACK = 2
 FLAG_TIMING = 4
 ENC_LRN = 1
+ENC_CONV_TF32 = 2
 MAX_BITS = 256
 
 _i64, _int, _u32, _vp, _sz = C.c_int64, C.c_int, C.c_uint, C.c_void_p, C.c_size_t
@@ -41,7 +42,8 @@ SIGNATURES = {
                                        C.POINTER(C.c_double), _vp]),
     "hg_release_cached": (_int, []),
     "hg_gemm_tf32": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _int, _int, _int, _int, _vp]),
-    "hg_alexnet_workspace_bytes": (_sz, [_int]),
+    "hg_alexnet_workspace_bytes": (_sz, [_int, _u32]),
+    "hg_conv_weight_pack": (_int, [_vp, _int, _int, _int, _int, _int, _vp, _vp]),
     "hg_alexnet_encode": (_int, [_vp, _int, _int, _vp, _int, _u32, _vp, _vp, _sz, _vp]),
     "hg_transpose_f32": (_int, [_vp, _int, _int, _vp, _vp]),
     "hg_popc_peak": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), _int, _vp]),
@@ -53,7 +55,7 @@ class AlexNetWeightsStruct(C.Structure):
     """HgAlexNetWeights of include/hashgan_b200.h."""
     _fields_ = [("conv_w", C.c_void_p * 5), ("conv_b", C.c_void_p * 5),
                 ("fc6_wt", C.c_void_p), ("fc6_b", C.c_void_p), ("fc7_wt", C.c_void_p), ("fc7_b", C.c_void_p),
-                ("fc8_wt", C.c_void_p), ("fc8_b", C.c_void_p)]
+                ("fc8_wt", C.c_void_p), ("fc8_b", C.c_void_p), ("conv_wt", C.c_void_p * 5)]
 
 
 _lib = None

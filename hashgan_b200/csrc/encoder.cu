@@ -242,6 +242,57 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
     }
 }
 
+// ---- tensor-core convolution (opt-in, HG_ENC_CONV_TF32): explicit im2col + the tcgen05 TF32 GEMM -------------------
+// A[m, k] with m = (n, oy, ox) and k = (ky, kx, ci) of one channel group, rows padded with zeros to Kpad (multiple of 32)
+template <bool VEC>
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ in, int N, int H, int W, int C, int c0, int Cg, int KH, int KW,
+                                                      int stride, int pad, int Ho, int Wo, int Kpad, float* __restrict__ out)
+{
+    const int K = KH * KW * Cg;
+    const int k4n = Kpad / 4;
+    const int64_t total = (int64_t)N * Ho * Wo * k4n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % k4n) * 4;
+        const int64_t m = i / k4n;
+        const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho);
+        const int64_t n = m / ((int64_t)Wo * Ho);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (VEC) {
+            if (k < K) {
+                const int ci = k % Cg, kx = (k / Cg) % KW, ky = k / (Cg * KW);
+                const int iy = oy * stride + ky - pad, ix = ox * stride + kx - pad;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float4*>(in + ((n * H + iy) * W + ix) * C + c0 + ci));
+            }
+        } else {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int kk = k + u;
+                if (kk < K) {
+                    const int ci = kk % Cg, kx = (kk / Cg) % KW, ky = kk / (Cg * KW);
+                    const int iy = oy * stride + ky - pad, ix = ox * stride + kx - pad;
+                    if (iy >= 0 && iy < H && ix >= 0 && ix < W) t[u] = __ldg(in + ((n * H + iy) * W + ix) * C + c0 + ci);
+                }
+            }
+            v = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        *reinterpret_cast<float4*>(out + m * Kpad + k) = v;
+    }
+}
+
+// HWIO weights [KH*KW*Cg, Cout] -> per group K-major [groups][Cog][Kpad] (zero padded) for the GEMM's B operand
+__global__ void __launch_bounds__(256) conv_weight_pack_kernel(const float* __restrict__ w, int K, int Cout, int groups, int Kpad, float* __restrict__ out)
+{
+    const int Cog = Cout / groups;
+    const int64_t total = (int64_t)Cout * Kpad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % Kpad);
+        const int co = (int)(i / Kpad);  // = g * Cog + n
+        (void)Cog;
+        out[i] = (k < K) ? w[(int64_t)k * Cout + co] : 0.0f;
+    }
+}
+
 static unsigned grid_1d(int64_t total, int threads)
 {
     const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
@@ -269,16 +320,53 @@ static int launch_conv(const float* in, const float* w, const float* bias, float
     return HG_OK;
 }
 
+static int conv_kpad(int KH, int KW, int Cg) { return (int)round_up((int64_t)KH * KW * Cg, 32); }
+
+// convolution on the tensor cores: per group im2col -> gemm_tf32 (+bias, ReLU) straight into the NHWC output
+static int launch_conv_tf32(const float* in, const float* wt, const float* bias, float* out, float* col, int N, int H, int W, int C, int KH, int KW,
+                            int stride, int pad, int Cout, int groups, cudaStream_t st)
+{
+    const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+    const int Cg = C / groups, Cog = Cout / groups;
+    const int Kpad = conv_kpad(KH, KW, Cg);
+    const int64_t M = (int64_t)N * Ho * Wo;
+    if (M >= (int64_t(1) << 31)) return fail(HG_EINVAL, "conv_tf32: batch too large");
+    const bool vec = (Cg % 4 == 0) && (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+    for (int g = 0; g < groups; ++g) {
+        const unsigned grid = grid_1d(M * (Kpad / 4), 256);
+        if (vec) im2col_kernel<true><<<grid, 256, 0, st>>>(in, N, H, W, C, g * Cg, Cg, KH, KW, stride, pad, Ho, Wo, Kpad, col);
+        else im2col_kernel<false><<<grid, 256, 0, st>>>(in, N, H, W, C, g * Cg, Cg, KH, KW, stride, pad, Ho, Wo, Kpad, col);
+        count_launch();
+        HG_CUDA_TRY(cudaGetLastError());
+        int rc = gemm_tf32(col, Kpad, wt + (size_t)g * Cog * Kpad, Kpad, bias + g * Cog, out + g * Cog, Cout, (int)M, Cog, Kpad, 1, st);
+        if (rc != HG_OK) return rc;
+    }
+    return HG_OK;
+}
+
 // bytes of ONE of the two ping-pong activation buffers: the largest activation, conv1's output [10n,55,55,96]
 // (crops [10n,227,227,3] and conv2's output [10n,27,27,256] are smaller)
 static size_t buf_bytes(int n) { return (((size_t)n * 10 * 55 * 55 * 96 * sizeof(float)) + 255) & ~size_t(255); }
 
 }  // namespace hg
 
-extern "C" size_t hg_alexnet_workspace_bytes(int n)
+// im2col buffer of the tensor-core convolution: the largest A matrix, conv1's [10n*55*55, 384]
+namespace hg { static size_t col_bytes(int n) { return (((size_t)n * 10 * 55 * 55 * 384 * sizeof(float)) + 255) & ~size_t(255); } }
+
+extern "C" size_t hg_alexnet_workspace_bytes(int n, unsigned flags)
 {
     if (n <= 0) return 0;
-    return 2 * hg::buf_bytes(n);
+    return 2 * hg::buf_bytes(n) + ((flags & HG_ENC_CONV_TF32) ? hg::col_bytes(n) : 0);
+}
+
+extern "C" int hg_conv_weight_pack(const float* d_w_hwio, int KH, int KW, int Cg, int Cout, int groups, float* d_out, void* stream)
+{
+    if (!d_w_hwio || !d_out || KH <= 0 || KW <= 0 || Cg <= 0 || Cout <= 0 || groups <= 0 || Cout % groups) return hg::fail(HG_EINVAL, "hg_conv_weight_pack: bad arguments");
+    const int K = KH * KW * Cg, Kpad = hg::conv_kpad(KH, KW, Cg);
+    hg::conv_weight_pack_kernel<<<hg::grid_1d((int64_t)Cout * Kpad, 256), 256, 0, (cudaStream_t)stream>>>(d_w_hwio, K, Cout, groups, Kpad, d_out);
+    hg::count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    return HG_OK;
 }
 
 extern "C" int hg_transpose_f32(const float* d_in, int rows, int cols, float* d_out, void* stream)
@@ -299,23 +387,33 @@ extern "C" int hg_alexnet_encode(const uint8_t* d_images, int n, int wh, const H
     if (n < 0 || wh <= 0 || wh > 256) return fail(HG_EINVAL, "hg_alexnet_encode: bad n=%d / wh=%d", n, wh);
     if (hash_dim <= 0 || hash_dim > 256) return fail(HG_EINVAL, "hg_alexnet_encode: unsupported HASH_DIM=%d (1..256)", hash_dim);
     if (!d_images || !w || !d_out || !d_workspace) return fail(HG_EINVAL, "hg_alexnet_encode: NULL pointer");
-    if (workspace_bytes < hg_alexnet_workspace_bytes(n)) return fail(HG_ENOMEM, "hg_alexnet_encode: workspace too small");
+    if (workspace_bytes < hg_alexnet_workspace_bytes(n, flags)) return fail(HG_ENOMEM, "hg_alexnet_encode: workspace too small");
     for (int i = 0; i < 5; ++i)
         if (!w->conv_w[i] || !w->conv_b[i]) return fail(HG_EINVAL, "hg_alexnet_encode: conv%d weights missing", i + 1);
     if (!w->fc6_wt || !w->fc6_b || !w->fc7_wt || !w->fc7_b || !w->fc8_wt || !w->fc8_b) return fail(HG_EINVAL, "hg_alexnet_encode: fc weights missing");
-    if (flags & ~(unsigned)HG_ENC_LRN) return fail(HG_EINVAL, "hg_alexnet_encode: only the deterministic mode is implemented (flags = HG_ENC_LRN or 0)");
+    if (flags & ~(unsigned)(HG_ENC_LRN | HG_ENC_CONV_TF32)) return fail(HG_EINVAL, "hg_alexnet_encode: unknown flag (only the deterministic mode is implemented)");
+    const bool tc = (flags & HG_ENC_CONV_TF32) != 0;
+    if (tc)
+        for (int i = 0; i < 5; ++i)
+            if (!w->conv_wt[i]) return fail(HG_EINVAL, "hg_alexnet_encode: HG_ENC_CONV_TF32 needs conv_wt[%d] (hg_conv_weight_pack)", i);
     cudaStream_t st = (cudaStream_t)stream;
     const bool lrn = (flags & HG_ENC_LRN) != 0;
     float* A = static_cast<float*>(d_workspace);
     float* B = reinterpret_cast<float*>(static_cast<char*>(d_workspace) + buf_bytes(n));
+    float* col = reinterpret_cast<float*>(static_cast<char*>(d_workspace) + 2 * buf_bytes(n));
     const int N = 10 * n;
     int rc;
+    // one convolution layer: fp32 on the CUDA cores (default, parity with the fp32 oracle to ~1e-5) or TF32 on tcgen05
+    auto conv = [&](int i, const float* src, float* dst, int H, int C, int KH, int stride, int pad, int Cout, int groups) -> int {
+        return tc ? launch_conv_tf32(src, w->conv_wt[i], w->conv_b[i], dst, col, N, H, H, C, KH, KH, stride, pad, Cout, groups, st)
+                  : launch_conv(src, w->conv_w[i], w->conv_b[i], dst, N, H, H, C, KH, KH, stride, pad, Cout, groups, st);
+    };
     // crops -> A
     prep_crops_kernel<<<grid_1d((int64_t)N * 227 * 227, 256), 256, 0, st>>>(d_images, n, wh, A);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     // conv1 11x11/4 VALID 3->96 : A -> B [N,55,55,96]
-    if ((rc = launch_conv(A, w->conv_w[0], w->conv_b[0], B, N, 227, 227, 3, 11, 11, 4, 0, 96, 1, st)) != HG_OK) return rc;
+    if ((rc = conv(0, A, B, 227, 3, 11, 4, 0, 96, 1)) != HG_OK) return rc;
     // pool1 : B -> A [N,27,27,96]
     maxpool3s2_kernel<<<grid_1d((int64_t)N * 27 * 27 * 96, 256), 256, 0, st>>>(B, N, 55, 55, 96, 27, 27, A);
     count_launch();
@@ -328,7 +426,7 @@ extern "C" int hg_alexnet_encode(const uint8_t* d_images, int n, int wh, const H
     }
     HG_CUDA_TRY(cudaGetLastError());
     // conv2 5x5 SAME, 2 groups 48->128 : -> [N,27,27,256]
-    if ((rc = launch_conv(cur, w->conv_w[1], w->conv_b[1], other, N, 27, 27, 96, 5, 5, 1, 2, 256, 2, st)) != HG_OK) return rc;
+    if ((rc = conv(1, cur, other, 27, 96, 5, 1, 2, 256, 2)) != HG_OK) return rc;
     std::swap(cur, other);
     maxpool3s2_kernel<<<grid_1d((int64_t)N * 13 * 13 * 256, 256), 256, 0, st>>>(cur, N, 27, 27, 256, 13, 13, other);
     count_launch();
@@ -340,11 +438,11 @@ extern "C" int hg_alexnet_encode(const uint8_t* d_images, int n, int wh, const H
     }
     HG_CUDA_TRY(cudaGetLastError());
     // conv3 3x3 SAME 256->384, conv4 3x3 SAME 2 groups 192->192, conv5 3x3 SAME 2 groups 192->128
-    if ((rc = launch_conv(cur, w->conv_w[2], w->conv_b[2], other, N, 13, 13, 256, 3, 3, 1, 1, 384, 1, st)) != HG_OK) return rc;
+    if ((rc = conv(2, cur, other, 13, 256, 3, 1, 1, 384, 1)) != HG_OK) return rc;
     std::swap(cur, other);
-    if ((rc = launch_conv(cur, w->conv_w[3], w->conv_b[3], other, N, 13, 13, 384, 3, 3, 1, 1, 384, 2, st)) != HG_OK) return rc;
+    if ((rc = conv(3, cur, other, 13, 384, 3, 1, 1, 384, 2)) != HG_OK) return rc;
     std::swap(cur, other);
-    if ((rc = launch_conv(cur, w->conv_w[4], w->conv_b[4], other, N, 13, 13, 384, 3, 3, 1, 1, 256, 2, st)) != HG_OK) return rc;
+    if ((rc = conv(4, cur, other, 13, 384, 3, 1, 1, 256, 2)) != HG_OK) return rc;
     std::swap(cur, other);
     // pool5 -> [N,6,6,256] == [N, 9216] in (h, w, c) order, the row order of the fc6 weights
     maxpool3s2_kernel<<<grid_1d((int64_t)N * 6 * 6 * 256, 256), 256, 0, st>>>(cur, N, 13, 13, 256, 6, 6, other);

@@ -88,7 +88,7 @@ class AlexNetWeights:
 class AlexNetHashEncoder:
     """images (uint8, [B, 3*wh*wh] as the loader yields them, lib/dataloader.py:110-113) -> CUDA float32 [B, HASH_DIM]."""
 
-    def __init__(self, weights: AlexNetWeights, *, lrn: bool = True, device=None):
+    def __init__(self, weights: AlexNetWeights, *, lrn: bool = True, device=None, conv_tf32: bool = False):
         import torch
 
         if not torch.cuda.is_available():
@@ -97,6 +97,7 @@ class AlexNetHashEncoder:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.hash_dim = weights.hash_dim
         self.lrn = lrn
+        self.conv_tf32 = conv_tf32  # opt-in: conv1-5 on tcgen05 (TF32) instead of fp32 CUDA cores
         self.lib = _native.lib()
         dev = self.device
         t = {k: torch.from_numpy(v).to(dev) for k, v in weights.tensors.items()}
@@ -113,6 +114,16 @@ class AlexNetHashEncoder:
                 dst = torch.empty((src.shape[1], src.shape[0]), dtype=torch.float32, device=dev)
                 _native.check(self.lib.hg_transpose_f32(src.data_ptr(), src.shape[0], src.shape[1], dst.data_ptr(), stream))
                 self._wt[key] = dst
+            if conv_tf32:
+                for i, (name, shp) in enumerate(CONV_SHAPES.items()):
+                    kh, kw, cg, cout = shp
+                    groups = 1 if name in ("conv1", "conv3") else 2
+                    kpad = ((kh * kw * cg + 31) // 32) * 32
+                    dst = torch.empty((cout * kpad,), dtype=torch.float32, device=dev)
+                    _native.check(self.lib.hg_conv_weight_pack(t[f"discriminator.{name}.weights"].data_ptr(), kh, kw, cg, cout, groups,
+                                                               dst.data_ptr(), stream))
+                    self._wt[name] = dst
+                    st.conv_wt[i] = dst.data_ptr()
             torch.cuda.synchronize(dev)
         st.fc6_wt, st.fc6_b = self._wt["fc6"].data_ptr(), t["discriminator.fc6.biases"].data_ptr()
         st.fc7_wt, st.fc7_b = self._wt["fc7"].data_ptr(), t["discriminator.fc7.biases"].data_ptr()
@@ -143,13 +154,13 @@ class AlexNetHashEncoder:
         with torch.cuda.device(dev):
             x = x.to(dev, non_blocking=True).contiguous()
             out = torch.empty((n, self.hash_dim), dtype=torch.float32, device=dev)
-            need = self.lib.hg_alexnet_workspace_bytes(n)
+            flags = (_native.ENC_LRN if self.lrn else 0) | (_native.ENC_CONV_TF32 if self.conv_tf32 else 0)
+            need = self.lib.hg_alexnet_workspace_bytes(n, flags)
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty((need,), dtype=torch.uint8, device=dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _native.check(self.lib.hg_alexnet_encode(x.data_ptr(), n, wh, C.byref(self._struct), self.hash_dim,
-                                                     _native.ENC_LRN if self.lrn else 0, out.data_ptr(), self._ws.data_ptr(),
-                                                     self._ws.numel(), stream))
+            _native.check(self.lib.hg_alexnet_encode(x.data_ptr(), n, wh, C.byref(self._struct), self.hash_dim, flags, out.data_ptr(),
+                                                     self._ws.data_ptr(), self._ws.numel(), stream))
             x.record_stream(torch.cuda.current_stream(dev))
         return out
 

@@ -139,12 +139,18 @@ typedef struct HgAlexNetWeights {
     const float* fc6_wt; const float* fc6_b;
     const float* fc7_wt; const float* fc7_b;
     const float* fc8_wt; const float* fc8_b;
+    const float* conv_wt[5];  /* optional (HG_ENC_CONV_TF32): hg_conv_weight_pack of conv_w[i] */
 } HgAlexNetWeights;
 
-#define HG_ENC_LRN 1u  /* local response normalisation after pool1/pool2: on iff TRAIN.WGAN_SCALE == 0 (architecture.py:268,294) */
+#define HG_ENC_LRN 1u        /* local response normalisation after pool1/pool2: on iff TRAIN.WGAN_SCALE == 0 (architecture.py:268,294) */
+#define HG_ENC_CONV_TF32 2u  /* opt-in: conv1-5 as im2col + tcgen05 TF32 GEMM (about 5x faster, ~1e-3 relative error) instead of fp32 CUDA cores */
 
-/* Workspace bytes for a batch of n images (10 n crops). */
-size_t hg_alexnet_workspace_bytes(int n);
+/* Workspace bytes for a batch of n images (10 n crops) with these flags. */
+size_t hg_alexnet_workspace_bytes(int n, unsigned flags);
+
+/* HWIO convolution weights [KH, KW, Cg, Cout] -> per-group K-major [groups][Cout/groups][Kpad] (Kpad = KH*KW*Cg rounded
+ * up to 32, zero padded): the B operand of the tensor-core convolution.  d_out holds Cout * Kpad floats. */
+int hg_conv_weight_pack(const float* d_w_hwio, int KH, int KW, int Cg, int Cout, int groups, float* d_out, void* stream);
 
 /* d_images: uint8 [n, 3, wh, wh], RGB planes -- the loader's flattened batch (lib/dataloader.py:110-113), wh <= 256.
  * d_out: float32 [n, hash_dim].  Deterministic mode only: no de-quantisation noise (main.py:147) and no eval-time

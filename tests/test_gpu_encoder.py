@@ -115,3 +115,19 @@ def test_evaluate_loop_and_cli_surface(tmp_path):
     ref = maps_oracle.OracleMAPs(300, tie="stable").get_maps_by_feature(NS(output=codes(db2.output), label=db2.label),
                                                                           NS(output=codes(q2.output), label=q2.label))
     assert abs(val - ref) <= 1e-12
+
+
+def test_tensor_core_convolution_option():
+    """HG_ENC_CONV_TF32: conv1-5 as im2col + tcgen05 TF32 GEMM.  Same graph, TF32 rounding in every layer: looser bound."""
+    from hashgan_b200.encoder import AlexNetHashEncoder, AlexNetWeights
+    from oracle import alexnet_oracle
+
+    w = AlexNetWeights.synthetic(64, seed=3)
+    img = np.random.default_rng(5).integers(0, 256, (9, 3 * 32 * 32), dtype=np.uint8)
+    want = alexnet_oracle.encode(img, w.tensors, 32, lrn=True)
+    got = AlexNetHashEncoder(w, lrn=True, conv_tf32=True)(img).cpu().numpy()
+    ref = AlexNetHashEncoder(w, lrn=True)(img).cpu().numpy()
+    assert np.abs(got - want).max() <= 3e-2
+    assert np.abs(got - ref).max() <= 3e-2
+    margin = np.abs(want) > 0.1
+    assert np.array_equal(got[margin] > 0, want[margin] > 0)
