@@ -29,7 +29,7 @@ __device__ __forceinline__ float scaled_pixel(unsigned char v)
     return (x + 1.0f) * 255.99f / 2.0f;               // lib/util.py:13
 }
 
-__global__ void __launch_bounds__(256) prep_crops_kernel(const unsigned char* __restrict__ img, int n, int wh, float* __restrict__ out)
+__global__ void __launch_bounds__(256) prep_crops_kernel(const unsigned char* __restrict__ img, int n, int wh, int cs, float* __restrict__ out)
 {
     const int64_t total = (int64_t)10 * n * 227 * 227;
     const float scale = (float)wh / 256.0f;  // tf.image.resize_bilinear, align_corners=False, no half-pixel centres
@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(256) prep_crops_kernel(const unsigned char* __
         const int y1 = min((int)ceilf(fy), wh - 1), x1 = min((int)ceilf(fx), wh - 1);
         const float ly = fy - (float)y0, lx = fx - (float)x0;
         const float mean[3] = {103.939f, 116.779f, 123.68f};
-        float* o = out + i * 3;
+        float* o = out + i * cs;  // cs = 3, or 4 (4th channel zero) for the tensor-core conv1
+        if (cs == 4) o[3] = 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const unsigned char* p = img + ((int64_t)b * 3 + c) * wh * wh;
@@ -244,52 +245,55 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 
 // ---- tensor-core convolution (opt-in, HG_ENC_CONV_TF32): explicit im2col + the tcgen05 TF32 GEMM -------------------
 // A[m, k] with m = (n, oy, ox) and k = (ky, kx, ci) of one channel group, rows padded with zeros to Kpad (multiple of 32)
-template <bool VEC>
+// One warp per output row; the (tap, channel-chunk) decomposition of every float4 column is tabulated once per CTA in
+// shared memory, so the inner loop is table lookup + bounds test + one 16-byte load + one 16-byte store.
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ in, int N, int H, int W, int C, int c0, int Cg, int KH, int KW,
                                                       int stride, int pad, int Ho, int Wo, int Kpad, float* __restrict__ out)
 {
+    extern __shared__ int2 tab[];  // per float4 column: {input offset (floats) relative to the window origin, ky | kx << 16}; x = -1: zero padding
     const int K = KH * KW * Cg;
     const int k4n = Kpad / 4;
-    const int64_t total = (int64_t)N * Ho * Wo * k4n;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(i % k4n) * 4;
-        const int64_t m = i / k4n;
+    for (int j = threadIdx.x; j < k4n; j += blockDim.x) {
+        const int k = j * 4;
+        if (k < K) {
+            const int ci = k % Cg, kx = (k / Cg) % KW, ky = k / (Cg * KW);
+            tab[j] = make_int2((ky * W + kx) * C + ci, ky | (kx << 16));
+        } else {
+            tab[j] = make_int2(-1, 0);
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t M = (int64_t)N * Ho * Wo;
+    for (int64_t m = (int64_t)blockIdx.x * 8 + warp; m < M; m += (int64_t)gridDim.x * 8) {
         const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho);
         const int64_t n = m / ((int64_t)Wo * Ho);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (VEC) {
-            if (k < K) {
-                const int ci = k % Cg, kx = (k / Cg) % KW, ky = k / (Cg * KW);
-                const int iy = oy * stride + ky - pad, ix = ox * stride + kx - pad;
-                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float4*>(in + ((n * H + iy) * W + ix) * C + c0 + ci));
+        const int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
+        const float* src = in + ((n * H + iy0) * W + ix0) * C + c0;
+        float4* dst = reinterpret_cast<float4*>(out + m * Kpad);
+        for (int j = lane; j < k4n; j += 32) {
+            const int2 t = tab[j];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t.x >= 0) {
+                const int iy = iy0 + (t.y & 0xffff), ix = ix0 + (t.y >> 16);
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float4*>(src + t.x));
             }
-        } else {
-            float t[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int kk = k + u;
-                if (kk < K) {
-                    const int ci = kk % Cg, kx = (kk / Cg) % KW, ky = kk / (Cg * KW);
-                    const int iy = oy * stride + ky - pad, ix = ox * stride + kx - pad;
-                    if (iy >= 0 && iy < H && ix >= 0 && ix < W) t[u] = __ldg(in + ((n * H + iy) * W + ix) * C + c0 + ci);
-                }
-            }
-            v = make_float4(t[0], t[1], t[2], t[3]);
+            dst[j] = v;
         }
-        *reinterpret_cast<float4*>(out + m * Kpad + k) = v;
     }
 }
 
 // HWIO weights [KH*KW*Cg, Cout] -> per group K-major [groups][Cog][Kpad] (zero padded) for the GEMM's B operand
-__global__ void __launch_bounds__(256) conv_weight_pack_kernel(const float* __restrict__ w, int K, int Cout, int groups, int Kpad, float* __restrict__ out)
+// (input channels per group are padded from Cg to Cgp -- conv1: 3 -> 4 -- so that every tap is a whole number of float4)
+__global__ void __launch_bounds__(256) conv_weight_pack_kernel(const float* __restrict__ w, int taps, int Cg, int Cgp, int Cout, int Kpad,
+                                                                float* __restrict__ out)
 {
-    const int Cog = Cout / groups;
     const int64_t total = (int64_t)Cout * Kpad;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int k = (int)(i % Kpad);
         const int co = (int)(i / Kpad);  // = g * Cog + n
-        (void)Cog;
-        out[i] = (k < K) ? w[(int64_t)k * Cout + co] : 0.0f;
+        const int tap = k / Cgp, ci = k % Cgp;
+        out[i] = (tap < taps && ci < Cg) ? w[((int64_t)tap * Cg + ci) * Cout + co] : 0.0f;
     }
 }
 
@@ -320,22 +324,23 @@ static int launch_conv(const float* in, const float* w, const float* bias, float
     return HG_OK;
 }
 
-static int conv_kpad(int KH, int KW, int Cg) { return (int)round_up((int64_t)KH * KW * Cg, 32); }
+static int conv_cgp(int Cg) { return (Cg + 3) & ~3; }  // channels per group as the tensor-core path lays them out
+static int conv_kpad(int KH, int KW, int Cg) { return (int)round_up((int64_t)KH * KW * conv_cgp(Cg), 32); }
 
 // convolution on the tensor cores: per group im2col -> gemm_tf32 (+bias, ReLU) straight into the NHWC output
 static int launch_conv_tf32(const float* in, const float* wt, const float* bias, float* out, float* col, int N, int H, int W, int C, int KH, int KW,
                             int stride, int pad, int Cout, int groups, cudaStream_t st)
 {
     const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
-    const int Cg = C / groups, Cog = Cout / groups;
+    const int Cg = C / groups, Cog = Cout / groups;  // C is the stored (padded) channel count: conv1 reads 4-channel crops
     const int Kpad = conv_kpad(KH, KW, Cg);
     const int64_t M = (int64_t)N * Ho * Wo;
     if (M >= (int64_t(1) << 31)) return fail(HG_EINVAL, "conv_tf32: batch too large");
-    const bool vec = (Cg % 4 == 0) && (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+    if ((Cg % 4) || (C % 4) || (reinterpret_cast<uintptr_t>(in) & 15)) return fail(HG_EINVAL, "conv_tf32: channels must be a multiple of 4");
+    const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
     for (int g = 0; g < groups; ++g) {
-        const unsigned grid = grid_1d(M * (Kpad / 4), 256);
-        if (vec) im2col_kernel<true><<<grid, 256, 0, st>>>(in, N, H, W, C, g * Cg, Cg, KH, KW, stride, pad, Ho, Wo, Kpad, col);
-        else im2col_kernel<false><<<grid, 256, 0, st>>>(in, N, H, W, C, g * Cg, Cg, KH, KW, stride, pad, Ho, Wo, Kpad, col);
+        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, 8), (int64_t)sms * 32);
+        im2col_kernel<<<grid, 256, sizeof(int2) * (Kpad / 4), st>>>(in, N, H, W, C, g * Cg, Cg, KH, KW, stride, pad, Ho, Wo, Kpad, col);
         count_launch();
         HG_CUDA_TRY(cudaGetLastError());
         int rc = gemm_tf32(col, Kpad, wt + (size_t)g * Cog * Kpad, Kpad, bias + g * Cog, out + g * Cog, Cout, (int)M, Cog, Kpad, 1, st);
@@ -350,8 +355,8 @@ static size_t buf_bytes(int n) { return (((size_t)n * 10 * 55 * 55 * 96 * sizeof
 
 }  // namespace hg
 
-// im2col buffer of the tensor-core convolution: the largest A matrix, conv1's [10n*55*55, 384]
-namespace hg { static size_t col_bytes(int n) { return (((size_t)n * 10 * 55 * 55 * 384 * sizeof(float)) + 255) & ~size_t(255); } }
+// im2col buffer of the tensor-core convolution: the largest A matrix, conv1's [10n*55*55, 512] (11 x 11 taps x 4 channels = 484, padded to 512)
+namespace hg { static size_t col_bytes(int n) { return (((size_t)n * 10 * 55 * 55 * 512 * sizeof(float)) + 255) & ~size_t(255); } }
 
 extern "C" size_t hg_alexnet_workspace_bytes(int n, unsigned flags)
 {
@@ -362,8 +367,8 @@ extern "C" size_t hg_alexnet_workspace_bytes(int n, unsigned flags)
 extern "C" int hg_conv_weight_pack(const float* d_w_hwio, int KH, int KW, int Cg, int Cout, int groups, float* d_out, void* stream)
 {
     if (!d_w_hwio || !d_out || KH <= 0 || KW <= 0 || Cg <= 0 || Cout <= 0 || groups <= 0 || Cout % groups) return hg::fail(HG_EINVAL, "hg_conv_weight_pack: bad arguments");
-    const int K = KH * KW * Cg, Kpad = hg::conv_kpad(KH, KW, Cg);
-    hg::conv_weight_pack_kernel<<<hg::grid_1d((int64_t)Cout * Kpad, 256), 256, 0, (cudaStream_t)stream>>>(d_w_hwio, K, Cout, groups, Kpad, d_out);
+    const int Kpad = hg::conv_kpad(KH, KW, Cg);
+    hg::conv_weight_pack_kernel<<<hg::grid_1d((int64_t)Cout * Kpad, 256), 256, 0, (cudaStream_t)stream>>>(d_w_hwio, KH * KW, Cg, hg::conv_cgp(Cg), Cout, Kpad, d_out);
     hg::count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     return HG_OK;
@@ -405,11 +410,11 @@ extern "C" int hg_alexnet_encode(const uint8_t* d_images, int n, int wh, const H
     int rc;
     // one convolution layer: fp32 on the CUDA cores (default, parity with the fp32 oracle to ~1e-5) or TF32 on tcgen05
     auto conv = [&](int i, const float* src, float* dst, int H, int C, int KH, int stride, int pad, int Cout, int groups) -> int {
-        return tc ? launch_conv_tf32(src, w->conv_wt[i], w->conv_b[i], dst, col, N, H, H, C, KH, KH, stride, pad, Cout, groups, st)
+        return tc ? launch_conv_tf32(src, w->conv_wt[i], w->conv_b[i], dst, col, N, H, H, (C + 3) & ~3, KH, KH, stride, pad, Cout, groups, st)
                   : launch_conv(src, w->conv_w[i], w->conv_b[i], dst, N, H, H, C, KH, KH, stride, pad, Cout, groups, st);
     };
     // crops -> A
-    prep_crops_kernel<<<grid_1d((int64_t)N * 227 * 227, 256), 256, 0, st>>>(d_images, n, wh, A);
+    prep_crops_kernel<<<grid_1d((int64_t)N * 227 * 227, 256), 256, 0, st>>>(d_images, n, wh, tc ? 4 : 3, A);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     // conv1 11x11/4 VALID 3->96 : A -> B [N,55,55,96]

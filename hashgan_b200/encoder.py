@@ -118,7 +118,7 @@ class AlexNetHashEncoder:
                 for i, (name, shp) in enumerate(CONV_SHAPES.items()):
                     kh, kw, cg, cout = shp
                     groups = 1 if name in ("conv1", "conv3") else 2
-                    kpad = ((kh * kw * cg + 31) // 32) * 32
+                    kpad = ((kh * kw * ((cg + 3) // 4 * 4) + 31) // 32) * 32
                     dst = torch.empty((cout * kpad,), dtype=torch.float32, device=dev)
                     _native.check(self.lib.hg_conv_weight_pack(t[f"discriminator.{name}.weights"].data_ptr(), kh, kw, cg, cout, groups,
                                                                dst.data_ptr(), stream))

@@ -148,8 +148,8 @@ typedef struct HgAlexNetWeights {
 /* Workspace bytes for a batch of n images (10 n crops) with these flags. */
 size_t hg_alexnet_workspace_bytes(int n, unsigned flags);
 
-/* HWIO convolution weights [KH, KW, Cg, Cout] -> per-group K-major [groups][Cout/groups][Kpad] (Kpad = KH*KW*Cg rounded
- * up to 32, zero padded): the B operand of the tensor-core convolution.  d_out holds Cout * Kpad floats. */
+/* HWIO convolution weights [KH, KW, Cg, Cout] -> per-group K-major [groups][Cout/groups][Kpad] (channels per group padded
+ * to a multiple of 4, Kpad = KH*KW*Cg4 rounded up to 32, zero padded): the B operand of the tensor-core convolution.  d_out holds Cout * Kpad floats. */
 int hg_conv_weight_pack(const float* d_w_hwio, int KH, int KW, int Cg, int Cout, int groups, float* d_out, void* stream);
 
 /* d_images: uint8 [n, 3, wh, wh], RGB planes -- the loader's flattened batch (lib/dataloader.py:110-113), wh <= 256.
