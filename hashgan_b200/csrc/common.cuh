@@ -61,7 +61,8 @@ struct UmmaSelectArgs {
     int64_t SL;
     uint32_t* lists;
     uint32_t cap;
-    uint32_t* bin_cnt;
+    uint32_t* bin_cnt;   // candidates closer than the threshold distance, stored from the start of the bin
+    uint32_t* bin_cnt0;  // candidates at the threshold distance, stored from the end of the bin downwards
     const uint8_t* q8;   // [nq, KP] int8 codes
     const uint8_t* db8;  // [ndb, KP]
 };

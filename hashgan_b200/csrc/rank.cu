@@ -40,7 +40,7 @@ struct Plan {
     int64_t n_seg = 0, seg_stride = 0, sample_rows = 0;
     int seg_per_chunk = 0, n_chunks = 0;
     // workspace byte offsets
-    size_t off_ctrl = 0, off_thr = 0, off_thr2 = 0, off_fail = 0, off_wide = 0, off_hist_s = 0, off_bin_cnt = 0, off_bin_cnt2 = 0,
+    size_t off_ctrl = 0, off_thr = 0, off_thr2 = 0, off_fail = 0, off_wide = 0, off_hist_s = 0, off_bin_cnt = 0, off_bin_cnt0 = 0, off_bin_cnt2 = 0,
            off_bin_off2 = 0, off_bin_cap2 = 0, off_quota2 = 0, off_hist2 = 0, off_lists = 0, off_q8 = 0, off_db8 = 0, total = 0;
     bool ok = false;
 };
@@ -136,6 +136,7 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
     p.off_wide = take(sizeof(int) * nq);
     p.off_hist_s = take(sizeof(uint32_t) * (size_t)nq * (b + 1));
     p.off_bin_cnt = take(sizeof(uint32_t) * bins);
+    p.off_bin_cnt0 = take(sizeof(uint32_t) * bins);
     p.off_bin_cnt2 = take(sizeof(uint32_t) * bins);
     p.off_bin_off2 = take(sizeof(uint32_t) * bins);
     p.off_bin_cap2 = take(sizeof(uint32_t) * bins);
@@ -302,7 +303,8 @@ struct SelectParams {
     const uint32_t* bin_off2;  // EXACT: bin = f*P + s at lists + f*R + bin_off2[bin]
     const uint32_t* bin_cap2;
     const uint32_t* quota2;
-    uint32_t* bin_cnt;  // out: candidates seen per bin (may exceed the capacity -> overflow)
+    uint32_t* bin_cnt;   // out: candidates with d < T seen per bin (EXACT: all candidates); front + back may exceed the capacity -> overflow
+    uint32_t* bin_cnt0;  // out (fast path): candidates with d == T seen per bin, stored from the end of the bin downwards
 };
 
 // row stride when the label fits one word (the common case: L <= 32) -- a compile-time constant so that a whole
@@ -431,16 +433,19 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams p)
                 if (d == T[k]) { ok = neq[k] < quota[k]; neq[k]++; }
             }
             if (ok) {
-                const uint32_t at = pos[k];
-                if (at < end[k]) {
+                // fast path: rows at the threshold distance (d == T) are stacked downwards from the end of the bin, closer
+                // rows upwards from its start, so the AP kernel can stream the d == T class and stop at the quota
+                const bool eq = !EXACT && d == T[k];
+                const uint32_t front = pos[k], back = EXACT ? 0u : neq[k];
+                if (front + back < end[k]) {
                     uint32_t m = lab & qlab[k];
                     if (!LW1) {
 #pragma unroll 1
                         for (int w = 1; w < LW; ++w) m |= row[W + w] & s_qlab[w * TQ + k * NT + tid];
                     }
-                    lists[at] = ((uint32_t)d * (1u << kIdxBits) + lidx) | (m ? 0x80000000u : 0u);
+                    lists[eq ? end[k] - 1u - back : front] = ((uint32_t)d * (1u << kIdxBits) + lidx) | (m ? 0x80000000u : 0u);
                 }
-                pos[k] = at + 1;
+                if (eq) neq[k] = back + 1; else pos[k] = front + 1;
             }
         };
 
@@ -481,7 +486,10 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams p)
 
 #pragma unroll
     for (int k = 0; k < QT; ++k)
-        if (bin[k] >= 0) p.bin_cnt[bin[k]] = pos[k] - start[k];
+        if (bin[k] >= 0) {
+            p.bin_cnt[bin[k]] = pos[k] - start[k];
+            if (!EXACT) p.bin_cnt0[bin[k]] = neq[k];
+        }
 }
 
 // ================================================================================================
@@ -510,6 +518,7 @@ struct ApParams {
     const uint32_t* bin_off2;  // exact path
     const uint32_t* bin_cap2;  // exact path
     const uint32_t* bin_cnt;
+    const uint32_t* bin_cnt0;  // fast path: d == T class stacked from the end of each bin (null: single class)
     const int* thr;
     double* ap;
     uint32_t* ids;
@@ -521,6 +530,16 @@ struct ApParams {
     int* n_wide;
     int no_fallback;
 };
+
+// Error-free accumulation (Knuth TwoSum): hi + lo carries the AP sum to ~2^-100, so the rounded result does not depend
+// on how the candidates of a query are split over threads (G, P) -- query chunking and the launch shape stay invisible.
+__device__ __forceinline__ void dd_add(double& hi, double& lo, double x)
+{
+    const double s = __dadd_rn(hi, x);
+    const double bb = __dsub_rn(s, hi);
+    lo = __dadd_rn(lo, __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(x, bb)));
+    hi = s;
+}
 
 template <bool WINDOW>
 __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
@@ -548,18 +567,21 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
     for (int c = 0; c < ncol; ++c) { cN[c * NTB] = 0; cM[c * NTB] = 0; }
 
     // ---- totals / overflow over the query's bins (group reduction) -------------------------
-    unsigned long long total = 0;
+    unsigned long long total = 0, total1 = 0;  // all candidates / candidates closer than the threshold distance
     int ovf = 0;
     if (live) {
         for (int s = s0; s < s1; ++s) {
-            const uint32_t c = p.bin_cnt[binbase + s];
+            const uint32_t c1 = p.bin_cnt[binbase + s];
+            const uint32_t c0 = p.bin_cnt0 ? p.bin_cnt0[binbase + s] : 0u;
             const uint32_t capb = exact ? p.bin_cap2[binbase + s] : p.cap;
-            ovf |= (c > capb);
-            total += c;
+            ovf |= ((unsigned long long)c1 + c0 > capb);
+            total += (unsigned long long)c1 + c0;
+            total1 += c1;
         }
     }
     for (int o = 1; o < G; o <<= 1) {
         total += __shfl_xor_sync(FULL, total, o);
+        total1 += __shfl_xor_sync(FULL, total1, o);
         ovf |= __shfl_xor_sync(FULL, ovf, o);
     }
     if (live && (ovf || total < (unsigned long long)p.R || T < 0)) {
@@ -649,7 +671,7 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
     }
 
     // ---- phase B: ranks, relevant prefix counts, AP ------------------------------------------------
-    double acc = 0.0;
+    double acc = 0.0, acc_lo = 0.0;
     int relc = 0;
     const uint32_t R32 = (uint32_t)p.R;
     if (live) {
@@ -665,17 +687,62 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
                 if (p.ids) p.ids[q * p.R + (rank - 1u)] = (uint32_t)(row0 + (ent & kIdxMask));
                 if (p.dist) p.dist[q * p.R + (rank - 1u)] = (uint16_t)d;
                 if (m) {
-                    acc += (double)cum / (double)rank;
+                    dd_add(acc, acc_lo, (double)cum / (double)rank);
                     relc += 1;
                 }
             }
         });
     }
-    // fixed-order reduction over the G ranges of the query (deterministic)
-    for (int o = 1; o < G; o <<= 1) {
-        acc += __shfl_xor_sync(FULL, acc, o);
-        relc += __shfl_xor_sync(FULL, relc, o);
+    // relevant rows among the closer-than-threshold class (all of them are inside the top-R when total1 < R)
+    for (int o = 1; o < G; o <<= 1) relc += __shfl_xor_sync(FULL, relc, o);
+
+    // ---- part 2: the d == T class, streamed in row order until the top-R is full ---------------------------------
+    int relc0 = 0;
+    if (p.bin_cnt0 != nullptr) {
+        const bool need0 = live && total1 < (unsigned long long)p.R;
+        const uint32_t quota = need0 ? (uint32_t)(p.R - (int64_t)total1) : 0u;
+        const uint32_t base_rank = (uint32_t)total1, base_cum = (uint32_t)relc;
+        uint32_t n_done = 0, m_done = 0;
+        const uint32_t gmask = G >= 32 ? FULL : ((1u << G) - 1u);
+        const int gshift = lane - g;  // first lane of my group
+        for (int s = 0; s < p.P; ++s) {
+            const uint32_t c0 = need0 ? p.bin_cnt0[binbase + s] : 0u;
+            const uint32_t* back = need0 ? bin_ptr(s) + (p.cap - 1u) : nullptr;  // entry i of the class (row order) lives at back - i
+            const int64_t row0 = (int64_t)s * p.SL;
+            for (uint32_t i0 = 0;; i0 += (uint32_t)G) {
+                const bool more = i0 < c0 && n_done < quota;
+                if (!__any_sync(FULL, more)) break;
+                const uint32_t i = i0 + (uint32_t)g;
+                const bool act = more && i < c0;
+                const uint32_t ent = act ? __ldg(back - i) : 0u;
+                const uint32_t relbit = act ? (ent >> 31) : 0u;
+                const uint32_t gb = (__ballot_sync(FULL, relbit != 0u) >> gshift) & gmask;  // relevance bits of my group
+                if (more) {
+                    const uint32_t rank = base_rank + n_done + (uint32_t)g + 1u;
+                    if (act && rank <= R32) {
+                        if (p.ids) p.ids[q * p.R + (rank - 1u)] = (uint32_t)(row0 + (ent & kIdxMask));
+                        if (p.dist) p.dist[q * p.R + (rank - 1u)] = (uint16_t)((ent >> kIdxBits) & kDistMask);
+                        if (relbit) {
+                            const uint32_t cum = base_cum + m_done + (uint32_t)__popc(gb & ((1u << g) - 1u)) + 1u;
+                            dd_add(acc, acc_lo, (double)cum / (double)rank);
+                            relc0 += 1;
+                        }
+                    }
+                    n_done += min((uint32_t)G, c0 - i0);
+                    m_done += (uint32_t)__popc(gb);
+                }
+            }
+        }
     }
+    // fixed-order reduction over the G lanes of the query (deterministic)
+    for (int o = 1; o < G; o <<= 1) {
+        const double ohi = __shfl_xor_sync(FULL, acc, o), olo = __shfl_xor_sync(FULL, acc_lo, o);
+        dd_add(acc, acc_lo, ohi);
+        acc_lo = __dadd_rn(acc_lo, olo);
+        relc0 += __shfl_xor_sync(FULL, relc0, o);
+    }
+    relc += relc0;
+    acc = __dadd_rn(acc, acc_lo);
     if (live && g == 0) {
         p.ap[q] = relc ? acc / (double)relc : __longlong_as_double(0x7ff8000000000000LL);
         if (p.rel) p.rel[q] = relc;
@@ -883,6 +950,7 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
     int* wide_list = reinterpret_cast<int*>(ws + pl.off_wide);
     uint32_t* hist_s = reinterpret_cast<uint32_t*>(ws + pl.off_hist_s);
     uint32_t* bin_cnt = reinterpret_cast<uint32_t*>(ws + pl.off_bin_cnt);
+    uint32_t* bin_cnt0 = reinterpret_cast<uint32_t*>(ws + pl.off_bin_cnt0);
     uint32_t* bin_cnt2 = reinterpret_cast<uint32_t*>(ws + pl.off_bin_cnt2);
     uint32_t* bin_off2 = reinterpret_cast<uint32_t*>(ws + pl.off_bin_off2);
     uint32_t* bin_cap2 = reinterpret_cast<uint32_t*>(ws + pl.off_bin_cap2);
@@ -928,13 +996,13 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
         sp.q_rows = q_rows; sp.db_rows = db_rows; sp.nq = pl.nq; sp.ndb = pl.ndb; sp.Wr = pl.Wr; sp.LW = pl.LW; sp.TILE = pl.TILE; sp.thr = thr;
         sp.n_active = nullptr; sp.qlist = nullptr; sp.P = pl.P; sp.SL = pl.SL; sp.R = pl.R;
         sp.lists = lists; sp.cap = pl.cap; sp.bin_off2 = nullptr; sp.bin_cap2 = nullptr; sp.quota2 = nullptr;
-        sp.bin_cnt = bin_cnt;
+        sp.bin_cnt = bin_cnt; sp.bin_cnt0 = bin_cnt0;
         UmmaSelectArgs ua{};
         uint8_t* q8 = reinterpret_cast<uint8_t*>(ws + pl.off_q8);
         uint8_t* db8 = reinterpret_cast<uint8_t*>(ws + pl.off_db8);
         if (pl.umma_kp) {
             ua.q_rows = q_rows; ua.db_rows = db_rows; ua.nq = pl.nq; ua.ndb = pl.ndb; ua.b = pl.b; ua.W = pl.W; ua.LW = pl.LW; ua.Wr = pl.Wr;
-            ua.KP = pl.umma_kp; ua.thr = thr; ua.P = pl.P; ua.SL = pl.SL; ua.lists = lists; ua.cap = pl.cap; ua.bin_cnt = bin_cnt;
+            ua.KP = pl.umma_kp; ua.thr = thr; ua.P = pl.P; ua.SL = pl.SL; ua.lists = lists; ua.cap = pl.cap; ua.bin_cnt = bin_cnt; ua.bin_cnt0 = bin_cnt0;
             ua.q8 = q8; ua.db8 = db8;
             if ((rc = umma_expand(q_rows, pl.nq, pl.b, pl.Wr, pl.umma_kp, q8, st)) != HG_OK) return rc;
         }
@@ -959,6 +1027,7 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
         }
     } else {
         HG_CUDA_TRY(cudaMemsetAsync(bin_cnt, 0, sizeof(uint32_t) * (size_t)pl.nq * pl.P, st));
+        HG_CUDA_TRY(cudaMemsetAsync(bin_cnt0, 0, sizeof(uint32_t) * (size_t)pl.nq * pl.P, st));
     }
     if (!select_marked) timer.mark(kPhaseSelect, st);
     // 4. AP (queries that cannot be answered exactly from their bins go to the fail list)
@@ -966,7 +1035,7 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
     {
         ApParams ap{};
         ap.nq = pl.nq; ap.n_active = nullptr; ap.qlist = nullptr; ap.bins_by_slot = 0; ap.P = pl.P; ap.b = pl.b; ap.SL = pl.SL; ap.R = pl.R;
-        ap.lists = lists; ap.cap = pl.cap; ap.bin_off2 = nullptr; ap.bin_cap2 = nullptr; ap.bin_cnt = bin_cnt; ap.thr = thr;
+        ap.lists = lists; ap.cap = pl.cap; ap.bin_off2 = nullptr; ap.bin_cap2 = nullptr; ap.bin_cnt = bin_cnt; ap.bin_cnt0 = bin_cnt0; ap.thr = thr;
         ap.ap = d_ap; ap.ids = d_ids; ap.dist = d_dist; ap.rel = d_rel;
         ap.fail_list = fail_list; ap.n_fail = n_fail; ap.no_fallback = no_fallback ? 1 : 0;
         ap.wide_list = wide_list; ap.n_wide = ctrl + 2;
@@ -1002,12 +1071,12 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
         sp.q_rows = q_rows; sp.db_rows = db_rows; sp.nq = pl.nq; sp.ndb = pl.ndb; sp.Wr = pl.Wr; sp.LW = pl.LW; sp.TILE = pl.TILE; sp.thr = thr2;
         sp.n_active = n_fail; sp.qlist = fail_list; sp.P = pl.P; sp.SL = pl.SL; sp.R = pl.R;
         sp.lists = lists; sp.cap = 0; sp.bin_off2 = bin_off2; sp.bin_cap2 = bin_cap2; sp.quota2 = quota2;
-        sp.bin_cnt = bin_cnt2; sp.split0 = 0;
+        sp.bin_cnt = bin_cnt2; sp.bin_cnt0 = nullptr; sp.split0 = 0;
         if ((rc = launch_select_w<W, true>(sp, pl, pl.P, st)) != HG_OK) return rc;
 
         ApParams ap{};
         ap.nq = pl.nq; ap.n_active = n_fail; ap.qlist = fail_list; ap.bins_by_slot = 1; ap.P = pl.P; ap.b = pl.b; ap.SL = pl.SL; ap.R = pl.R;
-        ap.lists = lists; ap.cap = 0; ap.bin_off2 = bin_off2; ap.bin_cap2 = bin_cap2; ap.bin_cnt = bin_cnt2; ap.thr = thr2;
+        ap.lists = lists; ap.cap = 0; ap.bin_off2 = bin_off2; ap.bin_cap2 = bin_cap2; ap.bin_cnt = bin_cnt2; ap.bin_cnt0 = nullptr; ap.thr = thr2;
         ap.ap = d_ap; ap.ids = d_ids; ap.dist = d_dist; ap.rel = d_rel;
         ap.fail_list = nullptr; ap.n_fail = ctrl + 1; ap.no_fallback = 0; ap.wide_list = nullptr; ap.n_wide = nullptr;
         if ((rc = launch_ap<false>(ap, pl.nq, st)) != HG_OK) return rc;

@@ -158,12 +158,14 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
         const int W = a.W, LW = a.LW, Wr = a.Wr;
         uint32_t qw[4] = {0, 0, 0, 0}, ql[4] = {0, 0, 0, 0};
         int thr_ip = 1 << 20;
-        uint32_t pos = 0, start = 0, end = 0;
+        uint32_t pos = 0, nback = 0, start = 0, end = 0;  // front stack (d < T) grows up from start, back stack (d == T) down from end
+        int Tq = -1;
         int64_t bin = -1;
         if (valid) {
             for (int w = 0; w < W && w < 4; ++w) qw[w] = a.q_rows[slot * Wr + w];
             for (int w = 0; w < LW && w < 4; ++w) ql[w] = a.q_rows[slot * Wr + W + w];
             const int T = a.thr[slot];
+            Tq = T;
             if (T >= 0) thr_ip = a.b - 2 * T;
             bin = slot * a.P + split;
             start = (uint32_t)(bin * (int64_t)a.cap);
@@ -228,14 +230,15 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
                     for (int w = 0; w < 4; ++w)
                         if (w < LW) m |= ql[w] & prow[W + w];
                 }
-                const uint32_t at = pos;
-                if (at < end) lists[at] = ((uint32_t)d * (1u << kIdxBits) + (uint32_t)(t * kUmmaTileRows + rl)) | (m ? 0x80000000u : 0u);
-                pos = at + 1;
+                const bool eq = d == Tq;
+                if (pos + nback < end)
+                    lists[eq ? end - 1u - nback : pos] = ((uint32_t)d * (1u << kIdxBits) + (uint32_t)(t * kUmmaTileRows + rl)) | (m ? 0x80000000u : 0u);
+                if (eq) nback += 1; else pos += 1;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);  // shared-memory stage free for the producer
         }
-        if (bin >= 0) a.bin_cnt[bin] = pos - start;
+        if (bin >= 0) { a.bin_cnt[bin] = pos - start; a.bin_cnt0[bin] = nback; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
