@@ -64,10 +64,16 @@ struct UmmaSelectArgs {
     uint32_t* bin_cnt;   // candidates closer than the threshold distance, stored from the start of the bin
     uint32_t* bin_cnt0;  // candidates at the threshold distance, stored from the end of the bin downwards
     const uint8_t* q8;   // [nq, KP] int8 codes
-    const uint8_t* db8;  // [ndb, KP]
+    const uint8_t* db8;  // [round_up(ndb, 32), KP], rows of every 32-row group permuted (select_umma.cu)
+    const uint8_t* qx;   // [round_up(nq, 256), 32] threshold columns of the A operand
+    const uint8_t* bx;   // [128, 32] threshold columns of the B operand (constant)
+    uint32_t prmt_sel;   // PRMT selector of the epilogue's sign gather
 };
 int umma_select_kp(int b, int Wr);  // int8 row bytes (64 / 128), 0 = shape not supported by the tensor-core path
-int umma_expand(const uint32_t* rows, int64_t n, int b, int Wr, int KP, uint8_t* out, cudaStream_t st);
+int umma_expand_q(const uint32_t* rows, int64_t n, int b, int Wr, int KP, uint8_t* out, cudaStream_t st);
+// database rows [lo, hi) of db_rows (whole 32-row groups, or up to the end of the database) -> db8
+int umma_expand_db(const uint32_t* db_rows, int64_t lo, int64_t hi, int64_t ndb, int b, int Wr, int KP, uint8_t* db8, cudaStream_t st);
+int umma_thr_columns(const int* thr, int64_t nq, int b, uint8_t* qx, uint8_t* bx, cudaStream_t st);
 int umma_select_launch(const UmmaSelectArgs& a, cudaStream_t st);
 
 struct DeviceFacts {

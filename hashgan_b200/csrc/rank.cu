@@ -41,7 +41,7 @@ struct Plan {
     int seg_per_chunk = 0, n_chunks = 0;
     // workspace byte offsets
     size_t off_ctrl = 0, off_thr = 0, off_thr2 = 0, off_fail = 0, off_wide = 0, off_hist_s = 0, off_bin_cnt = 0, off_bin_cnt0 = 0, off_bin_cnt2 = 0,
-           off_bin_off2 = 0, off_bin_cap2 = 0, off_quota2 = 0, off_hist2 = 0, off_lists = 0, off_q8 = 0, off_db8 = 0, total = 0;
+           off_bin_off2 = 0, off_bin_cap2 = 0, off_quota2 = 0, off_hist2 = 0, off_lists = 0, off_q8 = 0, off_db8 = 0, off_qx = 0, off_bx = 0, total = 0;
     bool ok = false;
 };
 
@@ -94,6 +94,22 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
     }
     int64_t P0 = std::max<int64_t>(1, ceil_div(target_ctas, units));
     int64_t SL = round_up(ceil_div(ndb, P0), p.TILE);
+    if (p.umma_kp && ctas_mult == 1 && env_int("HG_UMMA_WAVES", 0) == 0) {
+        // Two CTAs are resident per SM and every CTA costs (rows of its split + a fixed start-up), so the launch
+        // takes ceil(CTAs / slots) rounds of the longest split.  Pick the split count with the shortest makespan
+        // instead of a fixed wave count: a grid of 4.05 waves would leave the last 0.05 wave running alone.
+        const int64_t slots = (int64_t)sms * 2;
+        const int64_t startup_rows = 768;  // A-operand load + TMEM allocation + pipeline fill, in database rows
+        double best = 1e300;
+        for (int64_t cand = 1; cand <= 4 * P0 + 8; ++cand) {
+            const int64_t sl = std::max<int64_t>(p.TILE, round_up(ceil_div(ndb, cand), p.TILE));
+            if (sl > kMaxSplitRows) continue;
+            const int64_t np = ceil_div(ndb, sl);
+            const int64_t rounds = ceil_div(units * np, slots);
+            const double cost = (double)rounds * (double)(sl + startup_rows);
+            if (cost < best * 0.995) { best = cost; SL = sl; }  // prefer fewer splits unless clearly better
+        }
+    }
     SL = std::min<int64_t>(SL, kMaxSplitRows);
     SL = std::max<int64_t>(SL, p.TILE);
     p.SL = SL;
@@ -145,7 +161,9 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
     p.off_lists = take(sizeof(uint32_t) * bins * p.cap);
     if (p.umma_kp) {
         p.off_q8 = take((size_t)nq * p.umma_kp);
-        p.off_db8 = take((size_t)ndb * p.umma_kp);
+        p.off_db8 = take((size_t)round_up(ndb, 128) * p.umma_kp);
+        p.off_qx = take((size_t)std::max<int64_t>(round_up(nq, 256), 128) * 32);
+        p.off_bx = take((size_t)128 * 32);
     }
     p.total = off;
     p.ok = true;
@@ -1004,7 +1022,9 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
             ua.q_rows = q_rows; ua.db_rows = db_rows; ua.nq = pl.nq; ua.ndb = pl.ndb; ua.b = pl.b; ua.W = pl.W; ua.LW = pl.LW; ua.Wr = pl.Wr;
             ua.KP = pl.umma_kp; ua.thr = thr; ua.P = pl.P; ua.SL = pl.SL; ua.lists = lists; ua.cap = pl.cap; ua.bin_cnt = bin_cnt; ua.bin_cnt0 = bin_cnt0;
             ua.q8 = q8; ua.db8 = db8;
-            if ((rc = umma_expand(q_rows, pl.nq, pl.b, pl.Wr, pl.umma_kp, q8, st)) != HG_OK) return rc;
+            ua.qx = reinterpret_cast<uint8_t*>(ws + pl.off_qx); ua.bx = reinterpret_cast<uint8_t*>(ws + pl.off_bx);
+            if ((rc = umma_expand_q(q_rows, pl.nq, pl.b, pl.Wr, pl.umma_kp, q8, st)) != HG_OK) return rc;
+            if ((rc = umma_thr_columns(thr, pl.nq, pl.b, const_cast<uint8_t*>(ua.qx), const_cast<uint8_t*>(ua.bx), st)) != HG_OK) return rc;
         }
         if (K > 1 || !pl.umma_kp) { timer.mark(kPhaseSelect, st); select_marked = true; }  // chunked: expansion is interleaved with select
         // one launch per chunk of whole splits (a single chunk unless the host pipeline feeds the database piecewise)
@@ -1016,7 +1036,7 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
             }
             const int split0 = (int)(lo / pl.SL), n_splits = (int)ceil_div(hi - lo, pl.SL);
             if (pl.umma_kp) {
-                if ((rc = umma_expand(db_rows + lo * pl.Wr, hi - lo, pl.b, pl.Wr, pl.umma_kp, db8 + lo * pl.umma_kp, st)) != HG_OK) return rc;
+                if ((rc = umma_expand_db(db_rows, lo, hi, pl.ndb, pl.b, pl.Wr, pl.umma_kp, db8, st)) != HG_OK) return rc;
                 if (!select_marked) { timer.mark(kPhaseSelect, st); select_marked = true; }
                 ua.split0 = split0; ua.n_splits = n_splits;
                 if ((rc = umma_select_launch(ua, st)) != HG_OK) return rc;

@@ -1,21 +1,29 @@
 // Tensor-core variant of the hot kernel: the all-pairs contraction of lib/metric.py:13 as an EXACT int8 GEMM.
 //
 // On {-1,+1} codes  ip = sum_k q_k * db_k = b - 2 * d_H  (SURVEY A.3), so a row is a candidate (d_H <= T_q) iff
-// ip >= b - 2 T_q.  The codes are expanded once to int8 (+1 / -1, zero padding) and contracted with
+// ip - (b - 2 T_q) >= 0.  The codes are expanded once to int8 (+1 / -1, zero padding) and contracted with
 // tcgen05.mma kind::i8 (int32 accumulation in tensor memory: exact), which moves the contraction off the POPC pipe
-// that bounds select_kernel.  The epilogue then only has to threshold the accumulators:
+// that bounds select_kernel.  The per-query threshold rides in the GEMM as one extra K step
+// (A columns hold 2 T_q - b split over two int8 values, B columns hold 1), so the accumulator's SIGN is the answer
+// and the epilogue never subtracts:
 //
-//   per CTA: 256 queries (two 128-row A operands, loaded once by TMA) x one database split
+//   per CTA: 256 queries (two 128-row A operands + their threshold columns, loaded once by TMA) x one database split
 //   warp 0      TMA producer: per 128-row database tile the int8 tile (B operand, swizzled) and the packed rows
-//               (code + label words, for the rare path) into a 4-stage ring
+//               (code + label words, for the rare path) into a ring of stages
 //   warp 1      TMEM allocator (256 columns = 2 query halves x 128; two CTAs share an SM) and MMA issuer
-//   warps 2..9  epilogue: thread <-> query (TMEM lane).  tcgen05.ld 32 columns at a time; two integer ops per pair
-//               build four 32-bit hit masks (sub + funnel shift of the sign bit), then the accumulator is handed
-//               back to the MMA warp; the ~R/Ndb hits of the tile are walked in row order: distance recomputed
-//               from the packed words (POPC), relevance from the label words, entry appended to the thread's
-//               private bin exactly as select_kernel does.
+//   warps 2..9  epilogue: thread <-> query (TMEM lane).  tcgen05.ld ... .pack::16b brings two accumulators per
+//               register (|ip'| <= 384 fits 16 bits); one PRMT with sign replication turns two registers into four
+//               0x00/0xFF bytes, one LOP3 drops them into the hit mask: 0.5 integer op per pair.  The accumulator is
+//               then handed back to the MMA warp and the ~R/Ndb hits of the tile are walked in row order: distance
+//               recomputed from the packed words (POPC), relevance from the label words, entry appended to the
+//               thread's private bin exactly as select_kernel does.
+// The PRMT/LOP3 gather leaves accumulator column 4i+k of a 32-column group at mask bit 8k+i; expand_db_kernel stores
+// the int8 database rows of every 32-row group in the inverse order, so that mask bit j IS row j of the group.
 // The bins, thresholds, AP kernel and exactness guard are shared with the POPC path (rank.cu).
 #include "umma.cuh"
+
+#include <algorithm>
+#include <cstdlib>
 
 namespace hg {
 
@@ -23,6 +31,7 @@ constexpr int kUmmaThreads = 320;
 template <int KP> struct UmmaCfg { static constexpr int S = (KP == 64 ? 4 : 3); };  // ring depth: two CTAs must fit one SM
 constexpr int kUmmaTileRows = 128;
 constexpr uint32_t kUmmaRowsMax = 128 * 8 * 4;  // packed-row bytes per stage (Wr <= 8)
+constexpr int kUmmaXBytes = 32;                 // threshold K step: one UMMA_K of int8 columns, SWIZZLE_32B rows
 
 __host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N)
 {
@@ -46,40 +55,137 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// same on a precomputed shared-space address (keeps the address arithmetic out of the tile loop)
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "HG_WAITA:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra HG_DONEA;\n"
+        "bra HG_WAITA;\n"
+        "HG_DONEA:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
 
-// packed code words -> int8 rows [n, KP]: +1 where the bit is set, -1 where it is clear, 0 beyond bit b
-__global__ void __launch_bounds__(256) expand_codes_kernel(const uint32_t* __restrict__ rows, int64_t n, int b, int Wr, int KP, uint8_t* __restrict__ out)
+// 16 code bits starting at bit0 of a packed row -> 16 int8 values: +1 where the bit is set, -1 where it is clear,
+// 0 beyond bit b
+__device__ __forceinline__ uint4 expand16(const uint32_t* __restrict__ row, int bit0, int b)
+{
+    uint32_t bits = 0;
+    if (bit0 < b) bits = (__ldg(row + (bit0 >> 5)) >> (bit0 & 31)) & 0xFFFFu;
+    uint32_t w[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t nib = (bits >> (4 * g)) & 0xFu;
+        const uint32_t spread = (nib * 0x00204081u) & 0x01010101u;  // bit i of the nibble -> byte i
+        uint32_t v = (spread * 0xFEu) ^ 0xFFFFFFFFu;                // 1 -> 0x01, 0 -> 0xFF
+        const int valid = b - (bit0 + 4 * g);                       // bytes of this word that are real code bits
+        if (valid <= 0) v = 0;
+        else if (valid < 4) v &= (1u << (8 * valid)) - 1u;
+        w[g] = v;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// queries: packed code words -> int8 rows [n, KP] in query order
+__global__ void __launch_bounds__(256) expand_q_kernel(const uint32_t* __restrict__ rows, int64_t n, int b, int Wr, int KP, uint8_t* __restrict__ out)
 {
     const int cpr = KP / 16;  // 16-byte chunks per row
     const int64_t total = n * cpr;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = i / cpr;
         const int c = (int)(i - row * cpr);
-        const int bit0 = 16 * c;
-        uint32_t bits = 0;
-        if (bit0 < b) bits = (__ldg(rows + row * Wr + (bit0 >> 5)) >> (bit0 & 31)) & 0xFFFFu;
-        uint32_t w[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const uint32_t nib = (bits >> (4 * g)) & 0xFu;
-            const uint32_t spread = (nib * 0x00204081u) & 0x01010101u;  // bit i of the nibble -> byte i
-            uint32_t v = (spread * 0xFEu) ^ 0xFFFFFFFFu;                // 1 -> 0x01, 0 -> 0xFF
-            const int valid = b - (bit0 + 4 * g);                       // bytes of this word that are real code bits
-            if (valid <= 0) v = 0;
-            else if (valid < 4) v &= (1u << (8 * valid)) - 1u;
-            w[g] = v;
-        }
-        *reinterpret_cast<uint4*>(out + row * KP + 16 * c) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(out + row * KP + 16 * c) = expand16(rows + row * Wr, 16 * c, b);
     }
+}
+
+// database rows [lo, hi) -> int8 rows; position p of a 32-row group holds row 8 (p & 3) + (p >> 2) of that group
+// (see the header: mask bit j of the epilogue is then row j).  Positions up to the end of the last group are
+// written; rows >= ndb become zero rows (the epilogue masks them out).
+__global__ void __launch_bounds__(256) expand_db_kernel(const uint32_t* __restrict__ rows, int64_t lo, int64_t hi_pad, int64_t ndb, int b, int Wr, int KP,
+                                                        uint8_t* __restrict__ out)
+{
+    const int cpr = KP / 16;
+    const int64_t total = (hi_pad - lo) * cpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pos = lo + i / cpr;
+        const int c = (int)(i % cpr);
+        const int p = (int)(pos & 31);
+        const int64_t src = (pos - p) + 8 * (p & 3) + (p >> 2);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (src < ndb) v = expand16(rows + src * Wr, 16 * c, b);
+        *reinterpret_cast<uint4*>(out + pos * KP + 16 * c) = v;
+    }
+}
+
+// threshold columns: qx[slot] = 32 int8, the first two sum to 2 T - b = -(b - 2 T)  (never-hit rows: -128, -128);
+// bx = 128 rows of (1, 1, 0, ...).  ip' = ip + (2 T - b) >= 0  <=>  d_H <= T.
+__global__ void __launch_bounds__(256) thr_columns_kernel(const int* __restrict__ thr, int64_t nq, int64_t nq_pad, int b, uint8_t* __restrict__ qx,
+                                                          uint8_t* __restrict__ bx)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq_pad) {
+        int c0 = -128, c1 = -128;
+        if (i < nq) {
+            const int T = thr[i];
+            if (T >= 0) {
+                const int v = 2 * T - b;  // in [-b, b], |v| <= 128
+                c0 = v >> 1;              // floor
+                c1 = v - c0;
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(qx + i * 32);
+        dst[0] = make_uint4((uint32_t)(c0 & 0xFF) | ((uint32_t)(c1 & 0xFF) << 8), 0, 0, 0);
+        dst[1] = make_uint4(0, 0, 0, 0);
+    }
+    if (i < 128) {
+        uint4* dst = reinterpret_cast<uint4*>(bx + i * 32);
+        dst[0] = make_uint4(0x0101u, 0, 0, 0);
+        dst[1] = make_uint4(0, 0, 0, 0);
+    }
+}
+
+// tcgen05.ld of 64 accumulator columns as 32 registers: register j = (column 2j+1 low half) << 16 | (column 2j low half)
+__device__ __forceinline__ void tmem_ld_64cols_pack16(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+// bytes 1 and 3 of a and of b, each replaced by 8 copies of its sign bit (PRMT sign-replicate mode)
+__device__ __forceinline__ uint32_t sign_bytes(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
 }
 
 template <int KP>
 __global__ void __launch_bounds__(kUmmaThreads, 2)
 select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_constant__ CUtensorMap tmap_db8,
-                   const __grid_constant__ CUtensorMap tmap_rows, UmmaSelectArgs a)
+                   const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_qx,
+                   const __grid_constant__ CUtensorMap tmap_bx, UmmaSelectArgs a)
 {
     constexpr int S = UmmaCfg<KP>::S;
     constexpr uint32_t A_BYTES = 2 * 128 * KP;
+    constexpr uint32_t AX_BYTES = 2 * 128 * kUmmaXBytes;
+    constexpr uint32_t BX_BYTES = kUmmaTileRows * kUmmaXBytes;
+    constexpr uint32_t FIXED_BYTES = A_BYTES + AX_BYTES + BX_BYTES;
     constexpr uint32_t B_BYTES = kUmmaTileRows * KP;
     constexpr uint32_t STAGE_BYTES = B_BYTES + kUmmaRowsMax;
     extern __shared__ __align__(1024) uint8_t usm[];
@@ -115,14 +221,17 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(&a_full, A_BYTES);
+            mbar_arrive_expect_tx(&a_full, FIXED_BYTES);
             tma_load_2d(base, &tmap_q8, smem_u32(&a_full), 0, (int)q0);
             tma_load_2d(base + 128 * KP, &tmap_q8, smem_u32(&a_full), 0, (int)q0 + 128);
+            tma_load_2d(base + A_BYTES, &tmap_qx, smem_u32(&a_full), 0, (int)q0);
+            tma_load_2d(base + A_BYTES + 128 * kUmmaXBytes, &tmap_qx, smem_u32(&a_full), 0, (int)q0 + 128);
+            tma_load_2d(base + A_BYTES + AX_BYTES, &tmap_bx, smem_u32(&a_full), 0, 0);
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % S;
                 mbar_wait(&empty_bar[s], (uint32_t)(((t / S) & 1) ^ 1));
                 mbar_arrive_expect_tx(&full_bar[s], B_BYTES + rows_bytes);
-                const uint32_t sb = base + A_BYTES + s * STAGE_BYTES;
+                const uint32_t sb = base + FIXED_BYTES + s * STAGE_BYTES;
                 const int r = (int)(row0 + (int64_t)t * kUmmaTileRows);
                 tma_load_2d(sb, &tmap_db8, smem_u32(&full_bar[s]), 0, r);
                 tma_load_2d(sb + B_BYTES, &tmap_rows, smem_u32(&full_bar[s]), 0, r);
@@ -132,18 +241,21 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_i8(128, 128);
             mbar_wait(&a_full, 0);
+            const uint64_t bxdesc = umma_desc_kmajor(base + A_BYTES + AX_BYTES, kUmmaXBytes);
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % S;
                 mbar_wait(&full_bar[s], (uint32_t)((t / S) & 1));
                 mbar_wait(&tmem_empty, (uint32_t)((t & 1) ^ 1));  // the epilogue has read the previous tile's accumulators
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t bdesc = umma_desc_kmajor(base + A_BYTES + s * STAGE_BYTES, KP);
+                const uint64_t bdesc = umma_desc_kmajor(base + FIXED_BYTES + s * STAGE_BYTES, KP);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint64_t adesc = umma_desc_kmajor(base + h * 128 * KP, KP);
 #pragma unroll
                     for (int k = 0; k < KP / 32; ++k)  // UMMA_K = 32 int8 = 32 bytes: start address advances by 2 (x16 B)
                         umma_i8(tmem_base + (uint32_t)(h * 128), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)(k != 0));
+                    // threshold K step: ip' = ip + (2 T_q - b)
+                    umma_i8(tmem_base + (uint32_t)(h * 128), umma_desc_kmajor(base + A_BYTES + h * 128 * kUmmaXBytes, kUmmaXBytes), bxdesc, idesc, 1u);
                 }
                 umma_commit(&tmem_full);
             }
@@ -156,64 +268,68 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
         const int64_t slot = q0 + h * 128 + quarter * 32 + lane;
         const bool valid = slot < a.nq;
         const int W = a.W, LW = a.LW, Wr = a.Wr;
+        const uint32_t sel = a.prmt_sel;
         uint32_t qw[4] = {0, 0, 0, 0}, ql[4] = {0, 0, 0, 0};
-        int thr_ip = 1 << 20;
         uint32_t pos = 0, nback = 0, start = 0, end = 0;  // front stack (d < T) grows up from start, back stack (d == T) down from end
         int Tq = -1;
         int64_t bin = -1;
         if (valid) {
             for (int w = 0; w < W && w < 4; ++w) qw[w] = a.q_rows[slot * Wr + w];
             for (int w = 0; w < LW && w < 4; ++w) ql[w] = a.q_rows[slot * Wr + W + w];
-            const int T = a.thr[slot];
-            Tq = T;
-            if (T >= 0) thr_ip = a.b - 2 * T;
+            Tq = a.thr[slot];
             bin = slot * a.P + split;
             start = (uint32_t)(bin * (int64_t)a.cap);
             end = start + a.cap;
             pos = start;
         }
+        const uint32_t live = (valid && Tq >= 0) ? 0xFFFFFFFFu : 0u;
         uint32_t* const lists = a.lists;
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 128);
+        const uint32_t full_a = smem_u32(&full_bar[0]), empty_a = smem_u32(&empty_bar[0]);
+        const uint32_t tfull_a = smem_u32(&tmem_full), tempty_a = smem_u32(&tmem_empty);
         for (int t = 0; t < ntiles; ++t) {
             const int s = t % S;
-            mbar_wait(&full_bar[s], (uint32_t)((t / S) & 1));  // packed rows of tile t have landed (observed by this thread)
-            mbar_wait(&tmem_full, (uint32_t)(t & 1));           // MMAs of tile t are complete
+            mbar_wait_a(full_a + 8u * s, (uint32_t)((t / S) & 1));  // packed rows of tile t have landed (observed by this thread)
+            mbar_wait_a(tfull_a, (uint32_t)(t & 1));                 // MMAs of tile t are complete
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t* srows = reinterpret_cast<const uint32_t*>(base_ptr + A_BYTES + s * STAGE_BYTES + B_BYTES);
+            const uint32_t* srows = reinterpret_cast<const uint32_t*>(base_ptr + FIXED_BYTES + s * STAGE_BYTES + B_BYTES);
             const int tile_rows = (int)min((int64_t)kUmmaTileRows, nrows - (int64_t)t * kUmmaTileRows);
             uint32_t hits[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int gg = 0; gg < 2; ++gg) {
                 uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 128 + g * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                      "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-                      "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-                      "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr));
+                tmem_ld_64cols_pack16(tmem_row + (uint32_t)(gg * 64), r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // bit (31 - j) of `miss` = sign(ip_j - thr) = 1 when row j is NOT a candidate
-                uint32_t miss = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) miss = __funnelshift_l((uint32_t)((int)r[j] - thr_ip), miss, 1);
-                const int vr = tile_rows - g * 32;  // rows of this 32-column group that exist in the database
-                hits[g] = vr >= 32 ? ~miss : (vr <= 0 ? 0u : (~miss & (0xFFFFFFFFu << (32 - vr))));
+                for (int g2 = 0; g2 < 2; ++g2) {
+                    // byte k of sign_bytes(r[2i], r[2i+1]) = 0xFF iff column 4i+k is negative (not a candidate)
+                    uint32_t miss = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) miss |= sign_bytes(r[g2 * 16 + 2 * i], r[g2 * 16 + 2 * i + 1], sel) & (0x01010101u << i);
+                    const int g = gg * 2 + g2;
+                    const int vr = tile_rows - g * 32;  // rows of this 32-column group that exist in the database
+                    hits[g] = ~miss & live & (vr >= 32 ? 0xFFFFFFFFu : (vr <= 0 ? 0u : ((1u << vr) - 1u)));
+                }
             }
             // the accumulators are consumed: let the MMA warp start the next tile while the hits are written out
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty);
-            // rare path: about R/Ndb of the pairs, ascending row order
-            while (hits[0] | hits[1] | hits[2] | hits[3]) {
-                const int g = hits[0] ? 0 : (hits[1] ? 1 : (hits[2] ? 2 : 3));
-                const uint32_t hm = hits[0] ? hits[0] : (hits[1] ? hits[1] : (hits[2] ? hits[2] : hits[3]));
-                const int j = __clz(hm);
-                const uint32_t cleared = hm & ~(0x80000000u >> j);
-                if (g == 0) hits[0] = cleared; else if (g == 1) hits[1] = cleared; else if (g == 2) hits[2] = cleared; else hits[3] = cleared;
-                const int rl = g * 32 + j;
+            if (lane == 0) mbar_arrive_a(tempty_a);
+            // rare path: about R/Ndb of the pairs, ascending row order (mask bit j of group g = row 32 g + j)
+            uint32_t h0 = hits[0], h1 = hits[1], h2 = hits[2], h3 = hits[3];
+            while (h0 | h1 | h2 | h3) {
+                // lowest non-empty word, its lowest set bit; cleared in place
+                uint32_t hm = h0;
+                int base_row = 0;
+                if (hm == 0) { hm = h1; base_row = 32; }
+                if (hm == 0) { hm = h2; base_row = 64; }
+                if (hm == 0) { hm = h3; base_row = 96; }
+                const int rl = base_row + (__ffs((int)hm) - 1);
+                const uint32_t cleared = hm & (hm - 1u);
+                if (base_row == 0) h0 = cleared;
+                else if (base_row == 32) h1 = cleared;
+                else if (base_row == 64) h2 = cleared;
+                else h3 = cleared;
                 const uint32_t* prow = srows + rl * Wr;
                 int d = 0;
                 uint32_t m = 0;
@@ -236,7 +352,7 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
                 if (eq) nback += 1; else pos += 1;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);  // shared-memory stage free for the producer
+            if (lane == 0) mbar_arrive_a(empty_a + 8u * s);  // shared-memory stage free for the producer
         }
         if (bin >= 0) { a.bin_cnt[bin] = pos - start; a.bin_cnt0[bin] = nback; }
     }
@@ -249,18 +365,18 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
-static int make_map_u8(CUtensorMap* map, const uint8_t* ptr, int64_t rows, int KP)
+static int make_map_u8(CUtensorMap* map, const uint8_t* ptr, int64_t rows, int row_bytes)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(HG_ECUDA, "select_umma: cuTensorMapEncodeTiled is not available from the driver");
-    cuuint64_t gdim[2] = {(cuuint64_t)KP, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)KP};
-    cuuint32_t box[2] = {(cuuint32_t)KP, (cuuint32_t)kUmmaTileRows};
+    cuuint64_t gdim[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)row_bytes, (cuuint32_t)kUmmaTileRows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    KP == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(HG_ECUDA, "select_umma: cuTensorMapEncodeTiled(u8) failed (%d)", (int)r);
+    const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HG_ECUDA, "select_umma: cuTensorMapEncodeTiled(u8, %d B rows) failed (%d)", row_bytes, (int)r);
     return HG_OK;
 }
 
@@ -286,42 +402,74 @@ int umma_select_kp(int b, int Wr)
     return b <= 64 ? 64 : 128;
 }
 
-int umma_expand(const uint32_t* rows, int64_t n, int b, int Wr, int KP, uint8_t* out, cudaStream_t st)
+static unsigned grid_for(int64_t threads_needed)
+{
+    const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(threads_needed, 256), (int64_t)sms * 16));
+}
+
+int umma_expand_q(const uint32_t* rows, int64_t n, int b, int Wr, int KP, uint8_t* out, cudaStream_t st)
 {
     if (n <= 0) return HG_OK;
-    const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
-    const int64_t total = n * (KP / 16);
-    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 256), (int64_t)sms * 16));
-    expand_codes_kernel<<<(unsigned)blocks, 256, 0, st>>>(rows, n, b, Wr, KP, out);
+    expand_q_kernel<<<grid_for(n * (KP / 16)), 256, 0, st>>>(rows, n, b, Wr, KP, out);
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    return HG_OK;
+}
+
+int umma_expand_db(const uint32_t* db_rows, int64_t lo, int64_t hi, int64_t ndb, int b, int Wr, int KP, uint8_t* db8, cudaStream_t st)
+{
+    if (hi <= lo) return HG_OK;
+    if ((lo & 31) || ((hi & 31) && hi != ndb)) return fail(HG_EINVAL, "select_umma: database chunks must be whole 32-row groups");
+    const int64_t hi_pad = round_up(hi, 32);
+    expand_db_kernel<<<grid_for((hi_pad - lo) * (KP / 16)), 256, 0, st>>>(db_rows, lo, hi_pad, ndb, b, Wr, KP, db8);
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    return HG_OK;
+}
+
+int umma_thr_columns(const int* thr, int64_t nq, int b, uint8_t* qx, uint8_t* bx, cudaStream_t st)
+{
+    const int64_t nq_pad = std::max<int64_t>(round_up(nq, 256), 128);
+    thr_columns_kernel<<<(unsigned)ceil_div(nq_pad, 256), 256, 0, st>>>(thr, nq, nq_pad, b, qx, bx);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     return HG_OK;
 }
 
 template <int KP>
-static int launch_umma(const CUtensorMap& tq, const CUtensorMap& tdb, const CUtensorMap& trows, const UmmaSelectArgs& a, cudaStream_t st)
+static int launch_umma(const CUtensorMap& tq, const CUtensorMap& tdb, const CUtensorMap& trows, const CUtensorMap& tqx, const CUtensorMap& tbx,
+                       const UmmaSelectArgs& a, cudaStream_t st)
 {
-    const size_t smem = (size_t)2 * 128 * KP + (size_t)UmmaCfg<KP>::S * (kUmmaTileRows * KP + kUmmaRowsMax) + 1024;
+    const size_t smem = (size_t)2 * 128 * KP + (size_t)3 * 128 * kUmmaXBytes + (size_t)UmmaCfg<KP>::S * (kUmmaTileRows * KP + kUmmaRowsMax) + 1024;
     static thread_local bool configured = false;
     if (!configured) {
         HG_CUDA_TRY(cudaFuncSetAttribute(select_umma_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid((unsigned)ceil_div(a.nq, 256), (unsigned)a.n_splits);
-    select_umma_kernel<KP><<<grid, kUmmaThreads, smem, st>>>(tq, tdb, trows, a);
+    select_umma_kernel<KP><<<grid, kUmmaThreads, smem, st>>>(tq, tdb, trows, tqx, tbx, a);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     return HG_OK;
 }
 
-int umma_select_launch(const UmmaSelectArgs& a, cudaStream_t st)
+int umma_select_launch(const UmmaSelectArgs& a_in, cudaStream_t st)
 {
-    CUtensorMap tq, tdb, trows;
+    UmmaSelectArgs a = a_in;
+    if (a.prmt_sel == 0) {
+        a.prmt_sel = 0xFDB9u;  // bytes 1, 3 of the first register, bytes 1, 3 of the second, sign-replicated
+        const char* v = getenv("HG_UMMA_PRMT");  // probe override (hex)
+        if (v && *v) a.prmt_sel = (uint32_t)strtoul(v, nullptr, 16);
+    }
+    CUtensorMap tq, tdb, trows, tqx, tbx;
     int rc;
     if ((rc = make_map_u8(&tq, a.q8, a.nq, a.KP)) != HG_OK) return rc;
-    if ((rc = make_map_u8(&tdb, a.db8, a.ndb, a.KP)) != HG_OK) return rc;
+    if ((rc = make_map_u8(&tdb, a.db8, round_up(a.ndb, 32), a.KP)) != HG_OK) return rc;
     if ((rc = make_map_rows(&trows, a.db_rows, a.ndb, a.Wr)) != HG_OK) return rc;
-    return a.KP == 128 ? launch_umma<128>(tq, tdb, trows, a, st) : launch_umma<64>(tq, tdb, trows, a, st);
+    if ((rc = make_map_u8(&tqx, a.qx, std::max<int64_t>(round_up(a.nq, 256), 128), kUmmaXBytes)) != HG_OK) return rc;
+    if ((rc = make_map_u8(&tbx, a.bx, 128, kUmmaXBytes)) != HG_OK) return rc;
+    return a.KP == 128 ? launch_umma<128>(tq, tdb, trows, tqx, tbx, a, st) : launch_umma<64>(tq, tdb, trows, tqx, tbx, a, st);
 }
 
 }  // namespace hg

@@ -31,8 +31,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar)
 }
 
 
-// shared-memory matrix descriptor of a K-major operand whose rows are `row_bytes` (64 or 128) wide and swizzled with
-// the matching mode; 8-row groups are 8*row_bytes apart
+// shared-memory matrix descriptor of a K-major operand whose rows are `row_bytes` (32, 64 or 128) wide and swizzled
+// with the matching mode; 8-row groups are 8*row_bytes apart
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, int row_bytes)
 {
     uint64_t d = 0;
@@ -40,7 +40,7 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, int row
     d |= (uint64_t)1 << 16;
     d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)(row_bytes == 128 ? 2 : 4) << 61;  // SWIZZLE_128B = 2, SWIZZLE_64B = 4
+    d |= (uint64_t)(row_bytes == 128 ? 2 : (row_bytes == 64 ? 4 : 6)) << 61;  // SWIZZLE_128B = 2, SWIZZLE_64B = 4, SWIZZLE_32B = 6
     return d;
 }
 
