@@ -95,19 +95,20 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
     int64_t P0 = std::max<int64_t>(1, ceil_div(target_ctas, units));
     int64_t SL = round_up(ceil_div(ndb, P0), p.TILE);
     if (p.umma_kp && ctas_mult == 1 && env_int("HG_UMMA_WAVES", 0) == 0) {
-        // Two CTAs are resident per SM and every CTA costs (rows of its split + a fixed start-up), so the launch
-        // takes ceil(CTAs / slots) rounds of the longest split.  Pick the split count with the shortest makespan
-        // instead of a fixed wave count: a grid of 4.05 waves would leave the last 0.05 wave running alone.
+        // One CTA ranks 256 queries against a PAIR of adjacent splits; two CTAs are resident per SM and every CTA costs
+        // (rows of its pair + a fixed start-up), so the launch takes ceil(CTAs / slots) rounds of the longest pair.
+        // Pick the pair count with the shortest makespan instead of a fixed wave count: a grid of 4.05 waves would
+        // leave the last 0.05 wave running alone.
         const int64_t slots = (int64_t)sms * 2;
         const int64_t startup_rows = 768;  // A-operand load + TMEM allocation + pipeline fill, in database rows
         double best = 1e300;
-        for (int64_t cand = 1; cand <= 4 * P0 + 8; ++cand) {
-            const int64_t sl = std::max<int64_t>(p.TILE, round_up(ceil_div(ndb, cand), p.TILE));
-            if (sl > kMaxSplitRows) continue;
-            const int64_t np = ceil_div(ndb, sl);
+        for (int64_t cand = 1; cand <= 2 * P0 + 8; ++cand) {
+            const int64_t pair = std::max<int64_t>(2 * p.TILE, round_up(ceil_div(ndb, cand), 2 * p.TILE));
+            if (pair / 2 > kMaxSplitRows) continue;
+            const int64_t np = ceil_div(ndb, pair);
             const int64_t rounds = ceil_div(units * np, slots);
-            const double cost = (double)rounds * (double)(sl + startup_rows);
-            if (cost < best * 0.995) { best = cost; SL = sl; }  // prefer fewer splits unless clearly better
+            const double cost = (double)rounds * (double)(pair + startup_rows);
+            if (cost < best * 0.995) { best = cost; SL = pair / 2; }  // prefer fewer splits unless clearly better
         }
     }
     SL = std::min<int64_t>(SL, kMaxSplitRows);
@@ -1115,10 +1116,11 @@ int plan_chunks(int64_t nq, int64_t ndb, int b, int L, int64_t R, int k_req, Map
     const Plan pl = make_plan(nq, ndb, b, L, R, kChunkCtasMult);
     if (!pl.ok || !out) return fail(HG_EINVAL, "plan_chunks: sizes out of range");
     if (ws_bytes) *ws_bytes = pl.total;
-    int K = std::max(1, std::min(std::min(k_req, pl.P), MapChunks::kMax));
+    int K = std::max(1, std::min(std::min(k_req, pl.P / 2), MapChunks::kMax));
     out->K = K;
     for (int k = 0; k < K; ++k) {
-        const int64_t s_lo = (int64_t)k * pl.P / K, s_hi = (int64_t)(k + 1) * pl.P / K;
+        // whole splits per chunk; even boundaries because the tensor-core select ranks splits in pairs
+        const int64_t s_lo = ((int64_t)k * pl.P / K) & ~int64_t(1), s_hi = k + 1 == K ? (int64_t)pl.P : (((int64_t)(k + 1) * pl.P / K) & ~int64_t(1));
         out->row_lo[k] = s_lo * pl.SL;
         out->row_hi[k] = std::min<int64_t>(s_hi * pl.SL, ndb);
     }

@@ -27,9 +27,10 @@
 
 namespace hg {
 
-constexpr int kUmmaThreads = 320;
+constexpr int kUmmaEpiWarps = 16;
+constexpr int kUmmaThreads = 32 * (2 + kUmmaEpiWarps);
 template <int KP> struct UmmaCfg { static constexpr int S = (KP == 64 ? 4 : 3); };  // ring depth: two CTAs must fit one SM
-constexpr int kUmmaTileRows = 128;
+constexpr int kUmmaHalfRows = 64;  // database rows per split and tile (a B tile = two of these)
 constexpr uint32_t kUmmaRowsMax = 128 * 8 * 4;  // packed-row bytes per stage (Wr <= 8)
 constexpr int kUmmaXBytes = 32;                 // threshold K step: one UMMA_K of int8 columns, SWIZZLE_32B rows
 
@@ -153,17 +154,14 @@ __global__ void __launch_bounds__(256) thr_columns_kernel(const int* __restrict_
     }
 }
 
-// tcgen05.ld of 64 accumulator columns as 32 registers: register j = (column 2j+1 low half) << 16 | (column 2j low half)
-__device__ __forceinline__ void tmem_ld_64cols_pack16(uint32_t taddr, uint32_t (&r)[32])
+// tcgen05.ld of 32 accumulator columns as 16 registers: register j = (column 2j+1 low half) << 16 | (column 2j low half)
+__device__ __forceinline__ void tmem_ld_32cols_pack16(uint32_t taddr, uint32_t (&r)[16])
 {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
 
@@ -175,6 +173,22 @@ __device__ __forceinline__ uint32_t sign_bytes(uint32_t a, uint32_t b, uint32_t 
     return d;
 }
 
+// 32 accumulator columns -> 32-bit mask of the NEGATIVE ones (bit 8k+i = column 4i+k)
+__device__ __forceinline__ uint32_t miss_mask32(uint32_t taddr, uint32_t sel)
+{
+    uint32_t r[16];
+    tmem_ld_32cols_pack16(taddr, r);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    uint32_t miss = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) miss |= sign_bytes(r[2 * i], r[2 * i + 1], sel) & (0x01010101u << i);
+    return miss;
+}
+
+// One CTA = 256 queries x TWO adjacent database splits (bins).  A 128-row B tile holds 64 rows of the first split
+// (accumulator columns 0..63) and 64 rows of the second (columns 64..127); every epilogue warp owns 32 queries x one
+// split, so 16 epilogue warps per CTA (32 per SM) share the CUDA-core work and each bin still has a single writer
+// that sees its rows in ascending order.
 template <int KP>
 __global__ void __launch_bounds__(kUmmaThreads, 2)
 select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_constant__ CUtensorMap tmap_db8,
@@ -184,30 +198,34 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
     constexpr int S = UmmaCfg<KP>::S;
     constexpr uint32_t A_BYTES = 2 * 128 * KP;
     constexpr uint32_t AX_BYTES = 2 * 128 * kUmmaXBytes;
-    constexpr uint32_t BX_BYTES = kUmmaTileRows * kUmmaXBytes;
+    constexpr uint32_t BX_BYTES = 128 * kUmmaXBytes;
     constexpr uint32_t FIXED_BYTES = A_BYTES + AX_BYTES + BX_BYTES;
-    constexpr uint32_t B_BYTES = kUmmaTileRows * KP;
+    constexpr uint32_t B_BYTES = 128 * KP;
     constexpr uint32_t STAGE_BYTES = B_BYTES + kUmmaRowsMax;
     extern __shared__ __align__(1024) uint8_t usm[];
     const uint32_t base = (smem_u32(usm) + 1023u) & ~1023u;
     uint8_t* const base_ptr = usm + (base - smem_u32(usm));
-    __shared__ __align__(8) uint64_t a_full, full_bar[S], empty_bar[S], tmem_full, tmem_empty;
+    __shared__ __align__(8) uint64_t bars[2 * S + 3];  // one array: every barrier is (one opaque base register) + constant
     __shared__ uint32_t tmem_base_slot;
+    uint64_t& a_full = bars[0];
+    uint64_t* const full_bar = bars + 1;
+    uint64_t* const empty_bar = bars + 1 + S;
+    uint64_t& tmem_full = bars[2 * S + 1];
+    uint64_t& tmem_empty = bars[2 * S + 2];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t q0 = (int64_t)blockIdx.x * 256;
-    const int split = a.split0 + (int)blockIdx.y;
-    const int64_t row0 = (int64_t)split * a.SL;
-    const int64_t row1 = min(row0 + a.SL, a.ndb);
-    const int64_t nrows = row1 > row0 ? row1 - row0 : 0;
-    const int ntiles = (int)((nrows + kUmmaTileRows - 1) / kUmmaTileRows);
-    const uint32_t rows_bytes = (uint32_t)kUmmaTileRows * a.Wr * 4;
+    const int split_a = a.split0 + 2 * (int)blockIdx.y;  // this CTA's bins: split_a and split_a + 1
+    const int64_t rowa = (int64_t)split_a * a.SL;
+    const int64_t rows_first = max((int64_t)0, min(a.SL, a.ndb - rowa));  // the first split is never shorter than the second
+    const int ntiles = (int)((rows_first + kUmmaHalfRows - 1) / kUmmaHalfRows);
+    const uint32_t half_rows_bytes = (uint32_t)kUmmaHalfRows * a.Wr * 4;
 
     if (threadIdx.x == 0) {
         mbar_init(&a_full, 1);
-        for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 8); }
+        for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kUmmaEpiWarps); }
         mbar_init(&tmem_full, 1);
-        mbar_init(&tmem_empty, 8);
+        mbar_init(&tmem_empty, kUmmaEpiWarps);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -227,14 +245,18 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
             tma_load_2d(base + A_BYTES, &tmap_qx, smem_u32(&a_full), 0, (int)q0);
             tma_load_2d(base + A_BYTES + 128 * kUmmaXBytes, &tmap_qx, smem_u32(&a_full), 0, (int)q0 + 128);
             tma_load_2d(base + A_BYTES + AX_BYTES, &tmap_bx, smem_u32(&a_full), 0, 0);
+            tma_load_2d(base + A_BYTES + AX_BYTES + 64 * kUmmaXBytes, &tmap_bx, smem_u32(&a_full), 0, 64);
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % S;
                 mbar_wait(&empty_bar[s], (uint32_t)(((t / S) & 1) ^ 1));
-                mbar_arrive_expect_tx(&full_bar[s], B_BYTES + rows_bytes);
+                mbar_arrive_expect_tx(&full_bar[s], B_BYTES + 2 * half_rows_bytes);
                 const uint32_t sb = base + FIXED_BYTES + s * STAGE_BYTES;
-                const int r = (int)(row0 + (int64_t)t * kUmmaTileRows);
-                tma_load_2d(sb, &tmap_db8, smem_u32(&full_bar[s]), 0, r);
-                tma_load_2d(sb + B_BYTES, &tmap_rows, smem_u32(&full_bar[s]), 0, r);
+                const int ra = (int)(rowa + (int64_t)t * kUmmaHalfRows);  // rows of the first split; the second one starts SL rows later
+                const int rb = (int)(rowa + a.SL + (int64_t)t * kUmmaHalfRows);
+                tma_load_2d(sb, &tmap_db8, smem_u32(&full_bar[s]), 0, ra);
+                tma_load_2d(sb + 64 * KP, &tmap_db8, smem_u32(&full_bar[s]), 0, rb);
+                tma_load_2d(sb + B_BYTES, &tmap_rows, smem_u32(&full_bar[s]), 0, ra);
+                tma_load_2d(sb + B_BYTES + half_rows_bytes, &tmap_rows, smem_u32(&full_bar[s]), 0, rb);
             }
         }
     } else if (warp == 1) {
@@ -261,12 +283,16 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
             }
         }
     } else {
-        // ---- epilogue: thread <-> query ----------------------------------------------------------------
+        // ---- epilogue: thread <-> (query, split) ---------------------------------------------------------
         const int e = warp - 2;
-        const int h = e >> 2;            // which 128-query half (A operand)
         const int quarter = warp & 3;    // TMEM lane quarter this warp may read
+        const int h = (e >> 2) & 1;      // which 128-query half (A operand)
+        const int ch = e >> 3;           // which split of the pair (accumulator columns 64 ch .. 64 ch + 63)
         const int64_t slot = q0 + h * 128 + quarter * 32 + lane;
-        const bool valid = slot < a.nq;
+        const int split = split_a + ch;
+        const int64_t row0 = (int64_t)split * a.SL;
+        const int64_t nrows = max((int64_t)0, min(a.SL, a.ndb - row0));
+        const bool valid = slot < a.nq && split < a.P;
         const int W = a.W, LW = a.LW, Wr = a.Wr;
         const uint32_t sel = a.prmt_sel;
         uint32_t qw[4] = {0, 0, 0, 0}, ql[4] = {0, 0, 0, 0};
@@ -284,52 +310,33 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
         }
         const uint32_t live = (valid && Tq >= 0) ? 0xFFFFFFFFu : 0u;
         uint32_t* const lists = a.lists;
-        const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 128);
-        const uint32_t full_a = smem_u32(&full_bar[0]), empty_a = smem_u32(&empty_bar[0]);
-        const uint32_t tfull_a = smem_u32(&tmem_full), tempty_a = smem_u32(&tmem_empty);
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 128 + ch * 64);
+        uint32_t bar0 = smem_u32(&bars[0]);
+        asm volatile("" : "+r"(bar0));  // keep the shared-window address in a register instead of re-deriving it per tile
+        const uint32_t full_a = bar0 + 8u, empty_a = bar0 + 8u * (1 + S);
+        const uint32_t tfull_a = bar0 + 8u * (2 * S + 1), tempty_a = bar0 + 8u * (2 * S + 2);
         for (int t = 0; t < ntiles; ++t) {
             const int s = t % S;
             mbar_wait_a(full_a + 8u * s, (uint32_t)((t / S) & 1));  // packed rows of tile t have landed (observed by this thread)
             mbar_wait_a(tfull_a, (uint32_t)(t & 1));                 // MMAs of tile t are complete
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t* srows = reinterpret_cast<const uint32_t*>(base_ptr + FIXED_BYTES + s * STAGE_BYTES + B_BYTES);
-            const int tile_rows = (int)min((int64_t)kUmmaTileRows, nrows - (int64_t)t * kUmmaTileRows);
-            uint32_t hits[4];
-#pragma unroll
-            for (int gg = 0; gg < 2; ++gg) {
-                uint32_t r[32];
-                tmem_ld_64cols_pack16(tmem_row + (uint32_t)(gg * 64), r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int g2 = 0; g2 < 2; ++g2) {
-                    // byte k of sign_bytes(r[2i], r[2i+1]) = 0xFF iff column 4i+k is negative (not a candidate)
-                    uint32_t miss = 0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) miss |= sign_bytes(r[g2 * 16 + 2 * i], r[g2 * 16 + 2 * i + 1], sel) & (0x01010101u << i);
-                    const int g = gg * 2 + g2;
-                    const int vr = tile_rows - g * 32;  // rows of this 32-column group that exist in the database
-                    hits[g] = ~miss & live & (vr >= 32 ? 0xFFFFFFFFu : (vr <= 0 ? 0u : ((1u << vr) - 1u)));
-                }
-            }
+            const uint32_t* srows = reinterpret_cast<const uint32_t*>(base_ptr + FIXED_BYTES + s * STAGE_BYTES + B_BYTES + ch * half_rows_bytes);
+            const int64_t left = nrows - (int64_t)t * kUmmaHalfRows;  // rows of my split from this tile on (may be <= 0)
+            const uint32_t m0 = miss_mask32(tmem_row, sel);
+            const uint32_t m1 = miss_mask32(tmem_row + 32u, sel);
             // the accumulators are consumed: let the MMA warp start the next tile while the hits are written out
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive_a(tempty_a);
-            // rare path: about R/Ndb of the pairs, ascending row order (mask bit j of group g = row 32 g + j)
-            uint32_t h0 = hits[0], h1 = hits[1], h2 = hits[2], h3 = hits[3];
-            while (h0 | h1 | h2 | h3) {
-                // lowest non-empty word, its lowest set bit; cleared in place
-                uint32_t hm = h0;
-                int base_row = 0;
-                if (hm == 0) { hm = h1; base_row = 32; }
-                if (hm == 0) { hm = h2; base_row = 64; }
-                if (hm == 0) { hm = h3; base_row = 96; }
-                const int rl = base_row + (__ffs((int)hm) - 1);
+            uint32_t h0 = ~m0 & live & (left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u)));
+            uint32_t h1 = ~m1 & live & (left >= 64 ? 0xFFFFFFFFu : (left <= 32 ? 0u : ((1u << (int)(left - 32)) - 1u)));
+            // rare path: about R/Ndb of the pairs, ascending row order (mask bit j of word g = row 32 g + j of the tile half)
+            while (h0 | h1) {
+                const bool first = h0 != 0u;
+                const uint32_t hm = first ? h0 : h1;
+                const int rl = (first ? 0 : 32) + (__ffs((int)hm) - 1);
                 const uint32_t cleared = hm & (hm - 1u);
-                if (base_row == 0) h0 = cleared;
-                else if (base_row == 32) h1 = cleared;
-                else if (base_row == 64) h2 = cleared;
-                else h3 = cleared;
+                if (first) h0 = cleared; else h1 = cleared;
                 const uint32_t* prow = srows + rl * Wr;
                 int d = 0;
                 uint32_t m = 0;
@@ -348,7 +355,7 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
                 }
                 const bool eq = d == Tq;
                 if (pos + nback < end)
-                    lists[eq ? end - 1u - nback : pos] = ((uint32_t)d * (1u << kIdxBits) + (uint32_t)(t * kUmmaTileRows + rl)) | (m ? 0x80000000u : 0u);
+                    lists[eq ? end - 1u - nback : pos] = ((uint32_t)d * (1u << kIdxBits) + (uint32_t)(t * kUmmaHalfRows + rl)) | (m ? 0x80000000u : 0u);
                 if (eq) nback += 1; else pos += 1;
             }
             __syncwarp();
@@ -365,13 +372,13 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
-static int make_map_u8(CUtensorMap* map, const uint8_t* ptr, int64_t rows, int row_bytes)
+static int make_map_u8(CUtensorMap* map, const uint8_t* ptr, int64_t rows, int row_bytes, int box_rows)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(HG_ECUDA, "select_umma: cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)row_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)row_bytes, (cuuint32_t)kUmmaTileRows};
+    cuuint32_t box[2] = {(cuuint32_t)row_bytes, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
@@ -386,7 +393,7 @@ static int make_map_rows(CUtensorMap* map, const uint32_t* ptr, int64_t rows, in
     if (!fn) return fail(HG_ECUDA, "select_umma: cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t gdim[2] = {(cuuint64_t)Wr, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)Wr * 4};
-    cuuint32_t box[2] = {(cuuint32_t)Wr, (cuuint32_t)kUmmaTileRows};
+    cuuint32_t box[2] = {(cuuint32_t)Wr, (cuuint32_t)kUmmaHalfRows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -441,13 +448,13 @@ template <int KP>
 static int launch_umma(const CUtensorMap& tq, const CUtensorMap& tdb, const CUtensorMap& trows, const CUtensorMap& tqx, const CUtensorMap& tbx,
                        const UmmaSelectArgs& a, cudaStream_t st)
 {
-    const size_t smem = (size_t)2 * 128 * KP + (size_t)3 * 128 * kUmmaXBytes + (size_t)UmmaCfg<KP>::S * (kUmmaTileRows * KP + kUmmaRowsMax) + 1024;
+    const size_t smem = (size_t)2 * 128 * KP + (size_t)3 * 128 * kUmmaXBytes + (size_t)UmmaCfg<KP>::S * (128 * KP + kUmmaRowsMax) + 1024;
     static thread_local bool configured = false;
     if (!configured) {
         HG_CUDA_TRY(cudaFuncSetAttribute(select_umma_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    dim3 grid((unsigned)ceil_div(a.nq, 256), (unsigned)a.n_splits);
+    dim3 grid((unsigned)ceil_div(a.nq, 256), (unsigned)ceil_div(a.n_splits, 2));
     select_umma_kernel<KP><<<grid, kUmmaThreads, smem, st>>>(tq, tdb, trows, tqx, tbx, a);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
@@ -464,11 +471,12 @@ int umma_select_launch(const UmmaSelectArgs& a_in, cudaStream_t st)
     }
     CUtensorMap tq, tdb, trows, tqx, tbx;
     int rc;
-    if ((rc = make_map_u8(&tq, a.q8, a.nq, a.KP)) != HG_OK) return rc;
-    if ((rc = make_map_u8(&tdb, a.db8, round_up(a.ndb, 32), a.KP)) != HG_OK) return rc;
+    if (a.split0 & 1) return fail(HG_EINVAL, "select_umma: a launch must start at an even split");
+    if ((rc = make_map_u8(&tq, a.q8, a.nq, a.KP, 128)) != HG_OK) return rc;
+    if ((rc = make_map_u8(&tdb, a.db8, round_up(a.ndb, 32), a.KP, kUmmaHalfRows)) != HG_OK) return rc;
     if ((rc = make_map_rows(&trows, a.db_rows, a.ndb, a.Wr)) != HG_OK) return rc;
-    if ((rc = make_map_u8(&tqx, a.qx, std::max<int64_t>(round_up(a.nq, 256), 128), kUmmaXBytes)) != HG_OK) return rc;
-    if ((rc = make_map_u8(&tbx, a.bx, 128, kUmmaXBytes)) != HG_OK) return rc;
+    if ((rc = make_map_u8(&tqx, a.qx, std::max<int64_t>(round_up(a.nq, 256), 128), kUmmaXBytes, 128)) != HG_OK) return rc;
+    if ((rc = make_map_u8(&tbx, a.bx, 128, kUmmaXBytes, kUmmaHalfRows)) != HG_OK) return rc;
     return a.KP == 128 ? launch_umma<128>(tq, tdb, trows, tqx, tbx, a, st) : launch_umma<64>(tq, tdb, trows, tqx, tbx, a, st);
 }
 
