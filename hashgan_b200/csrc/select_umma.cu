@@ -315,21 +315,28 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
         asm volatile("" : "+r"(bar0));  // keep the shared-window address in a register instead of re-deriving it per tile
         const uint32_t full_a = bar0 + 8u, empty_a = bar0 + 8u * (1 + S);
         const uint32_t tfull_a = bar0 + 8u * (2 * S + 1), tempty_a = bar0 + 8u * (2 * S + 2);
+        const int nrows32 = (int)nrows;                 // <= 2^21
+        const int nfull = nrows32 / kUmmaHalfRows;      // tiles in which all 64 rows of my split exist
+        int s = 0;
+        uint32_t ph = 0, tph = 0;                       // ring-stage parity, accumulator parity
+        const uint8_t* stage_rows = base_ptr + FIXED_BYTES + B_BYTES + ch * half_rows_bytes;
         for (int t = 0; t < ntiles; ++t) {
-            const int s = t % S;
-            mbar_wait_a(full_a + 8u * s, (uint32_t)((t / S) & 1));  // packed rows of tile t have landed (observed by this thread)
-            mbar_wait_a(tfull_a, (uint32_t)(t & 1));                 // MMAs of tile t are complete
+            mbar_wait_a(full_a + 8u * s, ph);   // packed rows of tile t have landed (observed by this thread)
+            mbar_wait_a(tfull_a, tph);          // MMAs of tile t are complete
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t* srows = reinterpret_cast<const uint32_t*>(base_ptr + FIXED_BYTES + s * STAGE_BYTES + B_BYTES + ch * half_rows_bytes);
-            const int64_t left = nrows - (int64_t)t * kUmmaHalfRows;  // rows of my split from this tile on (may be <= 0)
+            const uint32_t* srows = reinterpret_cast<const uint32_t*>(stage_rows + s * STAGE_BYTES);
             const uint32_t m0 = miss_mask32(tmem_row, sel);
             const uint32_t m1 = miss_mask32(tmem_row + 32u, sel);
             // the accumulators are consumed: let the MMA warp start the next tile while the hits are written out
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive_a(tempty_a);
-            uint32_t h0 = ~m0 & live & (left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << (int)left) - 1u)));
-            uint32_t h1 = ~m1 & live & (left >= 64 ? 0xFFFFFFFFu : (left <= 32 ? 0u : ((1u << (int)(left - 32)) - 1u)));
+            uint32_t h0 = ~m0 & live, h1 = ~m1 & live;
+            if (t >= nfull) {  // last tile(s) of the split: drop the rows that do not exist
+                const int left = nrows32 - t * kUmmaHalfRows;
+                h0 &= left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+                h1 &= left <= 32 ? 0u : ((1u << (left - 32)) - 1u);
+            }
             // rare path: about R/Ndb of the pairs, ascending row order (mask bit j of word g = row 32 g + j of the tile half)
             while (h0 | h1) {
                 const bool first = h0 != 0u;
@@ -360,6 +367,8 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
             }
             __syncwarp();
             if (lane == 0) mbar_arrive_a(empty_a + 8u * s);  // shared-memory stage free for the producer
+            tph ^= 1u;
+            if (++s == S) { s = 0; ph ^= 1u; }
         }
         if (bin >= 0) { a.bin_cnt[bin] = pos - start; a.bin_cnt0[bin] = nback; }
     }
