@@ -18,8 +18,9 @@ __device__ __forceinline__ bool to_bit(T v, int& any_bad)
     return v > (T)0;
 }
 
-// Aligned features: cols % 32 == 0 and contiguous input rows (ld == cols), so 32 consecutive flat elements are
-// exactly one output word.  Four independent 128-byte warp loads in flight per warp.
+// Aligned features: cols % 32 == 0, contiguous input rows (ld == cols) and a 16-byte aligned base, so 32 consecutive
+// flat elements are exactly one output word.  Every lane loads 16 bytes (4 features) per request, four requests
+// (2 KB per warp) in flight; the 8 lanes that share an output word OR their nibbles together with three shuffles.
 __global__ void __launch_bounds__(256) pack_sign_aligned_kernel(const float* __restrict__ in, int64_t total, int words_per_row,
                                                                  uint32_t* __restrict__ out, int row_words)
 {
@@ -27,23 +28,78 @@ __global__ void __launch_bounds__(256) pack_sign_aligned_kernel(const float* __r
     const int lane = threadIdx.x & 31;
     const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t base = warp_id * (32 * U); base < total; base += n_warps * (32 * U)) {
-        float v[U];
+    const float4* __restrict__ in4 = reinterpret_cast<const float4*>(in);
+    const int64_t total4 = total >> 2;  // total % 32 == 0
+    for (int64_t base = warp_id * (32 * U); base < total4; base += n_warps * (32 * U)) {
+        float4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t e = base + u * 32 + lane;
-            v[u] = (e < total) ? __ldg(in + e) : 0.0f;
+            v[u] = (e < total4) ? __ldg(in4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t ballot = __ballot_sync(0xffffffffu, v[u] > 0.0f);
-            const int64_t e0 = base + u * 32;
-            if (lane == 0 && e0 < total) {
-                const int64_t fw = e0 >> 5;
+            uint32_t nib = (v[u].x > 0.0f ? 1u : 0u) | (v[u].y > 0.0f ? 2u : 0u) | (v[u].z > 0.0f ? 4u : 0u) | (v[u].w > 0.0f ? 8u : 0u);
+            uint32_t word = nib << (4 * (lane & 7));
+            word |= __shfl_xor_sync(0xffffffffu, word, 1);
+            word |= __shfl_xor_sync(0xffffffffu, word, 2);
+            word |= __shfl_xor_sync(0xffffffffu, word, 4);
+            const int64_t e = base + u * 32 + lane;  // float4 index; output word = e / 8
+            if ((lane & 7) == 0 && e < total4) {
+                const int64_t fw = e >> 3;
                 const int64_t row = fw / words_per_row;
-                out[row * row_words + (fw - row * words_per_row)] = ballot;
+                out[row * row_words + (fw - row * words_per_row)] = word;
             }
         }
+    }
+}
+
+// Labels, contiguous rows of L integers: one warp packs 32 rows at a time.  The 32 L values are read with coalesced
+// loads (all in flight), each lane turns its values into bits of a shared-memory word, then every lane stores the
+// label words of one row.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_labels_kernel(const T* __restrict__ in, int64_t n, int L, uint32_t* __restrict__ out, int row_words,
+                                                           int col0, int LW, int* __restrict__ bad)
+{
+    extern __shared__ uint32_t lab_sm[];  // [warps][32 * LW]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t* sm = lab_sm + wib * 32 * LW;
+    const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const uint32_t inv = 0xFFFFFFFFu / (uint32_t)L + 1u;  // e / L for e < 32 * L <= 32 * 1024 via mulhi
+    int any_bad = 0;
+    for (int64_t r0 = warp_id * 32; r0 < n; r0 += n_warps * 32) {
+        const int rows = (int)min((int64_t)32, n - r0);
+        const int count = rows * L;
+        for (int i = lane; i < 32 * LW; i += 32) sm[i] = 0;
+        __syncwarp();
+        const T* src = in + r0 * L;
+        for (int e0 = 0; e0 < count; e0 += 32 * 8) {
+            T v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * 32 + lane;
+                v[u] = e < count ? src[e] : (T)0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * 32 + lane;
+                any_bad |= (v[u] != (T)0 && v[u] != (T)1);
+                if (v[u] == (T)1) {
+                    const int r = L == 1 ? e : (int)__umulhi((uint32_t)e, inv);
+                    const int c = e - r * L;
+                    atomicOr(&sm[r * LW + (c >> 5)], 1u << (c & 31));
+                }
+            }
+        }
+        __syncwarp();
+        if (lane < rows)
+            for (int w = 0; w < LW; ++w) out[(r0 + lane) * row_words + col0 + w] = sm[lane * LW + w];
+        __syncwarp();
+    }
+    if (bad != nullptr) {
+        any_bad = __any_sync(0xffffffffu, any_bad);
+        if (any_bad && lane == 0) atomicOr(bad, 1);
     }
 }
 
@@ -95,8 +151,9 @@ static int64_t grid_for(int64_t warps_needed, int mult)
 template <typename T>
 static int launch_labels(const void* lab, int64_t n, int L, uint32_t* rows, int row_words, int col0, int* bad, cudaStream_t st)
 {
-    const int64_t total = n * (int64_t)L;
-    pack_bits_kernel<T, true><<<(unsigned)grid_for(ceil_div(total, 32), 4), 256, 0, st>>>((const T*)lab, n, L, L, rows, row_words, col0, bad);
+    const int LW = (L + 31) / 32;
+    const size_t smem = (size_t)8 * 32 * LW * sizeof(uint32_t);
+    pack_labels_kernel<T><<<(unsigned)grid_for(ceil_div(n, 32), 1), 256, smem, st>>>((const T*)lab, n, L, rows, row_words, col0, LW, bad);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     return HG_OK;
@@ -139,7 +196,7 @@ extern "C" int hg_pack_rows(const float* d_feat, int64_t ld, const void* d_lab, 
     cudaStream_t st = (cudaStream_t)stream;
     HG_CUDA_TRY(cudaMemsetAsync(d_rows, 0, sizeof(uint32_t) * (size_t)n * Wr, st));
     const int64_t total = n * (int64_t)b;
-    if ((b & 31) == 0 && ld == b) {
+    if ((b & 31) == 0 && ld == b && (reinterpret_cast<uintptr_t>(d_feat) & 15) == 0) {
         hg::pack_sign_aligned_kernel<<<(unsigned)hg::grid_for(hg::ceil_div(total, 128), 1), 256, 0, st>>>(d_feat, total, b / 32, d_rows, Wr);
     } else {
         hg::pack_bits_kernel<float, false><<<(unsigned)hg::grid_for(hg::ceil_div(total, 32), 4), 256, 0, st>>>(d_feat, n, b, ld, d_rows, Wr, 0, nullptr);
