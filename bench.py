@@ -307,11 +307,23 @@ def main():
         roofline.update({
             "kernel": f"select_umma_kernel<{kp}>",
             "note": ("fused kernel: the distance matrix is never written, 'achieved' is the distance-matrix-equivalent rate (1 B/pair, "
-                     "SURVEY 8(d)). The contraction is an exact int8 tcgen05.mma; the kernel is bound by its CUDA-core threshold "
-                     "epilogue (ALU pipe), see 'tensor' for the tensor-pipe view"),
+                     "SURVEY 8(d)) -- the rate a kernel that materialises the uint8 distance matrix would need, so frac > 1 means "
+                     "faster than any such kernel could be on this HBM; 'traffic' is what the kernel really moves. The contraction "
+                     "is an exact int8 tcgen05.mma; the binding resource is the CUDA-core epilogue (integer ALU pipe), see "
+                     "'binding' and 'tensor'"),
             "tensor": {"achieved_tops_int8": tops, "peak_tops_int8": 2.0 * bf16, "frac": tops / (2.0 * bf16),
                        "peak_source": "2 x measured bf16 cuBLAS burst (MEASURED_PEAKS.json); int8 dense = 2 x bf16 on B200"},
         })
+        try:  # binding-resource view from the committed ncu capture of this kernel
+            summ = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary_C4.json")))["select_umma_kernel"]
+            roofline["binding"] = {
+                "resource": "integer ALU pipe of the epilogue warps (64 lanes/clk/SM)",
+                "alu_pipe_pct": summ["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]["value"],
+                "issue_slots_pct": summ["smsp__issue_active.avg.pct_of_peak_sustained_active"]["value"],
+                "tensor_pipe_pct": summ["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]["value"],
+                "source": "profiles/r01_ncu_summary_C4.json (ncu --set full of the same command)"}
+        except Exception:
+            pass
     else:
         popc_ops, popc_ms = C.c_double(), C.c_double()
         _native.check(lib.hg_popc_peak(C.byref(popc_ops), C.byref(popc_ms), 1 << 14, None))
