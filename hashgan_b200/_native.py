@@ -24,6 +24,7 @@ _i64, _int, _u32, _vp, _sz = C.c_int64, C.c_int, C.c_uint, C.c_void_p, C.c_size_
 # name -> (restype, argtypes); every symbol include/hashgan_b200.h declares
 SIGNATURES = {
     "hg_version": (_int, []),
+    "hg_crc32c": (C.c_uint32, [_vp, _sz, C.c_uint32]),
     "hg_last_error": (C.c_char_p, []),
     "hg_device_info": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), C.POINTER(_sz)]),
     "hg_code_words": (_int, [_int]),

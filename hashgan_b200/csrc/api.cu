@@ -166,6 +166,33 @@ static int arena_reserve(Arena& a, size_t bytes, size_t n_ap)
 
 extern "C" int hg_version(void) { return 100; }  // 0.1.0
 
+// CRC-32C (Castagnoli) of a host buffer, continuing from `crc`: the checksum TensorFlow checkpoints carry per table
+// block and per tensor (hashgan_b200/tf_checkpoint.py verifies them on read).  Plain host code, slicing-by-4 tables.
+extern "C" uint32_t hg_crc32c(const void* data, size_t n, uint32_t crc)
+{
+    static uint32_t tab[4][256];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+            tab[0][i] = c;
+        }
+        for (uint32_t i = 0; i < 256; ++i)
+            for (int t = 1; t < 4; ++t) tab[t][i] = (tab[t - 1][i] >> 8) ^ tab[0][tab[t - 1][i] & 0xFFu];
+        ready = true;
+    }
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    uint32_t c = crc ^ 0xFFFFFFFFu;
+    while (n >= 4) {
+        c ^= (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+        c = tab[3][c & 0xFFu] ^ tab[2][(c >> 8) & 0xFFu] ^ tab[1][(c >> 16) & 0xFFu] ^ tab[0][c >> 24];
+        p += 4; n -= 4;
+    }
+    while (n--) c = tab[0][(c ^ *p++) & 0xFFu] ^ (c >> 8);
+    return c ^ 0xFFFFFFFFu;
+}
+
 extern "C" int64_t hg_launch_count(int reset)
 {
     const long long v = hg::g_launches.load(std::memory_order_relaxed);

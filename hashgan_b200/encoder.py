@@ -85,6 +85,22 @@ class AlexNetWeights:
         return cls(t, hash_dim)
 
 
+    def override_from_tf_checkpoint(self, prefix: str, verify: bool = True) -> list:
+        """The reference's restore order (main.py:187-195): variables first take their .npy / initial values
+        (lib/architecture.py:199), then `Saver.restore(session, D_PRETRAINED_MODEL_PATH)` overwrites every discriminator
+        variable the checkpoint holds.  Returns the names that were overridden; a checkpoint tensor whose shape does not
+        match the graph raises, as the restore op does."""
+        from . import tf_checkpoint
+
+        have = tf_checkpoint.list_variables(prefix)
+        names = [n for n in self.tensors if n in have]
+        for name, a in tf_checkpoint.read_checkpoint(prefix, names, verify=verify).items():
+            if tuple(a.shape) != tuple(self.tensors[name].shape):
+                raise ValueError(f"{name}: checkpoint shape {tuple(a.shape)} != graph shape {tuple(self.tensors[name].shape)}")
+            self.tensors[name] = np.ascontiguousarray(a, dtype=np.float32)
+        return names
+
+
 class AlexNetHashEncoder:
     """images (uint8, [B, 3*wh*wh] as the loader yields them, lib/dataloader.py:110-113) -> CUDA float32 [B, HASH_DIM]."""
 

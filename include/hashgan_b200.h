@@ -35,6 +35,10 @@ extern "C" {
 #define HG_FLAG_TIMING 4u       /* record CUDA events around the phases, read back with hg_hamming_map_phase_ms */
 
 int hg_version(void);
+
+/* CRC-32C (Castagnoli) of a HOST buffer, continuing from `crc` (0 to start).  Used by the TensorFlow-checkpoint reader
+ * (hashgan_b200/tf_checkpoint.py) that replaces tf.train.Saver.restore, main.py:187-195.  hg_crc32c("123456789") = 0xE3069283. */
+uint32_t hg_crc32c(const void* data, size_t n, uint32_t crc);
 const char* hg_last_error(void);
 
 /* Device facts used for grid sizing (multiples of the SM count). */

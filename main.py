@@ -5,7 +5,8 @@
 
 prints the merged config, writes it to OUTPUT_DIR/config.txt, evaluates and prints `map_val: <float>`
 (main.py:197-199).  Only TRAIN.EVALUATE_MODE: True is in scope (training is not part of this build).
-Weights: MODEL.ALEXNET_PRETRAINED_MODEL_PATH (.npy dict, lib/architecture.py:199) when present; with
+Weights: MODEL.ALEXNET_PRETRAINED_MODEL_PATH (.npy dict, lib/architecture.py:199) when present, then overridden by the
+TensorFlow checkpoint MODEL.D_PRETRAINED_MODEL_PATH (main.py:187-195; hashgan_b200/tf_checkpoint.py); with
 EVAL.SYNTHETIC: True seeded synthetic weights and images stand in for missing files.
 """
 import argparse
@@ -32,9 +33,13 @@ def main(cfg):
         print("synthetic AlexNet weights (seed {})".format(cfg.EVAL.SEED))
     else:
         raise SystemExit("{} not found (set EVAL.SYNTHETIC: True for seeded synthetic weights)".format(npy))
-    if len(cfg.MODEL.D_PRETRAINED_MODEL_PATH) > 0 and not cfg.EVAL.SYNTHETIC:
-        raise SystemExit("TensorFlow checkpoints (MODEL.D_PRETRAINED_MODEL_PATH) cannot be read yet: export the discriminator "
-                         "variables to the .npy dict format or set EVAL.SYNTHETIC: True")
+    ckpt = cfg.MODEL.D_PRETRAINED_MODEL_PATH
+    if len(ckpt) > 0 and os.path.exists(ckpt + ".index"):
+        # main.py:193-194: Saver.restore overrides the initial values with the trained discriminator
+        names = weights.override_from_tf_checkpoint(ckpt)
+        print("discriminator checkpoint restored: {} ({} tensors)".format(ckpt, len(names)))
+    elif len(ckpt) > 0 and not cfg.EVAL.SYNTHETIC:
+        raise SystemExit("{}.index not found (set EVAL.SYNTHETIC: True to evaluate without the trained checkpoint)".format(ckpt))
     encoder = AlexNetHashEncoder(weights, lrn=(cfg.TRAIN.WGAN_SCALE == 0))
     if os.path.isdir(cfg.DATA.DATA_ROOT) and os.path.isdir(cfg.DATA.LIST_ROOT):
         dataloader = Dataloader(cfg.TRAIN.BATCH_SIZE, cfg.DATA.WIDTH_HEIGHT, cfg.DATA.LIST_ROOT, cfg.DATA.DATA_ROOT)
