@@ -164,7 +164,8 @@ _DEFAULTS = {
         "WGAN_SCALE_GP": 10.0, "ACGAN_SCALE_G": 0.1, "WGAN_SCALE_G": 1.0, "NORMED_CROSS_ENTROPY": True, "FAKE_RATIO": 1.0,
     },
     "EVAL": {                                            # additive, build-only
-        "BINARIZE": True,        # sign() the hash outputs and rank by Hamming distance (the B200 path)
+        "BINARIZE": True,        # sign() the hash outputs and rank by Hamming distance (the B200 hot path); False = rank the raw
+                                 # outputs by inner product exactly as lib/metric.py:13-14 does (hg_ip_map)
         "TIE_BREAK": "index",    # (distance asc, database row asc) == np.argsort(kind='stable')
         "NUM_GPUS": 1,           # row-shard database and queries over this many GPUs (torchrun)
         "DETERMINISTIC": True,   # no de-quantisation noise (main.py:147), no eval-time dropout (architecture.py:369,377)

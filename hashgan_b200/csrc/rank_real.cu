@@ -1,0 +1,392 @@
+// Real-valued ranking mode: the reference's LITERAL metric on un-binarised features.
+//
+//   lib/metric.py:13   ips = np.dot(query.output, database.output.T)            -> ip_keys_kernel  (fp32 FMA GEMM)
+//   lib/metric.py:14   ids = np.argsort(-ips, 1)          (only ids[:, :R] is used) -> topr_ap_kernel: exact radix SELECT of the
+//                                                                                   R-th key, ordered collect, stable radix sort
+//   lib/metric.py:16-23 label gather / compare / cumsum / AP                      -> topr_ap_kernel (label words of the packed rows)
+//
+// Order: inner product descending, ties by database row ascending (np.argsort(kind='stable'), the order the build
+// defines everywhere; the reference's default argsort leaves tie order to the NumPy build).  The inner products are fp32
+// sums in increasing k with FMA; OpenBLAS sums in another order, so keys may differ from the reference's in the last
+// bit -- rankings are identical whenever the products are exactly representable, and within fp32 rounding otherwise.
+//
+// Keys: key' = order-reversing integer image of ip (ascending key' <=> descending ip, -0 == +0), one uint32 per
+// (query, row) in a scratch matrix of one query chunk (the reference materialises 16 B per pair for ALL queries).
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace hg {
+
+__device__ __forceinline__ uint32_t ip_to_key(float ip)
+{
+    const uint32_t u = __float_as_uint(ip + 0.0f);  // -0 -> +0
+    return (u >> 31) ? u : (~u & 0x7FFFFFFFu);
+}
+__device__ __forceinline__ float key_to_ip(uint32_t k) { return __uint_as_float((k >> 31) ? k : (~k & 0x7FFFFFFFu)); }
+
+// ---- 1. all-pairs inner products of one query chunk -> keys ----------------------------------------------------------
+constexpr int IP_BM = 128, IP_BN = 128, IP_BK = 16;
+
+__global__ void __launch_bounds__(256) ip_keys_kernel(const float* __restrict__ Q, int64_t nq, const float* __restrict__ D, int64_t ndb, int b,
+                                                      uint32_t* __restrict__ keys, int64_t key_stride)
+{
+    __shared__ __align__(16) float sq[IP_BK][IP_BM + 4];
+    __shared__ __align__(16) float sd[IP_BK][IP_BN + 4];
+    const int tid = threadIdx.x;
+    const int64_t q0 = (int64_t)blockIdx.y * IP_BM, r0 = (int64_t)blockIdx.x * IP_BN;
+    const int tq = (tid >> 4) * 8, tr = (tid & 15) * 8;  // 16 x 16 threads, 8 x 8 outputs each
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    for (int k0 = 0; k0 < b; k0 += IP_BK) {
+        // 128 rows x 16 k per operand = 2048 values, 8 per thread: row = idx / 16, k = idx % 16 (k fastest: coalesced)
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int idx = it * 256 + tid;
+            const int row = idx >> 4, k = idx & 15;
+            const int64_t gq = q0 + row, gr = r0 + row;
+            sq[k][row] = (gq < nq && k0 + k < b) ? __ldg(Q + gq * b + k0 + k) : 0.0f;
+            sd[k][row] = (gr < ndb && k0 + k < b) ? __ldg(D + gr * b + k0 + k) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < IP_BK; ++k) {
+            float a[8], d[8];
+            *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&sq[k][tq]);
+            *reinterpret_cast<float4*>(a + 4) = *reinterpret_cast<const float4*>(&sq[k][tq + 4]);
+            *reinterpret_cast<float4*>(d) = *reinterpret_cast<const float4*>(&sd[k][tr]);
+            *reinterpret_cast<float4*>(d + 4) = *reinterpret_cast<const float4*>(&sd[k][tr + 4]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], d[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t gq = q0 + tq + i;
+        if (gq >= nq) continue;
+        uint32_t* out = keys + gq * key_stride + r0 + tr;
+        if (r0 + tr + 8 <= ndb && ((key_stride & 3) == 0)) {
+            *reinterpret_cast<uint4*>(out) = make_uint4(ip_to_key(acc[i][0]), ip_to_key(acc[i][1]), ip_to_key(acc[i][2]), ip_to_key(acc[i][3]));
+            *reinterpret_cast<uint4*>(out + 4) = make_uint4(ip_to_key(acc[i][4]), ip_to_key(acc[i][5]), ip_to_key(acc[i][6]), ip_to_key(acc[i][7]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (r0 + tr + j < ndb) out[j] = ip_to_key(acc[i][j]);
+        }
+    }
+}
+
+// ---- 2. per query: exact top-R by (key' ascending, row ascending), AP ---------------------------------------------------
+constexpr int TR_THREADS = 256;
+constexpr int TR_WARPS = TR_THREADS / 32;
+
+struct ToprParams {
+    const uint32_t* keys;   // [nq_chunk, key_stride]
+    int64_t key_stride, ndb, R;
+    const uint32_t* q_rows;   // packed rows of the chunk's queries (label words used)
+    const uint32_t* db_rows;
+    int W, LW, Wr;
+    uint2* bufA;  // global sort buffers [nq_chunk, R] when the top-R does not fit shared memory (else null)
+    uint2* bufB;
+    double* ap;   // [nq_chunk]
+    uint32_t* ids;  // [nq_chunk, R] or null
+    float* ips;     // [nq_chunk, R] or null
+    int32_t* rel;   // [nq_chunk] or null
+};
+
+__device__ __forceinline__ void dd_add_r(double& hi, double& lo, double x)
+{
+    const double s = __dadd_rn(hi, x);
+    const double bb = __dsub_rn(s, hi);
+    lo = __dadd_rn(lo, __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(x, bb)));
+    hi = s;
+}
+
+// block-wide exclusive scan of one value per thread (+ total), TR_THREADS threads
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp /*[TR_WARPS + 1]*/, uint32_t& total)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();  // s_warp may still be read from a previous call
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < TR_WARPS; ++i) {
+        const uint32_t c = s_warp[i];
+        if (i < w) base += c;
+        tot += c;
+    }
+    total = tot;
+    return base + inc - v;
+}
+
+// one radix-select pass: histogram of digit(key) over the keys whose higher bits equal `prefix`; returns the digit that
+// holds the `remaining`-th smallest such key and subtracts the keys below it from `remaining`
+template <int SHIFT, int BITS, int HI_SHIFT>
+__device__ __forceinline__ uint32_t select_pass(const uint32_t* __restrict__ keys, int64_t n, uint32_t prefix, uint32_t& remaining,
+                                                uint32_t* hist, uint32_t* s_misc)
+{
+    constexpr int NB = 1 << BITS;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < NB; i += TR_THREADS) hist[i] = 0;
+    __syncthreads();
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int64_t i0 = 0; i0 < n; i0 += TR_THREADS) {
+        const int64_t i = i0 + tid;
+        uint32_t bin = 0xFFFFFFFFu;
+        if (i < n) {
+            const uint32_t k = __ldg(keys + i);
+            if (HI_SHIFT >= 32 || (k >> (HI_SHIFT & 31)) == prefix) bin = (k >> SHIFT) & (NB - 1);
+        }
+        const uint32_t grp = __match_any_sync(0xffffffffu, bin);
+        if (bin != 0xFFFFFFFFu && (grp & lt) == 0) atomicAdd(&hist[bin], (uint32_t)__popc(grp));
+    }
+    __syncthreads();
+    // locate: thread t owns NB / TR_THREADS consecutive bins
+    constexpr int PER = NB / TR_THREADS;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) mine += hist[tid * PER + j];
+    uint32_t total;
+    const uint32_t before = block_excl_scan(mine, s_misc, total);
+    __syncthreads();
+    if (before < remaining && remaining <= before + mine) {  // exactly one thread
+        uint32_t cum = before;
+        for (int j = 0; j < PER; ++j) {
+            const uint32_t c = hist[tid * PER + j];
+            if (remaining <= cum + c) { s_misc[16] = (uint32_t)(tid * PER + j); s_misc[17] = remaining - cum; break; }
+            cum += c;
+        }
+    }
+    __syncthreads();
+    const uint32_t digit = s_misc[16];
+    remaining = s_misc[17];
+    __syncthreads();
+    return digit;
+}
+
+__global__ void __launch_bounds__(TR_THREADS) topr_ap_kernel(ToprParams p)
+{
+    extern __shared__ __align__(16) uint8_t tr_smem[];
+    __shared__ uint32_t hist[2048];
+    __shared__ uint32_t s_misc[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q = blockIdx.x;
+    const uint32_t* keys = p.keys + q * p.key_stride;
+    const int64_t n = p.ndb;
+    const uint32_t R = (uint32_t)p.R;
+    const uint32_t ltmask = (1u << lane) - 1u;
+
+    // ---- radix select: kappa = R-th smallest key', quota = how many rows equal to kappa belong to the top-R ----
+    uint32_t remaining = R;
+    const uint32_t d1 = select_pass<21, 11, 32>(keys, n, 0u, remaining, hist, s_misc);
+    const uint32_t d2 = select_pass<10, 11, 21>(keys, n, d1, remaining, hist, s_misc);
+    const uint32_t d3 = select_pass<0, 10, 10>(keys, n, (d1 << 11) | d2, remaining, hist, s_misc);
+    const uint32_t kappa = (d1 << 21) | (d2 << 10) | d3;
+    const uint32_t quota = remaining;
+    const uint32_t n_lt = R - quota;
+
+    uint2* A = p.bufA ? p.bufA + q * p.R : reinterpret_cast<uint2*>(tr_smem);
+    uint2* B = p.bufB ? p.bufB + q * p.R : reinterpret_cast<uint2*>(tr_smem) + p.R;
+
+    // ---- ordered collect: rows with key' < kappa in row order -> A[0, n_lt); the first `quota` rows with key' == kappa
+    //      in row order -> A[n_lt, R) (they rank last and are already in their final order) ----
+    uint32_t ql[4] = {0, 0, 0, 0};
+    for (int w = 0; w < p.LW && w < 4; ++w) ql[w] = p.q_rows[q * p.Wr + p.W + w];
+    uint32_t base_lt = 0, base_eq = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += TR_THREADS) {
+        const int64_t i = i0 + tid;
+        uint32_t k = 0xFFFFFFFFu;
+        bool is_lt = false, is_eq = false;
+        if (i < n) {
+            k = __ldg(keys + i);
+            is_lt = k < kappa;
+            is_eq = k == kappa;
+        }
+        const uint32_t bl = __ballot_sync(0xffffffffu, is_lt), be = __ballot_sync(0xffffffffu, is_eq);
+        if (lane == 0) { s_misc[warp] = (uint32_t)__popc(bl); s_misc[8 + warp] = (uint32_t)__popc(be); }
+        __syncthreads();
+        uint32_t off_lt = base_lt, off_eq = base_eq, tot_lt = 0, tot_eq = 0;
+#pragma unroll
+        for (int w = 0; w < TR_WARPS; ++w) {
+            const uint32_t cl = s_misc[w], ce = s_misc[8 + w];
+            if (w < warp) { off_lt += cl; off_eq += ce; }
+            tot_lt += cl; tot_eq += ce;
+        }
+        if (is_lt || (is_eq && off_eq + (uint32_t)__popc(be & ltmask) < quota)) {
+            uint32_t m = 0;
+            const uint32_t* lab = p.db_rows + i * p.Wr + p.W;
+            for (int w = 0; w < p.LW && w < 4; ++w) m |= ql[w] & __ldg(lab + w);
+            const uint32_t pos = is_lt ? off_lt + (uint32_t)__popc(bl & ltmask) : n_lt + off_eq + (uint32_t)__popc(be & ltmask);
+            A[pos] = make_uint2(k, (uint32_t)i | (m ? 0x80000000u : 0u));
+        }
+        base_lt += tot_lt;
+        base_eq += tot_eq;
+        __syncthreads();
+    }
+
+    // ---- stable LSD radix sort of A[0, n_lt) by key' (8-bit digits; a pass whose digit is constant is skipped) ----
+    uint2* src = A;
+    uint2* dst = B;
+    for (int pass = 0; pass < 4 && n_lt > 1; ++pass) {
+        const int shift = 8 * pass;
+        for (int i = tid; i < 256; i += TR_THREADS) hist[i] = 0;
+        __syncthreads();
+        for (uint32_t i0 = 0; i0 < n_lt; i0 += TR_THREADS) {
+            const uint32_t i = i0 + tid;
+            const uint32_t dg = i < n_lt ? ((src[i].x >> shift) & 255u) : 0xFFFFFFFFu;
+            const uint32_t grp = __match_any_sync(0xffffffffu, dg);
+            if (i < n_lt && (grp & ltmask) == 0) atomicAdd(&hist[dg], (uint32_t)__popc(grp));
+        }
+        __syncthreads();
+        const uint32_t mine = hist[tid];  // TR_THREADS == 256 bins
+        uint32_t total;
+        const uint32_t excl = block_excl_scan(mine, s_misc, total);
+        const bool constant = __syncthreads_or(mine == n_lt);
+        if (constant) continue;  // every key has the same digit: the order does not change
+        hist[tid] = excl;
+        __syncthreads();
+        for (uint32_t i0 = 0; i0 < n_lt; i0 += TR_THREADS) {
+            const uint32_t i = i0 + tid;
+            uint2 e = make_uint2(0, 0);
+            uint32_t dg = 0xFFFFFFFFu;
+            if (i < n_lt) { e = src[i]; dg = (e.x >> shift) & 255u; }
+            const uint32_t grp = __match_any_sync(0xffffffffu, dg);
+            const uint32_t rank_in_warp = (uint32_t)__popc(grp & ltmask);
+            const uint32_t act = __ballot_sync(0xffffffffu, i < n_lt);
+            // warps take their turn in order: stable
+            for (int w = 0; w < TR_WARPS; ++w) {
+                if (warp == w && i < n_lt) {
+                    const uint32_t at = hist[dg];
+                    dst[at + rank_in_warp] = e;
+                    __syncwarp(act);  // every lane of the warp has read its base before the group leaders advance it
+                    if (rank_in_warp == 0) hist[dg] = at + (uint32_t)__popc(grp);
+                }
+                __syncthreads();
+            }
+        }
+        uint2* t = src; src = dst; dst = t;
+        __syncthreads();
+    }
+
+    // ---- AP over the R rows in rank order: positions [0, n_lt) from `src`, [n_lt, R) from A ----
+    double acc = 0.0, acc_lo = 0.0;
+    uint32_t carry = 0;  // relevant rows before this chunk
+    for (uint32_t i0 = 0; i0 < R; i0 += TR_THREADS) {
+        const uint32_t i = i0 + tid;
+        uint2 e = make_uint2(0, 0);
+        if (i < R) e = i < n_lt ? src[i] : A[i];
+        const uint32_t m = (i < R) ? (e.y >> 31) : 0u;
+        uint32_t total;
+        const uint32_t before = block_excl_scan(m, s_misc, total);
+        if (i < R) {
+            if (p.ids) p.ids[q * p.R + i] = e.y & 0x7FFFFFFFu;
+            if (p.ips) p.ips[q * p.R + i] = key_to_ip(e.x);
+            if (m) dd_add_r(acc, acc_lo, (double)(carry + before + 1u) / (double)(i + 1u));
+        }
+        carry += total;
+    }
+    // deterministic reduction: lanes by xor tree, warps in order
+    for (int o = 1; o < 32; o <<= 1) {
+        const double ohi = __shfl_xor_sync(0xffffffffu, acc, o), olo = __shfl_xor_sync(0xffffffffu, acc_lo, o);
+        dd_add_r(acc, acc_lo, ohi);
+        acc_lo = __dadd_rn(acc_lo, olo);
+    }
+    __shared__ double s_hi[TR_WARPS], s_lo[TR_WARPS];
+    if (lane == 0) { s_hi[warp] = acc; s_lo[warp] = acc_lo; }
+    __syncthreads();
+    if (tid == 0) {
+        double hi = 0.0, lo = 0.0;
+        for (int w = 0; w < TR_WARPS; ++w) { dd_add_r(hi, lo, s_hi[w]); lo = __dadd_rn(lo, s_lo[w]); }
+        const double sum = __dadd_rn(hi, lo);
+        p.ap[q] = carry ? sum / (double)carry : __longlong_as_double(0x7ff8000000000000LL);
+        if (p.rel) p.rel[q] = (int32_t)carry;
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+struct RealPlan {
+    int64_t key_stride = 0, chunk = 0;
+    bool smem_sort = false;
+    size_t off_keys = 0, off_a = 0, off_b = 0, total = 0, smem = 0;
+    bool ok = false;
+};
+
+static RealPlan make_real_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, size_t ws_bytes /*0: size for the default chunk*/)
+{
+    RealPlan p;
+    if (nq <= 0 || ndb <= 0 || R <= 0 || R > ndb || ndb >= (int64_t(1) << 31) || b <= 0 || b > HG_MAX_BITS || hg_label_words(L) == 0) return p;
+    p.key_stride = round_up(ndb, 4);
+    p.smem_sort = (size_t)R * 16 <= 160 * 1024;
+    p.smem = p.smem_sort ? (size_t)R * 16 : 0;
+    const size_t per_query = (size_t)p.key_stride * 4 + (p.smem_sort ? 0 : (size_t)R * 16);
+    int64_t chunk = std::min<int64_t>(nq, 256);
+    if (ws_bytes) chunk = std::min<int64_t>(nq, (int64_t)((ws_bytes - 1024) / per_query));
+    if (chunk <= 0) return p;
+    p.chunk = chunk;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+    p.off_keys = take((size_t)chunk * p.key_stride * 4);
+    if (!p.smem_sort) { p.off_a = take((size_t)chunk * R * 8); p.off_b = take((size_t)chunk * R * 8); }
+    p.total = off;
+    p.ok = true;
+    return p;
+}
+
+}  // namespace hg
+
+extern "C" size_t hg_ip_map_workspace_bytes(int64_t nq, int64_t ndb, int b, int L, int64_t R)
+{
+    const hg::RealPlan p = hg::make_real_plan(nq, ndb, b, L, R, 0);
+    return p.ok ? p.total + 1024 : 0;
+}
+
+extern "C" int hg_ip_map(const float* d_q_feat, const uint32_t* d_q_rows, int64_t nq, const float* d_db_feat, const uint32_t* d_db_rows,
+                         int64_t ndb, int b, int L, int64_t R, double* d_ap, uint32_t* d_ids, float* d_ips, int32_t* d_rel,
+                         void* d_workspace, size_t workspace_bytes, void* stream)
+{
+    using namespace hg;
+    if (nq == 0) return HG_OK;
+    if (!d_q_feat || !d_q_rows || !d_db_feat || !d_db_rows || !d_ap || !d_workspace) return fail(HG_EINVAL, "hg_ip_map: NULL pointer");
+    const RealPlan pl = make_real_plan(nq, ndb, b, L, R, workspace_bytes);
+    if (!pl.ok) return fail(HG_EINVAL, "hg_ip_map: sizes out of range or workspace too small (nq=%lld ndb=%lld b=%d L=%d R=%lld ws=%zu)",
+                            (long long)nq, (long long)ndb, b, L, (long long)R, workspace_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = static_cast<char*>(d_workspace);
+    const int W = hg_code_words(b), LW = hg_label_words(L), Wr = hg_row_words(b, L);
+    static thread_local size_t configured = 0;
+    if (pl.smem > 48 * 1024 - 12 * 1024 && pl.smem > configured) {
+        HG_CUDA_TRY(cudaFuncSetAttribute(topr_ap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        configured = pl.smem;
+    }
+    for (int64_t s = 0; s < nq; s += pl.chunk) {
+        const int64_t n = std::min<int64_t>(pl.chunk, nq - s);
+        uint32_t* keys = reinterpret_cast<uint32_t*>(ws + pl.off_keys);
+        dim3 grid((unsigned)ceil_div(ndb, IP_BN), (unsigned)ceil_div(n, IP_BM));
+        ip_keys_kernel<<<grid, 256, 0, st>>>(d_q_feat + s * b, n, d_db_feat, ndb, b, keys, pl.key_stride);
+        count_launch();
+        HG_CUDA_TRY(cudaGetLastError());
+        ToprParams tp{};
+        tp.keys = keys; tp.key_stride = pl.key_stride; tp.ndb = ndb; tp.R = R;
+        tp.q_rows = d_q_rows + s * Wr; tp.db_rows = d_db_rows; tp.W = W; tp.LW = LW; tp.Wr = Wr;
+        tp.bufA = pl.smem_sort ? nullptr : reinterpret_cast<uint2*>(ws + pl.off_a);
+        tp.bufB = pl.smem_sort ? nullptr : reinterpret_cast<uint2*>(ws + pl.off_b);
+        tp.ap = d_ap + s; tp.ids = d_ids ? d_ids + s * R : nullptr; tp.ips = d_ips ? d_ips + s * R : nullptr; tp.rel = d_rel ? d_rel + s : nullptr;
+        topr_ap_kernel<<<(unsigned)n, TR_THREADS, pl.smem, st>>>(tp);
+        count_launch();
+        HG_CUDA_TRY(cudaGetLastError());
+    }
+    return HG_OK;
+}

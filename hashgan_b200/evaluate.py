@@ -32,5 +32,8 @@ def evaluate(encoder, dataloader, cfg, metric=None):
     """main.py:161-164."""
     db = forward_all(encoder, dataloader.db_gen, cfg.DATA.DB_SIZE, cfg)
     test = forward_all(encoder, dataloader.test_gen, cfg.DATA.TEST_SIZE, cfg)
-    metric = metric if metric is not None else MAPs(cfg.DATA.MAP_R)
+    if metric is None:
+        ev = getattr(cfg, "EVAL", None)
+        # EVAL.BINARIZE False = the reference's literal ranking of the raw tanh outputs (lib/metric.py:13-14)
+        metric = MAPs(cfg.DATA.MAP_R, binarize=bool(getattr(ev, "BINARIZE", True)))
     return metric.get_maps_by_feature(db, test)

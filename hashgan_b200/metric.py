@@ -28,7 +28,7 @@ import numpy as np
 
 from . import _native
 
-__all__ = ["MAPs", "MAPs_CQ", "pack_rows", "hamming_map_device"]
+__all__ = ["MAPs", "MAPs_CQ", "pack_rows", "hamming_map_device", "ip_map_device"]
 
 # One call of hg_hamming_map handles a query chunk whose workspace stays under this many bytes.
 DEFAULT_WORKSPACE_LIMIT = 24 << 30
@@ -206,6 +206,38 @@ def hamming_map_device(q_rows, db_rows, b: int, L: int, R: int, *, flags: int = 
     return ap, ids, dist, rel
 
 
+def ip_map_device(q_feat, q_rows, db_feat, db_rows, b: int, L: int, R: int, *, want_ids: bool = False, want_rel: bool = False,
+                  workspace_limit: int = DEFAULT_WORKSPACE_LIMIT):
+    """Per-query AP@R by REAL-VALUED inner-product ranking (C ABI: hg_ip_map; lib/metric.py:13-23 without binarisation).
+    q_feat / db_feat: float32 CUDA tensors [N, b]; q_rows / db_rows: their packed rows (label words).  Returns
+    (ap, ids, ips, rel); ids / ips / rel are None unless requested."""
+    torch = _torch()
+    lib = _native.lib()
+    device = db_feat.device
+    nq, ndb = int(q_feat.shape[0]), int(db_feat.shape[0])
+    if R > ndb:
+        raise ValueError(f"operands could not be broadcast together: R={R} exceeds the database size {ndb}")
+    if R <= 0:
+        raise ValueError("R must be positive")
+    with torch.cuda.device(device):
+        ap = torch.empty((nq,), dtype=torch.float64, device=device)
+        ids = torch.empty((nq, R), dtype=torch.int32, device=device) if want_ids else None
+        ips = torch.empty((nq, R), dtype=torch.float32, device=device) if want_ids else None
+        rel = torch.empty((nq,), dtype=torch.int32, device=device) if want_rel else None
+        if nq == 0:
+            return ap, ids, ips, rel
+        need = lib.hg_ip_map_workspace_bytes(nq, ndb, b, L, R)
+        if need == 0:
+            raise ValueError(f"sizes out of range for the inner-product ranking: ndb={ndb} b={b} L={L} R={R}")
+        one = lib.hg_ip_map_workspace_bytes(1, ndb, b, L, R)
+        ws_bytes = max(one, min(need, workspace_limit))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=device)
+        _native.check(lib.hg_ip_map(q_feat.data_ptr(), q_rows.data_ptr(), nq, db_feat.data_ptr(), db_rows.data_ptr(), ndb, b, L, R,
+                                    ap.data_ptr(), ids.data_ptr() if ids is not None else None, ips.data_ptr() if ips is not None else None,
+                                    rel.data_ptr() if rel is not None else None, ws.data_ptr(), ws_bytes, _stream_ptr(torch, device)))
+    return ap, ids, ips, rel
+
+
 class _Record:
     __slots__ = ("output", "label")
 
@@ -228,9 +260,11 @@ def _as_record(x):
 class MAPs:
     """Drop-in for ``lib.metric.MAPs`` (lib/metric.py:4-24)."""
 
-    def __init__(self, r, *, device=None, flags: int = 0, workspace_limit: int = DEFAULT_WORKSPACE_LIMIT):
+    def __init__(self, r, *, device=None, flags: int = 0, workspace_limit: int = DEFAULT_WORKSPACE_LIMIT, binarize: bool = True):
         self.R = r
         self.device = device
+        # binarize=False: rank by the real-valued inner products exactly as lib/metric.py:13-14 does (config: EVAL.BINARIZE)
+        self.binarize = binarize
         self.flags = flags
         self.workspace_limit = workspace_limit
         self.collect_stats = False
@@ -321,6 +355,8 @@ class MAPs:
         """Per-query AP@R as a NumPy float64 vector (NaN where the reference would skip the query).
         With ``want_ids`` also returns (ids [Nq, R] int64, dist [Nq, R] int32) in rank order."""
         database, query = _as_record(database), _as_record(query)
+        if not self.binarize:
+            return self._per_query_ap_real(database, query, want_ids)
         if not want_ids and not self.collect_stats:
             host = self._host_call(database, query)
             if host is not None:
@@ -335,6 +371,23 @@ class MAPs:
             raise ValueError("labels must be 0/1 integers (lib/metric.py:17-19 is only defined for 0/1 labels)")
         if want_ids:
             return ap_h, ids.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, dist.cpu().numpy().astype(np.int32) & 0xFFFF
+        return ap_h
+
+    def _per_query_ap_real(self, database, query, want_ids: bool):
+        """binarize=False: (ip descending, row ascending) ranking of the raw features; with want_ids returns
+        (ap, ids [Nq, R] int64, ips [Nq, R] float32)."""
+        torch = _torch()
+        device, bad, db_rows, q_rows, b, L = self._pack_all(database, query)
+        with torch.cuda.device(device):
+            db_f = _features_to_device(torch, database.output, device)
+            q_f = _features_to_device(torch, query.output, device)
+            ap, ids, ips, _ = ip_map_device(q_f, q_rows, db_f, db_rows, b, L, int(self.R), want_ids=want_ids,
+                                            workspace_limit=self.workspace_limit)
+            ap_h = ap.cpu().numpy()
+        if int(bad.item()) != 0:
+            raise ValueError("labels must be 0/1 integers (lib/metric.py:17-19 is only defined for 0/1 labels)")
+        if want_ids:
+            return ap_h, ids.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, ips.cpu().numpy()
         return ap_h
 
     def get_maps_by_feature(self, database, query):

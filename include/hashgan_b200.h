@@ -101,6 +101,20 @@ int hg_hamming_map_phase_ms(float out[6]);
  * The environment variable HG_SELECT_BACKEND=popc forces 0. */
 int hg_select_backend(int b, int L);
 
+/* Real-valued ranking mode -- the reference's literal behaviour on un-binarised features:
+ *   lib/metric.py:13  ips = np.dot(query.output, database.output.T)   fp32 inner products (FMA, increasing k)
+ *   lib/metric.py:14  np.argsort(-ips, 1)[:, :R]                       exact top-R by (ip descending, database row ascending)
+ *   lib/metric.py:16-23  per-query relevance / cumsum / AP             label words of the packed rows (hg_pack_rows)
+ * d_q_feat [nq, b] / d_db_feat [ndb, b] fp32 row-major; d_q_rows / d_db_rows packed rows of the same inputs (only their label
+ * words are read).  d_ap [nq] (NaN where no relevant row is in the top-R); optional d_ids [nq, R] (database rows in rank
+ * order), d_ips [nq, R] (their inner products), d_rel [nq].  The workspace holds the keys of one query chunk
+ * (4 B per pair; hg_ip_map_workspace_bytes sizes it for chunks of up to 256 queries, any size from one query up works).
+ * Exact by construction (radix select + stable radix sort): no sampling, no fallback.  Asynchronous on `stream`. */
+size_t hg_ip_map_workspace_bytes(int64_t nq, int64_t ndb, int b, int L, int64_t R);
+int hg_ip_map(const float* d_q_feat, const uint32_t* d_q_rows, int64_t nq, const float* d_db_feat, const uint32_t* d_db_rows,
+              int64_t ndb, int b, int L, int64_t R, double* d_ap, uint32_t* d_ids, float* d_ips, int32_t* d_rel,
+              void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Number of kernels this library has launched in this process so far (reset != 0 zeroes the counter). */
 int64_t hg_launch_count(int reset);
 
