@@ -168,7 +168,7 @@ def main():
 
     from hashgan_b200 import _native
     from hashgan_b200.metric import MAPs, hamming_map_device, pack_rows
-    from hashgan_b200.sharding import ShardedMAPs, gather_rows, gather_vector, row_shard
+    from hashgan_b200.sharding import ShardedMAPs, gather_rows, gather_vector, row_shard, shard_bounds
     from hashgan_b200.synthetic import Workload, make_workload
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -189,6 +189,7 @@ def main():
         wl_r = Workload(wl.name, wl.nq, 1, wl.b, wl.L, wl.R, wl.labels, wl.seed + 100 * rank, wl.note)
         _, _, q = make_workload(wl_r, ndb=1)
     lo, hi = row_shard(wl.ndb, rank, world)
+    db_counts = [b_ - a_ for a_, b_ in shard_bounds(wl.ndb, world)]
     db_f = torch.from_numpy(db.output[lo:hi]).to(device)
     db_l = torch.from_numpy(db.label[lo:hi]).to(device)
     q_f = torch.from_numpy(q.output).to(device)
@@ -200,11 +201,29 @@ def main():
     phase = (C.c_float * 6)()
     phase_acc = np.zeros(6)
 
+    # N > 1: the exchange step is fused into the pack kernel (peer-memory stores into every rank's symmetric database
+    # buffer + one signal-pad barrier); NCCL all-gather of the packed rows when symmetric memory is unavailable
+    sym, exchange = None, "none"
+    if world > 1:
+        exchange = "NCCL all-gather of packed rows"
+        if os.environ.get("HG_EXCHANGE", "push") != "nccl":
+            try:
+                from hashgan_b200.sharding import SymmetricRows
+
+                sym = SymmetricRows(wl.ndb, wl.b, wl.L, device)
+                exchange = "pack kernel pushes rows into every rank's symmetric buffer (NVLink peer stores) + 1 barrier"
+            except Exception as exc:  # pragma: no cover
+                print(f"[bench] symmetric memory unavailable ({exc}); using the NCCL all-gather", file=sys.stderr)
+                sym = None
+
     def step(timed: bool):
-        db_rows = pack_rows(db_f, db_l, device)
         q_rows = pack_rows(q_f, q_l, device)
-        if world > 1:
-            db_rows, _ = gather_rows(db_rows)  # the one exchange step: packed code + label words of every shard
+        if sym is not None:
+            db_rows = sym.pack(db_f, db_l, lo)
+        else:
+            db_rows = pack_rows(db_f, db_l, device)
+        if world > 1 and sym is None:
+            db_rows, _ = gather_rows(db_rows, counts=db_counts)  # the one exchange step: packed code + label words of every shard
         ap_d, _, _, _ = hamming_map_device(q_rows, db_rows, wl.b, wl.L, wl.R, flags=timing_flag)
         ap_host.copy_(ap_d, non_blocking=True)
         stream.synchronize()
@@ -254,7 +273,8 @@ def main():
         h_q = NS(output=pinned(q.output), label=pinned(q.label))
         h2d = sum(int(t.numel() * t.element_size()) for t in (h_db.output, h_db.label, h_q.output, h_q.label))
         d2h = wl.nq * 8
-        api = ShardedMAPs(wl.R, device=device) if world > 1 else MAPs(wl.R, device=device)
+        api = (ShardedMAPs(wl.R, device=device, db_counts=db_counts, query_counts=[wl.nq] * world, symmetric=sym is not None)
+               if world > 1 else MAPs(wl.R, device=device))
         for _ in range(2):
             e2e_map = api.get_maps_by_feature(h_db, h_q)
         barrier()
@@ -352,7 +372,7 @@ def main():
         "config": {"workload": f"{wl.name}: {wl.nq} queries/GPU x {wl.ndb} db, {wl.b}-bit, L={wl.L}, mAP@{wl.R}",
                    "queries_total": total_queries, "db_rows": wl.ndb, "bits": wl.b, "R": wl.R, "select_backend": ("tcgen05 int8 (select_umma_kernel)" if kp > 0 else "popc (select_kernel)"),
                    "l2": "no flush: every step re-reads the float32 feature matrix (256 MB at C4) which exceeds the 126 MB L2",
-                   "parallelism": f"query-sharded x{world}, db row-sharded for packing + 1 all-gather" if world > 1 else "1 GPU"},
+                   "parallelism": f"query-sharded x{world}, db row-sharded for packing; exchange: {exchange}" if world > 1 else "1 GPU"},
         "mAP": map_val, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

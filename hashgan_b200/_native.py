@@ -31,6 +31,7 @@ SIGNATURES = {
     "hg_label_words": (_int, [_int]),
     "hg_row_words": (_int, [_int, _int]),
     "hg_pack_rows": (_int, [_vp, _i64, _vp, _int, _i64, _int, _int, _vp, _vp, _vp]),
+    "hg_pack_rows_push": (_int, [_vp, _i64, _vp, _int, _i64, _int, _int, C.POINTER(_vp), _int, _vp, _vp]),
     "hg_hamming_map_workspace_bytes": (_sz, [_i64, _i64, _int, _int, _i64]),
     "hg_hamming_map": (_int, [_vp, _i64, _vp, _i64, _int, _int, _i64, _u32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hg_hamming_map_stats": (_int, [_vp, _sz, _i64, _i64, _int, _int, _i64, C.POINTER(_i64), _vp]),

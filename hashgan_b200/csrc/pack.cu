@@ -6,6 +6,8 @@
 // the label bits replace the per-query gather/compare of lib/metric.py:17-19.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace hg {
 
 template <typename T, bool LABEL>
@@ -140,6 +142,114 @@ __global__ void __launch_bounds__(256) pack_bits_kernel(const T* __restrict__ in
     }
 }
 
+// ---- pack fused with its exchange: the all-gather of packed rows as peer-memory stores -------------------------------
+// Multi-GPU evaluation row-shards the database, packs locally and all-gathers the packed rows (sharding.py).
+// Here the pack kernel IS the all-gather: every packed row is stored straight into the database buffer of every rank
+// (NVLink / NVSwitch peer pointers of a symmetric allocation; dst[r] already points at this rank's first row inside rank
+// r's buffer), so no separate collective runs -- one signal-pad barrier afterwards publishes the rows.
+// One warp packs 32 rows: code words by 16-byte loads + shuffles, label words through shared memory, then whole rows
+// (pads zeroed) are written with coalesced stores, destination by destination.
+constexpr int kMaxPeers = 16;
+struct PeerDst { uint32_t* p[kMaxPeers]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_rows_push_kernel(const float* __restrict__ feat, const T* __restrict__ lab, int64_t n, int b, int L,
+                                                             int W, int LW, int Wr, const __grid_constant__ PeerDst dst, int n_dst,
+                                                             int* __restrict__ bad)
+{
+    extern __shared__ uint32_t push_sm[];  // [warps][32 * Wr]: the 32 packed rows of the warp
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t* rows = push_sm + wib * 32 * Wr;
+    const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int cw = b >> 5;              // code words that carry bits (b % 32 == 0)
+    const int f4_per_row = b >> 2;      // float4 per feature row
+    const uint32_t inv = 0xFFFFFFFFu / (uint32_t)L + 1u;
+    int any_bad = 0;
+    for (int64_t r0 = warp_id * 32; r0 < n; r0 += n_warps * 32) {
+        const int nrows = (int)min((int64_t)32, n - r0);
+        for (int i = lane; i < 32 * Wr; i += 32) rows[i] = 0;
+        __syncwarp();
+        // code words: the warp's rows are one contiguous block of nrows * b floats
+        const float4* src4 = reinterpret_cast<const float4*>(feat + r0 * b);
+        const int total4 = nrows * f4_per_row;
+        for (int e0 = 0; e0 < total4; e0 += 32 * 4) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 32 + lane;
+                v[u] = e < total4 ? __ldg(src4 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t nib = (v[u].x > 0.0f ? 1u : 0u) | (v[u].y > 0.0f ? 2u : 0u) | (v[u].z > 0.0f ? 4u : 0u) | (v[u].w > 0.0f ? 8u : 0u);
+                uint32_t word = nib << (4 * (lane & 7));
+                word |= __shfl_xor_sync(0xffffffffu, word, 1);
+                word |= __shfl_xor_sync(0xffffffffu, word, 2);
+                word |= __shfl_xor_sync(0xffffffffu, word, 4);
+                const int e = e0 + u * 32 + lane;
+                if ((lane & 7) == 0 && e < total4) {
+                    const int fw = e >> 3;  // flat code word of the block
+                    const int row = fw / cw;
+                    rows[row * Wr + (fw - row * cw)] = word;
+                }
+            }
+        }
+        // label words
+        if (lab != nullptr) {
+            const T* lsrc = lab + r0 * L;
+            const int count = nrows * L;
+            for (int e0 = 0; e0 < count; e0 += 32 * 8) {
+                T v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + u * 32 + lane;
+                    v[u] = e < count ? lsrc[e] : (T)0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + u * 32 + lane;
+                    any_bad |= (v[u] != (T)0 && v[u] != (T)1);
+                    if (v[u] == (T)1) {
+                        const int r = L == 1 ? e : (int)__umulhi((uint32_t)e, inv);
+                        const int c = e - r * L;
+                        atomicOr(&rows[r * Wr + W + (c >> 5)], 1u << (c & 31));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // push: nrows * Wr contiguous words per destination
+        const int words = nrows * Wr;
+        for (int d = 0; d < n_dst; ++d) {
+            uint32_t* out = dst.p[d] + r0 * Wr;
+            if ((Wr & 3) == 0) {
+                for (int i = lane * 4; i < words; i += 128) *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<const uint4*>(rows + i);
+            } else {
+                for (int i = lane; i < words; i += 32) out[i] = rows[i];
+            }
+        }
+        __syncwarp();
+    }
+    if (bad != nullptr) {
+        any_bad = __any_sync(0xffffffffu, any_bad);
+        if (any_bad && lane == 0) atomicOr(bad, 1);
+    }
+}
+
+template <typename T>
+static int launch_push(const float* feat, const void* lab, int64_t n, int b, int L, int W, int LW, int Wr, const PeerDst& dst, int n_dst, int* bad,
+                       cudaStream_t st)
+{
+    const size_t smem = (size_t)8 * 32 * Wr * sizeof(uint32_t);
+    const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
+    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(ceil_div(ceil_div(n, 32), 8), (int64_t)sms * 8));
+    pack_rows_push_kernel<T><<<(unsigned)blocks, 256, smem, st>>>(feat, (const T*)lab, n, b, L, W, LW, Wr, dst, n_dst, bad);
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    return HG_OK;
+}
+
 static int64_t grid_for(int64_t warps_needed, int mult)
 {
     const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
@@ -208,5 +318,30 @@ extern "C" int hg_pack_rows(const float* d_feat, int64_t ld, const void* d_lab, 
         case 8: return hg::launch_labels<long long>(d_lab, n, L, d_rows, Wr, W, d_bad, st);
         case 4: return hg::launch_labels<int>(d_lab, n, L, d_rows, Wr, W, d_bad, st);
         default: return hg::launch_labels<signed char>(d_lab, n, L, d_rows, Wr, W, d_bad, st);
+    }
+}
+
+extern "C" int hg_pack_rows_push(const float* d_feat, int64_t ld, const void* d_lab, int lab_elem_bytes, int64_t n, int b, int L,
+                                 uint32_t* const* h_dst_rows, int n_dst, int* d_bad, void* stream)
+{
+    const int W = hg_code_words(b), LW = hg_label_words(L), Wr = hg_row_words(b, L);
+    if (W == 0 || LW == 0) return hg::fail(HG_EINVAL, "hg_pack_rows_push: unsupported b=%d / L=%d", b, L);
+    if (n < 0 || !h_dst_rows || n_dst < 1 || n_dst > hg::kMaxPeers) return hg::fail(HG_EINVAL, "hg_pack_rows_push: 1..%d destinations", hg::kMaxPeers);
+    if ((b & 31) != 0 || ld != b || (reinterpret_cast<uintptr_t>(d_feat) & 15) != 0)
+        return hg::fail(HG_ERANGE, "hg_pack_rows_push: needs b %% 32 == 0 and contiguous 16-byte aligned feature rows (use hg_pack_rows + all-gather)");
+    if (d_lab && lab_elem_bytes != 8 && lab_elem_bytes != 4 && lab_elem_bytes != 1)
+        return hg::fail(HG_EINVAL, "hg_pack_rows_push: lab_elem_bytes must be 8, 4 or 1 (got %d)", lab_elem_bytes);
+    if (n == 0) return HG_OK;
+    hg::PeerDst dst{};
+    for (int d = 0; d < n_dst; ++d) {
+        if (!h_dst_rows[d] || (reinterpret_cast<uintptr_t>(h_dst_rows[d]) & ((Wr & 3) == 0 ? 15 : 3)) != 0)
+            return hg::fail(HG_EINVAL, "hg_pack_rows_push: destination %d is NULL or misaligned", d);
+        dst.p[d] = h_dst_rows[d];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (d_lab ? lab_elem_bytes : 8) {
+        case 8: return hg::launch_push<long long>(d_feat, d_lab, n, b, L, W, LW, Wr, dst, n_dst, d_bad, st);
+        case 4: return hg::launch_push<int>(d_feat, d_lab, n, b, L, W, LW, Wr, dst, n_dst, d_bad, st);
+        default: return hg::launch_push<signed char>(d_feat, d_lab, n, b, L, W, LW, Wr, dst, n_dst, d_bad, st);
     }
 }

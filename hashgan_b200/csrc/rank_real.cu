@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) ip_keys_kernel(const float* __restrict__ 
 }
 
 // ---- 2. per query: exact top-R by (key' ascending, row ascending), AP ---------------------------------------------------
-constexpr int TR_THREADS = 256;
+constexpr int TR_THREADS = 512;
 constexpr int TR_WARPS = TR_THREADS / 32;
 
 struct ToprParams {
@@ -166,13 +166,13 @@ __device__ __forceinline__ uint32_t select_pass(const uint32_t* __restrict__ key
         uint32_t cum = before;
         for (int j = 0; j < PER; ++j) {
             const uint32_t c = hist[tid * PER + j];
-            if (remaining <= cum + c) { s_misc[16] = (uint32_t)(tid * PER + j); s_misc[17] = remaining - cum; break; }
+            if (remaining <= cum + c) { s_misc[2 * TR_WARPS] = (uint32_t)(tid * PER + j); s_misc[2 * TR_WARPS + 1] = remaining - cum; break; }
             cum += c;
         }
     }
     __syncthreads();
-    const uint32_t digit = s_misc[16];
-    remaining = s_misc[17];
+    const uint32_t digit = s_misc[2 * TR_WARPS];
+    remaining = s_misc[2 * TR_WARPS + 1];
     __syncthreads();
     return digit;
 }
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(TR_THREADS) topr_ap_kernel(ToprParams p)
 {
     extern __shared__ __align__(16) uint8_t tr_smem[];
     __shared__ uint32_t hist[2048];
-    __shared__ uint32_t s_misc[32];
+    __shared__ uint32_t s_misc[2 * TR_WARPS + 8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q = blockIdx.x;
     const uint32_t* keys = p.keys + q * p.key_stride;
@@ -216,12 +216,12 @@ __global__ void __launch_bounds__(TR_THREADS) topr_ap_kernel(ToprParams p)
             is_eq = k == kappa;
         }
         const uint32_t bl = __ballot_sync(0xffffffffu, is_lt), be = __ballot_sync(0xffffffffu, is_eq);
-        if (lane == 0) { s_misc[warp] = (uint32_t)__popc(bl); s_misc[8 + warp] = (uint32_t)__popc(be); }
+        if (lane == 0) { s_misc[warp] = (uint32_t)__popc(bl); s_misc[TR_WARPS + warp] = (uint32_t)__popc(be); }
         __syncthreads();
         uint32_t off_lt = base_lt, off_eq = base_eq, tot_lt = 0, tot_eq = 0;
 #pragma unroll
         for (int w = 0; w < TR_WARPS; ++w) {
-            const uint32_t cl = s_misc[w], ce = s_misc[8 + w];
+            const uint32_t cl = s_misc[w], ce = s_misc[TR_WARPS + w];
             if (w < warp) { off_lt += cl; off_eq += ce; }
             tot_lt += cl; tot_eq += ce;
         }
@@ -251,12 +251,12 @@ __global__ void __launch_bounds__(TR_THREADS) topr_ap_kernel(ToprParams p)
             if (i < n_lt && (grp & ltmask) == 0) atomicAdd(&hist[dg], (uint32_t)__popc(grp));
         }
         __syncthreads();
-        const uint32_t mine = hist[tid];  // TR_THREADS == 256 bins
+        const uint32_t mine = tid < 256 ? hist[tid] : 0u;  // 256 digit bins
         uint32_t total;
         const uint32_t excl = block_excl_scan(mine, s_misc, total);
         const bool constant = __syncthreads_or(mine == n_lt);
         if (constant) continue;  // every key has the same digit: the order does not change
-        hist[tid] = excl;
+        if (tid < 256) hist[tid] = excl;
         __syncthreads();
         for (uint32_t i0 = 0; i0 < n_lt; i0 += TR_THREADS) {
             const uint32_t i = i0 + tid;
@@ -332,7 +332,7 @@ static RealPlan make_real_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R,
     p.smem_sort = (size_t)R * 16 <= 160 * 1024;
     p.smem = p.smem_sort ? (size_t)R * 16 : 0;
     const size_t per_query = (size_t)p.key_stride * 4 + (p.smem_sort ? 0 : (size_t)R * 16);
-    int64_t chunk = std::min<int64_t>(nq, 256);
+    int64_t chunk = std::min<int64_t>(nq, 592);  // 2 resident CTAs x 148 SMs x 2 rounds
     if (ws_bytes) chunk = std::min<int64_t>(nq, (int64_t)((ws_bytes - 1024) / per_query));
     if (chunk <= 0) return p;
     p.chunk = chunk;

@@ -17,7 +17,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-__all__ = ["row_shard", "shard_bounds", "gather_rows", "gather_vector", "ShardedMAPs"]
+__all__ = ["row_shard", "shard_bounds", "gather_rows", "gather_vector", "ShardedMAPs", "SymmetricRows"]
 
 
 def shard_bounds(n: int, world: int) -> List[Tuple[int, int]]:
@@ -41,19 +41,26 @@ def _dist():
     return dist
 
 
-def gather_rows(local, group=None):
+def gather_rows(local, group=None, counts: Optional[Sequence[int]] = None):
     """All-gather of row blocks with possibly different row counts.  local: [n_r, ...] tensor (any device the
-    group's backend supports).  Returns the [sum n_r, ...] concatenation in rank order plus the row counts."""
+    group's backend supports).  Returns the [sum n_r, ...] concatenation in rank order plus the row counts.
+    `counts` (rows of every rank, e.g. from shard_bounds) skips the count exchange and its host synchronisation,
+    which leaves ONE collective on the stream and lets the host run ahead of the GPU."""
     import torch
 
     dist = _dist()
     world = dist.get_world_size(group)
     if world == 1:
         return local, [int(local.shape[0])]
-    n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    counts_t = torch.empty((world,), dtype=torch.int64, device=local.device)
-    dist.all_gather_into_tensor(counts_t, n_local, group=group)
-    counts = [int(x) for x in counts_t.cpu().tolist()]
+    if counts is not None:
+        counts = [int(c) for c in counts]
+        if len(counts) != world or counts[dist.get_rank(group)] != int(local.shape[0]):
+            raise ValueError(f"counts {counts} do not describe this rank's block of {int(local.shape[0])} rows")
+    else:
+        n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        counts_t = torch.empty((world,), dtype=torch.int64, device=local.device)
+        dist.all_gather_into_tensor(counts_t, n_local, group=group)
+        counts = [int(x) for x in counts_t.cpu().tolist()]
     n_max = max(counts)
     tail = tuple(local.shape[1:])
     if all(c == n_max for c in counts):
@@ -67,9 +74,68 @@ def gather_rows(local, group=None):
     return torch.cat([buf[r, : counts[r]] for r in range(world)], 0), counts
 
 
-def gather_vector(local, group=None):
-    out, _ = gather_rows(local.reshape(-1, 1), group)
+def gather_vector(local, group=None, counts: Optional[Sequence[int]] = None):
+    out, _ = gather_rows(local.reshape(-1, 1), group, counts)
     return out.reshape(-1)
+
+
+class SymmetricRows:
+    """The exchange step fused into the pack kernel (C ABI: hg_pack_rows_push): every rank owns a full-size packed
+    database buffer in SYMMETRIC memory (torch.distributed._symmetric_memory: same allocation on every GPU, peer
+    pointers over NVLink / NVSwitch); the pack kernel stores each packed row into all of them, one signal-pad barrier
+    publishes the rows.  No NCCL collective, no extra pass over the packed rows.
+
+    Two buffers alternate: a rank may already pack step t+1 into its peers while they still rank step t.  A rank's
+    writes into buffer i of step t+2 happen after barrier t+1, which every peer enters only after its step-t ranking
+    (the last reader of buffer i) has finished on its stream."""
+
+    def __init__(self, ndb: int, b: int, L: int, device, group=None):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _native
+
+        dist = _dist()
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.ndb, self.b, self.L, self.Wr = int(ndb), int(b), int(L), _native.row_words(b, L)
+        self.device = torch.device(device)
+        self.lib = _native.lib()
+        self.bufs, self.handles = [], []
+        with torch.cuda.device(self.device):
+            for _ in range(2):
+                t = symm.empty((self.ndb, self.Wr), dtype=torch.int32, device=self.device)
+                self.handles.append(symm.rendezvous(t, self.group))
+                self.bufs.append(t)
+        self.step = 0
+
+    def pack(self, feat, lab, row_lo: int, bad_flag=None):
+        """Packs this rank's rows [row_lo, row_lo + n) into every rank's buffer; returns this rank's full buffer,
+        valid on the current stream once the call returns (kernel + barrier are enqueued)."""
+        import ctypes as C
+
+        import torch
+
+        from . import _native, metric
+
+        i = self.step & 1
+        self.step += 1
+        h = self.handles[i]
+        with torch.cuda.device(self.device):
+            f = metric._features_to_device(torch, feat, self.device)
+            t, nbytes = metric._labels_to_device(torch, lab, self.device)
+            n = int(f.shape[0])
+            if int(f.shape[1]) != self.b or int(t.shape[1]) != self.L or t.shape[0] != n or row_lo + n > self.ndb:
+                raise ValueError("block does not fit the symmetric database buffer")
+            off = int(row_lo) * self.Wr * 4
+            ptrs = (C.c_void_p * self.world)(*[int(p) + off for p in h.buffer_ptrs])
+            stream = torch.cuda.current_stream(self.device)
+            _native.check(self.lib.hg_pack_rows_push(f.data_ptr(), self.b, t.data_ptr(), nbytes, n, self.b, self.L, ptrs, self.world,
+                                                     bad_flag.data_ptr() if bad_flag is not None else None, int(stream.cuda_stream)))
+            f.record_stream(stream)
+            t.record_stream(stream)
+            h.barrier(channel=0)
+        return self.bufs[i]
 
 
 class ShardedMAPs:
@@ -77,7 +143,13 @@ class ShardedMAPs:
     contiguous row blocks (rank order == global row order) and returns the global mAP on every rank."""
 
     def __init__(self, r: int, group=None, *, device=None, flags: int = 0,
-                 pack_rows: Optional[Callable] = None, rank_fn: Optional[Callable] = None):
+                 pack_rows: Optional[Callable] = None, rank_fn: Optional[Callable] = None,
+                 db_counts: Optional[Sequence[int]] = None, query_counts: Optional[Sequence[int]] = None, symmetric: bool = False):
+        # symmetric: fuse the exchange into the pack kernel (SymmetricRows; needs db_counts and the CUDA packers)
+        self.symmetric = bool(symmetric)
+        self._sym = None
+        # db_counts / query_counts: rows per rank when the caller knows them (shard_bounds): no count exchange, no host sync
+        self.db_counts, self.query_counts = db_counts, query_counts
         self.R = r
         self.group = group
         self.device = device
@@ -102,15 +174,23 @@ class ShardedMAPs:
         pack, rank = self._hooks()
         b = int(database.output.shape[1])
         L = int(database.label.shape[1])
-        db_rows_local = pack(database.output, database.label)
         q_rows = pack(query.output, query.label)
-        db_rows, counts = gather_rows(db_rows_local, self.group)   # the ONE exchange step: packed code + label words
+        if self.symmetric and self.db_counts is not None and self._pack_rows is None and b % 32 == 0:
+            dist = _dist()
+            counts = [int(c) for c in self.db_counts]
+            ndb_all, my_rank = sum(counts), dist.get_rank(self.group)
+            if self._sym is None or (self._sym.ndb, self._sym.b, self._sym.L) != (ndb_all, b, L):
+                self._sym = SymmetricRows(ndb_all, b, L, q_rows.device, self.group)
+            db_rows = self._sym.pack(database.output, database.label, sum(counts[:my_rank]))   # pack + exchange in one kernel
+        else:
+            db_rows_local = pack(database.output, database.label)
+            db_rows, counts = gather_rows(db_rows_local, self.group, self.db_counts)   # the ONE exchange step: packed code + label words
         self.last_counts = counts
         ndb = int(db_rows.shape[0])
         if self.R > ndb:
             raise ValueError(f"operands could not be broadcast together: R={self.R} exceeds the database size {ndb}")
         ap_local = rank(q_rows, db_rows, b, L, int(self.R))
-        return gather_vector(ap_local, self.group)
+        return gather_vector(ap_local, self.group, self.query_counts)
 
     def get_maps_by_feature(self, database, query):
         ap = self.per_query_ap_device(database, query).cpu().numpy()

@@ -65,6 +65,16 @@ int hg_row_words(int b, int L);
 int hg_pack_rows(const float* d_feat, int64_t ld, const void* d_lab, int lab_elem_bytes, int64_t n, int b, int L,
                  uint32_t* d_rows, int* d_bad, void* stream);
 
+/* hg_pack_rows fused with the exchange step of the multi-GPU path (one all-gather of packed rows): the rows
+ * are stored straight into n_dst destination buffers -- this rank's own database buffer and its peers', reached through
+ * NVLink / NVSwitch peer pointers of a symmetric allocation.  h_dst_rows is a HOST array of n_dst (<= 16) DEVICE pointers,
+ * each already offset to this rank's first row inside that destination, 16-byte aligned.  The caller publishes the rows
+ * with a cross-GPU barrier afterwards (hashgan_b200/sharding.py: SymmetricRows).  Needs b % 32 == 0 and contiguous
+ * feature rows; returns HG_ERANGE otherwise (use hg_pack_rows + an all-gather then).  The reference has no multi-GPU
+ * path (main.py:263). */
+int hg_pack_rows_push(const float* d_feat, int64_t ld, const void* d_lab, int lab_elem_bytes, int64_t n, int b, int L,
+                      uint32_t* const* h_dst_rows, int n_dst, int* d_bad, void* stream);
+
 /* Workspace (bytes) hg_hamming_map needs for these sizes; 0 on invalid arguments. */
 size_t hg_hamming_map_workspace_bytes(int64_t nq, int64_t ndb, int b, int L, int64_t R);
 
@@ -108,7 +118,7 @@ int hg_select_backend(int b, int L);
  * d_q_feat [nq, b] / d_db_feat [ndb, b] fp32 row-major; d_q_rows / d_db_rows packed rows of the same inputs (only their label
  * words are read).  d_ap [nq] (NaN where no relevant row is in the top-R); optional d_ids [nq, R] (database rows in rank
  * order), d_ips [nq, R] (their inner products), d_rel [nq].  The workspace holds the keys of one query chunk
- * (4 B per pair; hg_ip_map_workspace_bytes sizes it for chunks of up to 256 queries, any size from one query up works).
+ * (4 B per pair; hg_ip_map_workspace_bytes sizes it for chunks of up to 592 queries, any size from one query up works).
  * Exact by construction (radix select + stable radix sort): no sampling, no fallback.  Asynchronous on `stream`. */
 size_t hg_ip_map_workspace_bytes(int64_t nq, int64_t ndb, int b, int L, int64_t R);
 int hg_ip_map(const float* d_q_feat, const uint32_t* d_q_rows, int64_t nq, const float* d_db_feat, const uint32_t* d_db_rows,
