@@ -327,7 +327,15 @@ static int launch_conv(const float* in, const float* w, const float* bias, float
 static int conv_cgp(int Cg) { return (Cg + 3) & ~3; }  // channels per group as the tensor-core path lays them out
 static int conv_kpad(int KH, int KW, int Cg) { return (int)round_up((int64_t)KH * KW * conv_cgp(Cg), 32); }
 
-// convolution on the tensor cores: per group im2col -> gemm_tf32 (+bias, ReLU) straight into the NHWC output
+int conv_gemm_tf32(const float* in, const float* wt, const float* bias, float* out, int64_t M, int H, int W, int C, int c0, int Cg, int KH, int KW,
+                   int stride, int pad, int Ho, int Wo, int Kpad, int Cog, int ldc, cudaStream_t st);  // gemm_tf32.cu
+static bool env_flag_implicit()
+{
+    const char* v = getenv("HG_CONV_IM2COL");  // =1: the earlier explicit im2col + GEMM pair (kept for comparison)
+    return !(v && v[0] == '1');
+}
+
+// convolution on the tensor cores: implicit GEMM (default) or per group im2col -> gemm_tf32, (+bias, ReLU) straight into the NHWC output
 static int launch_conv_tf32(const float* in, const float* wt, const float* bias, float* out, float* col, int N, int H, int W, int C, int KH, int KW,
                             int stride, int pad, int Cout, int groups, cudaStream_t st)
 {
@@ -337,6 +345,14 @@ static int launch_conv_tf32(const float* in, const float* wt, const float* bias,
     const int64_t M = (int64_t)N * Ho * Wo;
     if (M >= (int64_t(1) << 31)) return fail(HG_EINVAL, "conv_tf32: batch too large");
     if ((Cg % 4) || (C % 4) || (reinterpret_cast<uintptr_t>(in) & 15)) return fail(HG_EINVAL, "conv_tf32: channels must be a multiple of 4");
+    if (env_flag_implicit()) {  // implicit GEMM: the A tiles are gathered inside the GEMM kernel, no im2col matrix
+        for (int g = 0; g < groups; ++g) {
+            int rc = conv_gemm_tf32(in, wt + (size_t)g * Cog * Kpad, bias + g * Cog, out + g * Cog, M, H, W, C, g * Cg, Cg, KH, KW, stride, pad, Ho, Wo,
+                                    Kpad, Cog, Cout, st);
+            if (rc != HG_OK) return rc;
+        }
+        return HG_OK;
+    }
     const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
     for (int g = 0; g < groups; ++g) {
         const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, 8), (int64_t)sms * 32);

@@ -12,6 +12,8 @@
 //   warps 2..5  : epilogue -- tcgen05.ld 32 lanes x 32 columns, + bias, ReLU, float4 stores
 #include "umma.cuh"
 
+#include <climits>
+
 namespace hg {
 
 constexpr int kGemmBM = 128;
@@ -147,6 +149,188 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
 }
 
+// ================================================================================================================
+// Convolution as an IMPLICIT GEMM on the tensor cores (lib/architecture.py:253-351):
+//   out[m, co] = relu(bias[co] + sum_k A[m, k] * Wt[co, k]),  m = (crop, oy, ox),  k = (ky, kx, ci) of one channel group
+// The im2col matrix A is never written: the four producer warps gather each 128 x 32 A tile straight from the NHWC
+// activations (16-byte loads, 8 lanes cover the 128 bytes of a row so a warp reads four whole rows) and store it into the
+// shared-memory stage in the SWIZZLE_128B K-major layout tcgen05.mma expects (chunk ^= row & 7), fence.proxy.async,
+// mbarrier arrive.  The weights (B operand, [Cout_g, Kpad] K-major) arrive by TMA as in gemm_tf32_kernel; the producer
+// warps then turn into the epilogue warps (bias + ReLU, NHWC stores).
+// ================================================================================================================
+struct ConvGemmArgs {
+    const float* in;    // [N, H, W, C] NHWC (C = stored channels, multiple of 4)
+    const float* bias;  // [Cog] of this group
+    float* out;         // [M, ldc], already offset to the group's first output channel
+    int64_t M;
+    int H, W, C, c0, Cg, KH, KW, stride, pad, Ho, Wo, Kpad, Cog, ldc;
+};
+
+constexpr int kConvStages = 3;
+__host__ __device__ constexpr int conv_tmem_cols(int BN) { return BN <= 64 ? 64 : (BN <= 128 ? 128 : 256); }
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, (BN <= 128 ? 2 : 1))
+conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, ConvGemmArgs a)
+{
+    extern __shared__ __align__(1024) uint8_t csm[];
+    constexpr uint32_t A_BYTES = kGemmBM * kGemmBK * 4;  // 16 KB
+    constexpr uint32_t B_BYTES = BN * kGemmBK * 4;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    const uint32_t base = (smem_u32(csm) + 1023u) & ~1023u;
+    uint8_t* const base_ptr = csm + (base - smem_u32(csm));
+    int2* const tab = reinterpret_cast<int2*>(base_ptr + kConvStages * STAGE_BYTES);  // per 16-byte K chunk: {input offset, ky | kx << 16}
+    __shared__ __align__(8) uint64_t full_bar[kConvStages], empty_bar[kConvStages], tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.y * kGemmBM;
+    const int n0 = blockIdx.x * BN;
+    const int nkb = a.Kpad / kGemmBK;
+    const int K = a.KH * a.KW * a.Cg;
+
+    for (int j = threadIdx.x; j < a.Kpad / 4; j += kGemmThreads) {
+        const int k = j * 4;
+        if (k < K) {
+            const int ci = k % a.Cg, kx = (k / a.Cg) % a.KW, ky = k / (a.Cg * a.KW);
+            tab[j] = make_int2((ky * a.W + kx) * a.C + ci, ky | (kx << 16));
+        } else {
+            tab[j] = make_int2(-1, 0);
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kConvStages; ++s) { mbar_init(&full_bar[s], 1 + 4); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)conv_tmem_cols(BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // weights by TMA
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kConvStages;
+                mbar_wait(&empty_bar[s], (uint32_t)(((kb / kConvStages) & 1) ^ 1));
+                mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
+                tma_load_2d(base + s * STAGE_BYTES + A_BYTES, &tmap_b, smem_u32(&full_bar[s]), kb * kGemmBK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(kGemmBM, BN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % kConvStages;
+                mbar_wait(&full_bar[s], (uint32_t)((kb / kConvStages) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+                const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sb);
+#pragma unroll
+                for (int k = 0; k < kGemmBK / 8; ++k)
+                    umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        // ---- producer: gather the A tiles (thread g: 16-byte chunk g & 7 of rows (g >> 3) + 16 i) ----
+        const int g = threadIdx.x - 64;
+        const int chunk = g & 7;
+        int rbase[8];      // input offset of the window origin of row i (floats), INT_MIN: row beyond M
+        int ryx[8];        // (iy0 + 1024) | (ix0 + 1024) << 16
+        uint32_t soff[8];  // byte offset of my chunk inside an A stage
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = (g >> 3) + 16 * i;
+            const int64_t m = m0 + r;
+            soff[i] = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
+            if (m < a.M) {
+                const int ox = (int)(m % a.Wo), oy = (int)((m / a.Wo) % a.Ho);
+                const int64_t n = m / ((int64_t)a.Wo * a.Ho);
+                const int iy0 = oy * a.stride - a.pad, ix0 = ox * a.stride - a.pad;
+                rbase[i] = (int)(((n * a.H + iy0) * a.W + ix0) * a.C + a.c0);
+                ryx[i] = (iy0 + 1024) | ((ix0 + 1024) << 16);
+            } else {
+                rbase[i] = INT_MIN;
+                ryx[i] = 0;
+            }
+        }
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % kConvStages;
+            const int2 t = tab[kb * 8 + chunk];
+            const int ky = t.y & 0xffff, kx = t.y >> 16;
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int iy = (ryx[i] & 0xffff) - 1024 + ky, ix = (ryx[i] >> 16) - 1024 + kx;
+                if (t.x >= 0 && rbase[i] != INT_MIN && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+                    v[i] = __ldg(reinterpret_cast<const float4*>(a.in + rbase[i] + t.x));
+            }
+            mbar_wait(&empty_bar[s], (uint32_t)(((kb / kConvStages) & 1) ^ 1));  // the loads above are already in flight
+            uint8_t* sa = base_ptr + s * STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(sa + soff[i]) = v[i];
+            fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+            }
+        }
+        // ---- epilogue: TMEM lane quarter = warp % 4 ----
+        const int quarter = warp & 3;
+        mbar_wait(&tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t row = m0 + quarter * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < a.M && n0 + c0 < a.Cog) {
+                float* crow = a.out + (size_t)row * a.ldc + n0 + c0;
+                const bool vec = ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) && (n0 + c0 + 32 <= a.Cog);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float o[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int n = n0 + c0 + j + t;
+                        o[t] = fmaxf(__uint_as_float(r[j + t]) + (n < a.Cog ? __ldg(a.bias + n) : 0.0f), 0.0f);
+                    }
+                    if (vec) {
+                        *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (n0 + c0 + j + t < a.Cog) crow[j + t] = o[t];
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)conv_tmem_cols(BN)) : "memory");
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------
 EncodeTiledFn encode_tiled_fn()
 {
@@ -174,6 +358,44 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t K,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HG_ECUDA, "gemm_tf32: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return HG_OK;
+}
+
+template <int BN>
+static int launch_conv_gemm(const CUtensorMap& tb, const ConvGemmArgs& a, cudaStream_t st)
+{
+    const size_t smem = (size_t)kConvStages * (kGemmBM + BN) * kGemmBK * 4 + (size_t)(a.Kpad / 4) * sizeof(int2) + 1024;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        HG_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((unsigned)ceil_div(a.Cog, BN), (unsigned)ceil_div(a.M, kGemmBM));
+    conv_gemm_tf32_kernel<BN><<<grid, kGemmThreads, smem, st>>>(tb, a);
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    return HG_OK;
+}
+
+// one channel group of a convolution layer; wt = this group's weights [Cog, Kpad] K-major (hg_conv_weight_pack)
+int conv_gemm_tf32(const float* in, const float* wt, const float* bias, float* out, int64_t M, int H, int W, int C, int c0, int Cg, int KH, int KW,
+                   int stride, int pad, int Ho, int Wo, int Kpad, int Cog, int ldc, cudaStream_t st)
+{
+    if ((Cg % 4) || (C % 4) || (c0 % 4) || (reinterpret_cast<uintptr_t>(in) & 15) || (Kpad % kGemmBK))
+        return fail(HG_EINVAL, "conv_gemm_tf32: channels must be multiples of 4, Kpad a multiple of %d", kGemmBK);
+    if ((int64_t)M / ((int64_t)Ho * Wo) * H * W * C >= (int64_t(1) << 31)) return fail(HG_EINVAL, "conv_gemm_tf32: input too large for 32-bit offsets");
+    ConvGemmArgs a{};
+    a.in = in; a.bias = bias; a.out = out; a.M = M; a.H = H; a.W = W; a.C = C; a.c0 = c0; a.Cg = Cg; a.KH = KH; a.KW = KW; a.stride = stride;
+    a.pad = pad; a.Ho = Ho; a.Wo = Wo; a.Kpad = Kpad; a.Cog = Cog; a.ldc = ldc;
+    const int BN = (Cog % 128 == 0) ? 128 : ((Cog % 192 == 0) ? 192 : ((Cog % 96 == 0) ? 96 : (Cog <= 64 ? 64 : 128)));
+    CUtensorMap tb;
+    int rc;
+    if ((rc = make_map(&tb, wt, Cog, Kpad, Kpad, BN)) != HG_OK) return rc;
+    switch (BN) {
+        case 64: return launch_conv_gemm<64>(tb, a, st);
+        case 96: return launch_conv_gemm<96>(tb, a, st);
+        case 192: return launch_conv_gemm<192>(tb, a, st);
+        default: return launch_conv_gemm<128>(tb, a, st);
+    }
 }
 
 template <int BN, bool RELU>
