@@ -83,6 +83,37 @@ def test_pack_rows_label_words_bit_exact(hb, L, dtype):
         assert np.array_equal(got[:, W:W + LW], maps_oracle.pack_label_bits(lab.astype(np.int64)))
 
 
+@pytest.mark.parametrize("b,L,dtype", [(64, 10, np.int64), (128, 81, np.int64), (32, 1, np.int32), (96, 33, np.int8), (256, 128, np.int64)])
+def test_pack_rows_push_matches_pack_rows(hb, b, L, dtype):
+    """hg_pack_rows_push (pack fused with the multi-GPU exchange) with several destination buffers on ONE GPU: every
+    destination must hold exactly the rows hg_pack_rows produces, at the pushed row offset, and nothing else."""
+    import ctypes as C
+    import torch
+    from hashgan_b200 import _native
+
+    lib = _native.lib()
+    rng = np.random.default_rng(b + L)
+    n, row_lo, total = 4099, 1200, 6000
+    feat = torch.from_numpy(rng.normal(size=(n, b)).astype(np.float32)).cuda()
+    lab = torch.from_numpy((rng.random((n, L)) < 0.2).astype(dtype)).cuda()
+    want = hb.pack_rows(feat, lab)
+    Wr = _native.row_words(b, L)
+    dsts = [torch.full((total, Wr), -1, dtype=torch.int32, device="cuda") for _ in range(3)]
+    ptrs = (C.c_void_p * 3)(*[d.data_ptr() + row_lo * Wr * 4 for d in dsts])
+    bad = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    _native.check(lib.hg_pack_rows_push(feat.data_ptr(), b, lab.data_ptr(), lab.element_size(), n, b, L, ptrs, 3, bad.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    for d in dsts:
+        assert torch.equal(d[row_lo:row_lo + n], want)
+        assert bool((d[:row_lo] == -1).all()) and bool((d[row_lo + n:] == -1).all())
+    assert int(bad.item()) == 0
+    # ragged hash length: the fused kernel declines, the caller falls back to hg_pack_rows + all-gather
+    f2 = torch.zeros((8, 48), dtype=torch.float32, device="cuda")
+    rc = lib.hg_pack_rows_push(f2.data_ptr(), 48, None, 8, 8, 48, 10, ptrs, 3, None, torch.cuda.current_stream().cuda_stream)
+    assert rc == _native.HG_ERANGE
+
+
 def test_bad_labels_are_rejected(hb):
     rng = np.random.default_rng(0)
     db = NS(output=(rng.integers(0, 2, (300, 32)) * 2 - 1).astype(np.float32), label=rng.integers(0, 3, (300, 4)))
