@@ -189,7 +189,9 @@ __device__ __forceinline__ uint32_t miss_mask32(uint32_t taddr, uint32_t sel)
 // (accumulator columns 0..63) and 64 rows of the second (columns 64..127); every epilogue warp owns 32 queries x one
 // split, so 16 epilogue warps per CTA (32 per SM) share the CUDA-core work and each bin still has a single writer
 // that sees its rows in ascending order.
-template <int KP>
+// MODE fixes the packed-row shape at compile time: 1 = two code words in 4-word rows (32 < b <= 64, L <= 64: C4),
+// 2 = four code words in 8-word rows (96 < b <= 128: C5), 0 = read it from the arguments.
+template <int KP, int MODE>
 __global__ void __launch_bounds__(kUmmaThreads, 2)
 select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_constant__ CUtensorMap tmap_db8,
                    const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_qx,
@@ -219,7 +221,8 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
     const int64_t rowa = (int64_t)split_a * a.SL;
     const int64_t rows_first = max((int64_t)0, min(a.SL, a.ndb - rowa));  // the first split is never shorter than the second
     const int ntiles = (int)((rows_first + kUmmaHalfRows - 1) / kUmmaHalfRows);
-    const uint32_t half_rows_bytes = (uint32_t)kUmmaHalfRows * a.Wr * 4;
+    const int WrK = MODE == 1 ? 4 : (MODE == 2 ? 8 : a.Wr);
+    const uint32_t half_rows_bytes = (uint32_t)kUmmaHalfRows * WrK * 4;
 
     if (threadIdx.x == 0) {
         mbar_init(&a_full, 1);
@@ -293,7 +296,7 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
         const int64_t row0 = (int64_t)split * a.SL;
         const int64_t nrows = max((int64_t)0, min(a.SL, a.ndb - row0));
         const bool valid = slot < a.nq && split < a.P;
-        const int W = a.W, LW = a.LW, Wr = a.Wr;
+        const int W = MODE == 1 ? 2 : (MODE == 2 ? 4 : a.W), LW = a.LW, Wr = WrK;
         const uint32_t sel = a.prmt_sel;
         uint32_t qw[4] = {0, 0, 0, 0}, ql[4] = {0, 0, 0, 0};
         uint32_t pos = 0, nback = 0, start = 0, end = 0;  // front stack (d < T) grows up from start, back stack (d == T) down from end
@@ -347,7 +350,15 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
                 const uint32_t* prow = srows + rl * Wr;
                 int d = 0;
                 uint32_t m = 0;
-                if (Wr == 4) {  // one 16-byte load brings the code words and the label word(s): W = 2 (+ <= 2 label words) or W = 3 (+ 1)
+                if (MODE == 1) {
+                    const uint4 pr = *reinterpret_cast<const uint4*>(prow);
+                    d = __popc(qw[0] ^ pr.x) + __popc(qw[1] ^ pr.y);
+                    m = (ql[0] & pr.z) | (ql[1] & pr.w);
+                } else if (MODE == 2) {
+                    const uint4 pc = *reinterpret_cast<const uint4*>(prow), pl = *reinterpret_cast<const uint4*>(prow + 4);
+                    d = __popc(qw[0] ^ pc.x) + __popc(qw[1] ^ pc.y) + __popc(qw[2] ^ pc.z) + __popc(qw[3] ^ pc.w);
+                    m = (ql[0] & pl.x) | (ql[1] & pl.y) | (ql[2] & pl.z) | (ql[3] & pl.w);
+                } else if (Wr == 4) {  // one 16-byte load brings the code words and the label word(s): W = 2 (+ <= 2 label words) or W = 3 (+ 1)
                     const uint4 pr = *reinterpret_cast<const uint4*>(prow);
                     d = __popc(qw[0] ^ pr.x) + __popc(qw[1] ^ pr.y);
                     if (W == 3) { d += __popc(qw[2] ^ pr.z); m = ql[0] & pr.w; }
@@ -453,18 +464,18 @@ int umma_thr_columns(const int* thr, int64_t nq, int b, uint8_t* qx, uint8_t* bx
     return HG_OK;
 }
 
-template <int KP>
+template <int KP, int MODE>
 static int launch_umma(const CUtensorMap& tq, const CUtensorMap& tdb, const CUtensorMap& trows, const CUtensorMap& tqx, const CUtensorMap& tbx,
                        const UmmaSelectArgs& a, cudaStream_t st)
 {
     const size_t smem = (size_t)2 * 128 * KP + (size_t)3 * 128 * kUmmaXBytes + (size_t)UmmaCfg<KP>::S * (128 * KP + kUmmaRowsMax) + 1024;
     static thread_local bool configured = false;
     if (!configured) {
-        HG_CUDA_TRY(cudaFuncSetAttribute(select_umma_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HG_CUDA_TRY(cudaFuncSetAttribute(select_umma_kernel<KP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid((unsigned)ceil_div(a.nq, 256), (unsigned)ceil_div(a.n_splits, 2));
-    select_umma_kernel<KP><<<grid, kUmmaThreads, smem, st>>>(tq, tdb, trows, tqx, tbx, a);
+    select_umma_kernel<KP, MODE><<<grid, kUmmaThreads, smem, st>>>(tq, tdb, trows, tqx, tbx, a);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     return HG_OK;
@@ -486,7 +497,8 @@ int umma_select_launch(const UmmaSelectArgs& a_in, cudaStream_t st)
     if ((rc = make_map_rows(&trows, a.db_rows, a.ndb, a.Wr)) != HG_OK) return rc;
     if ((rc = make_map_u8(&tqx, a.qx, std::max<int64_t>(round_up(a.nq, 256), 128), kUmmaXBytes, 128)) != HG_OK) return rc;
     if ((rc = make_map_u8(&tbx, a.bx, 128, kUmmaXBytes, kUmmaHalfRows)) != HG_OK) return rc;
-    return a.KP == 128 ? launch_umma<128>(tq, tdb, trows, tqx, tbx, a, st) : launch_umma<64>(tq, tdb, trows, tqx, tbx, a, st);
+    if (a.KP == 64) return (a.W == 2 && a.Wr == 4) ? launch_umma<64, 1>(tq, tdb, trows, tqx, tbx, a, st) : launch_umma<64, 0>(tq, tdb, trows, tqx, tbx, a, st);
+    return (a.W == 4 && a.Wr == 8) ? launch_umma<128, 2>(tq, tdb, trows, tqx, tbx, a, st) : launch_umma<128, 0>(tq, tdb, trows, tqx, tbx, a, st);
 }
 
 }  // namespace hg
