@@ -308,7 +308,7 @@ extern "C" int hg_maps_by_feature_host(const float* h_db_feat, const void* h_db_
     hg::MapChunks chunks;
     size_t ws_bytes = 0;
     const char* kenv = getenv("HG_HOST_CHUNKS");
-    if (hg::plan_chunks(nq, ndb, b, L, R, (kenv && *kenv) ? atoi(kenv) : 6, &chunks, &ws_bytes) != HG_OK || ws_bytes == 0)
+    if (hg::plan_chunks(nq, ndb, b, L, R, (kenv && *kenv) ? atoi(kenv) : 8, &chunks, &ws_bytes) != HG_OK || ws_bytes == 0)
         return hg::fail(HG_EINVAL, "hg_maps_by_feature_host: sizes out of range (split the query batch)");
 
     std::lock_guard<std::mutex> lock(hg::g_arena_mu);

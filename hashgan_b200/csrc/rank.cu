@@ -1121,13 +1121,25 @@ int plan_chunks(int64_t nq, int64_t ndb, int b, int L, int64_t R, int k_req, Map
     if (!pl.ok || !out) return fail(HG_EINVAL, "plan_chunks: sizes out of range");
     if (ws_bytes) *ws_bytes = pl.total;
     int K = std::max(1, std::min(std::min(k_req, pl.P / 2), MapChunks::kMax));
-    out->K = K;
+    // Chunk k is ranked while chunk k + 1 is still on the PCIe bus, so what is exposed at the end is the work on the LAST
+    // chunk: the last two chunks are short (0.6 and 0.25 of a regular one).  Whole splits per chunk, even boundaries
+    // because the tensor-core select ranks splits in pairs.
+    double wsum = 0.0, w[MapChunks::kMax];
+    for (int k = 0; k < K; ++k) { w[k] = (K >= 4 && k == K - 1) ? 0.25 : ((K >= 4 && k == K - 2) ? 0.6 : 1.0); wsum += w[k]; }
+    int64_t s_prev = 0;
+    double acc = 0.0;
+    int kk = 0;
     for (int k = 0; k < K; ++k) {
-        // whole splits per chunk; even boundaries because the tensor-core select ranks splits in pairs
-        const int64_t s_lo = ((int64_t)k * pl.P / K) & ~int64_t(1), s_hi = k + 1 == K ? (int64_t)pl.P : (((int64_t)(k + 1) * pl.P / K) & ~int64_t(1));
-        out->row_lo[k] = s_lo * pl.SL;
-        out->row_hi[k] = std::min<int64_t>(s_hi * pl.SL, ndb);
+        acc += w[k];
+        int64_t s_hi = k + 1 == K ? (int64_t)pl.P : ((int64_t)llround(acc / wsum * (double)pl.P) & ~int64_t(1));
+        s_hi = std::min<int64_t>(std::max<int64_t>(s_hi, s_prev), pl.P);
+        if (s_hi == s_prev) continue;  // rounding left nothing for this chunk
+        out->row_lo[kk] = s_prev * pl.SL;
+        out->row_hi[kk] = std::min<int64_t>(s_hi * pl.SL, ndb);
+        s_prev = s_hi;
+        ++kk;
     }
+    out->K = std::max(1, kk);
     return HG_OK;
 }
 
