@@ -289,7 +289,11 @@ extern "C" int hg_row_words(int b, int L)
     const int W = hg_code_words(b), LW = hg_label_words(L);
     if (W == 0 || LW == 0) return 0;
     const int align = (W == 2) ? 2 : ((W == 4 || W == 8) ? 4 : 1);  // vector loads of the code words
-    return ((W + LW + align - 1) / align) * align;
+    int Wr = ((W + LW + align - 1) / align) * align;
+    // the tensor-core select stages packed rows by TMA: 16- or 32-byte rows.  Hash lengths of 33..128 bits with more than
+    // 32 labels (e.g. 64-bit codes on NUS-WIDE's 81 labels) get 8-word rows instead of 5..7.
+    if (W >= 2 && W <= 4 && LW <= 4 && W + LW > 4) Wr = 8;
+    return Wr;
 }
 
 extern "C" int hg_pack_rows(const float* d_feat, int64_t ld, const void* d_lab, int lab_elem_bytes, int64_t n, int b, int L,

@@ -48,7 +48,8 @@ int hg_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes
  *     row = [ W code words | LW label words | zero pad ]   (uint32, row stride hg_row_words(b, L))
  * W  = hg_code_words(b)  = ceil(b/32) for b <= 128, 8 for 128 < b <= 256 (zero pad words); 0 if unsupported.
  * LW = hg_label_words(L) = ceil(L/32), L <= HG_MAX_LABELS; 0 if unsupported.
- * The stride rounds W+LW up so that the code words can be fetched with one 64/128-bit load. */
+ * The stride rounds W+LW up so that the code words can be fetched with one 64/128-bit load; 33..128-bit codes get
+ * 4- or 8-word rows (16 / 32 bytes) so that the tensor-core select can stage them by TMA. */
 int hg_code_words(int b);
 int hg_label_words(int L);
 int hg_row_words(int b, int L);

@@ -208,6 +208,22 @@ def test_hash_lengths(hb, c_oracle, b):
         _check_against_c_oracle(hb, c_oracle, db, q, R)
 
 
+@pytest.mark.parametrize("b,L", [(64, 81), (48, 40), (96, 81), (96, 33), (128, 128), (64, 64)])
+def test_multilabel_widths_on_the_tensor_core_path(hb, c_oracle, b, L):
+    """Every 33..128-bit hash length runs on the tensor-core select whatever the label width (64-bit codes with the 81
+    labels of NUS-WIDE are the reference's own nuswide configuration): rows are padded to 4 or 8 words."""
+    from hashgan_b200 import _native
+
+    assert _native.lib().hg_select_backend(b, L) in (64, 128)
+    assert _native.row_words(b, L) in (4, 8)
+    rng = np.random.default_rng(b * 1000 + L)
+    ndb, nq = 60000, 150
+    db = NS(output=(rng.integers(0, 2, (ndb, b)) * 2 - 1).astype(np.float32), label=(rng.random((ndb, L)) < 0.03).astype(np.int64))
+    q = NS(output=(rng.integers(0, 2, (nq, b)) * 2 - 1).astype(np.float32), label=(rng.random((nq, L)) < 0.03).astype(np.int64))
+    for R in (50, 3000):
+        _check_against_c_oracle(hb, c_oracle, db, q, R)
+
+
 def test_all_codes_equal_forces_exact_path(hb, c_oracle):
     """Adversarial: one distance bucket holds the whole database -> candidate bins overflow -> exact two-pass path."""
     rng = np.random.default_rng(1)
