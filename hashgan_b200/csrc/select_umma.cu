@@ -61,6 +61,21 @@ __device__ __forceinline__ void mbar_arrive_a(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// one non-blocking probe
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity)
 {
     asm volatile(
@@ -207,13 +222,13 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
     extern __shared__ __align__(1024) uint8_t usm[];
     const uint32_t base = (smem_u32(usm) + 1023u) & ~1023u;
     uint8_t* const base_ptr = usm + (base - smem_u32(usm));
-    __shared__ __align__(8) uint64_t bars[2 * S + 3];  // one array: every barrier is (one opaque base register) + constant
+    __shared__ __align__(8) uint64_t bars[2 * S + 5];  // one array: every barrier is (one opaque base register) + constant
     __shared__ uint32_t tmem_base_slot;
     uint64_t& a_full = bars[0];
     uint64_t* const full_bar = bars + 1;
     uint64_t* const empty_bar = bars + 1 + S;
-    uint64_t& tmem_full = bars[2 * S + 1];
-    uint64_t& tmem_empty = bars[2 * S + 2];
+    uint64_t* const tmem_full = bars + 2 * S + 1;   // [2]: one accumulator (128 queries x 128 rows) per query half,
+    uint64_t* const tmem_empty = bars + 2 * S + 3;  // [2]  handed back and forth independently
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t q0 = (int64_t)blockIdx.x * 256;
@@ -227,8 +242,7 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
     if (threadIdx.x == 0) {
         mbar_init(&a_full, 1);
         for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kUmmaEpiWarps); }
-        mbar_init(&tmem_full, 1);
-        mbar_init(&tmem_empty, kUmmaEpiWarps);
+        for (int h = 0; h < 2; ++h) { mbar_init(&tmem_full[h], 1); mbar_init(&tmem_empty[h], kUmmaEpiWarps / 2); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -270,19 +284,27 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % S;
                 mbar_wait(&full_bar[s], (uint32_t)((t / S) & 1));
-                mbar_wait(&tmem_empty, (uint32_t)((t & 1) ^ 1));  // the epilogue has read the previous tile's accumulators
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t bdesc = umma_desc_kmajor(base + FIXED_BYTES + s * STAGE_BYTES, KP);
+                // each query half as soon as ITS eight epilogue warps have read the previous tile's accumulator
+                uint32_t todo = 3u;
+                while (todo) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint64_t adesc = umma_desc_kmajor(base + h * 128 * KP, KP);
+                    for (int h = 0; h < 2; ++h) {
+                        if (!(todo & (1u << h))) continue;
+                        if (todo == (1u << h)) mbar_wait(&tmem_empty[h], (uint32_t)((t & 1) ^ 1));
+                        else if (!mbar_try(&tmem_empty[h], (uint32_t)((t & 1) ^ 1))) continue;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t adesc = umma_desc_kmajor(base + h * 128 * KP, KP);
 #pragma unroll
-                    for (int k = 0; k < KP / 32; ++k)  // UMMA_K = 32 int8 = 32 bytes: start address advances by 2 (x16 B)
-                        umma_i8(tmem_base + (uint32_t)(h * 128), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)(k != 0));
-                    // threshold K step: ip' = ip + (2 T_q - b)
-                    umma_i8(tmem_base + (uint32_t)(h * 128), umma_desc_kmajor(base + A_BYTES + h * 128 * kUmmaXBytes, kUmmaXBytes), bxdesc, idesc, 1u);
+                        for (int k = 0; k < KP / 32; ++k)  // UMMA_K = 32 int8 = 32 bytes: start address advances by 2 (x16 B)
+                            umma_i8(tmem_base + (uint32_t)(h * 128), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)(k != 0));
+                        // threshold K step: ip' = ip + (2 T_q - b)
+                        umma_i8(tmem_base + (uint32_t)(h * 128), umma_desc_kmajor(base + A_BYTES + h * 128 * kUmmaXBytes, kUmmaXBytes), bxdesc, idesc, 1u);
+                        umma_commit(&tmem_full[h]);
+                        todo &= ~(1u << h);
+                    }
                 }
-                umma_commit(&tmem_full);
             }
         }
     } else {
@@ -317,7 +339,7 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
         uint32_t bar0 = smem_u32(&bars[0]);
         asm volatile("" : "+r"(bar0));  // keep the shared-window address in a register instead of re-deriving it per tile
         const uint32_t full_a = bar0 + 8u, empty_a = bar0 + 8u * (1 + S);
-        const uint32_t tfull_a = bar0 + 8u * (2 * S + 1), tempty_a = bar0 + 8u * (2 * S + 2);
+        const uint32_t tfull_a = bar0 + 8u * (2 * S + 1 + h), tempty_a = bar0 + 8u * (2 * S + 3 + h);
         const int nrows32 = (int)nrows;                 // <= 2^21
         const int nfull = nrows32 / kUmmaHalfRows;      // tiles in which all 64 rows of my split exist
         int s = 0;
