@@ -280,12 +280,32 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(HistParams p)
 // ================================================================================================
 // 2. Threshold from the sampled histogram.
 // ================================================================================================
-__global__ void thr_kernel(const uint32_t* __restrict__ hist_s, int64_t nq, int b, int64_t sample_rows, int64_t ndb, int64_t R,
-                           float z, int force_exact, int* __restrict__ thr)
+// smallest distance whose cumulative count reaches `need` (b when it never does); one warp per query, coalesced bins
+__device__ __forceinline__ int first_reaching(const uint32_t* __restrict__ h, int b, double need)
 {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    double carry = 0.0;
+    for (int d0 = 0; d0 <= b; d0 += 32) {
+        const int d = d0 + lane;
+        double v = d <= b ? (double)h[d] : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, d <= b && carry + v >= need);
+        if (hit) return d0 + __ffs(hit) - 1;
+        carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+    return b;
+}
+
+__global__ void __launch_bounds__(256) thr_kernel(const uint32_t* __restrict__ hist_s, int64_t nq, int b, int64_t sample_rows, int64_t ndb, int64_t R,
+                                                  float z, int force_exact, int* __restrict__ thr)
+{
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= nq) return;
-    if (force_exact) { thr[q] = -1; return; }
+    if (force_exact) { if ((threadIdx.x & 31) == 0) thr[q] = -1; return; }
     double need;
     if (sample_rows >= ndb) {
         need = (double)R;  // the "sample" is the whole database: exact
@@ -294,14 +314,8 @@ __global__ void thr_kernel(const uint32_t* __restrict__ hist_s, int64_t nq, int 
         const double mu = p0 * (double)sample_rows;
         need = ceil(mu + (double)z * sqrt(mu * (1.0 - p0)) + 2.0);
     }
-    int T = b;
-    double cum = 0.0;
-    const uint32_t* h = hist_s + q * (b + 1);
-    for (int d = 0; d <= b; ++d) {
-        cum += (double)h[d];
-        if (cum >= need) { T = d; break; }
-    }
-    thr[q] = T;
+    const int T = first_reaching(hist_s + q * (b + 1), b, need);
+    if ((threadIdx.x & 31) == 0) thr[q] = T;
 }
 
 // ================================================================================================
@@ -1007,8 +1021,8 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
     }
     // 2. thresholds
     timer.mark(kPhaseThreshold, st);
-    thr_kernel<<<(unsigned)ceil_div(pl.nq, 256), 256, 0, st>>>(hist_s, pl.nq, pl.b, sample_rows, pl.ndb, pl.R, kSampleZ,
-                                                               force_exact ? 1 : 0, thr);
+    thr_kernel<<<(unsigned)ceil_div(pl.nq * 32, 256), 256, 0, st>>>(hist_s, pl.nq, pl.b, sample_rows, pl.ndb, pl.R, kSampleZ,
+                                                                    force_exact ? 1 : 0, thr);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     timer.mark(kPhaseExpand, st);
