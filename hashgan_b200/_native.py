@@ -49,6 +49,7 @@ SIGNATURES = {
     "hg_alexnet_workspace_bytes": (_sz, [_int, _u32]),
     "hg_conv_weight_pack": (_int, [_vp, _int, _int, _int, _int, _int, _vp, _vp]),
     "hg_alexnet_encode": (_int, [_vp, _int, _int, _vp, _int, _u32, _vp, _vp, _sz, _vp]),
+    "hg_alexnet_encode_stochastic": (_int, [_vp, _int, _int, _vp, _int, _u32, _vp, _vp, _sz, C.c_uint64, _vp]),
     "hg_transpose_f32": (_int, [_vp, _int, _int, _vp, _vp]),
     "hg_popc_peak": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), _int, _vp]),
 }

@@ -170,7 +170,8 @@ _DEFAULTS = {
                                  # fp32 CUDA-core convolutions, outputs within 3e-2 of the fp32 graph (code bits equal where |h| > 0.1)
         "TIE_BREAK": "index",    # (distance asc, database row asc) == np.argsort(kind='stable')
         "NUM_GPUS": 1,           # row-shard database and queries over this many GPUs (torchrun)
-        "DETERMINISTIC": True,   # no de-quantisation noise (main.py:147), no eval-time dropout (architecture.py:369,377)
+        "DETERMINISTIC": True,   # no de-quantisation noise (main.py:147), no eval-time dropout (architecture.py:369,377);
+                                 # False = the reference's stochastic eval graph, draws seeded by EVAL.SEED
         "SYNTHETIC": False,      # seeded synthetic images / weights when the data and checkpoints are absent
         "SEED": 0,
     },

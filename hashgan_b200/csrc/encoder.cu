@@ -23,13 +23,38 @@ int gemm_tf32(const float* A, int64_t lda, const float* Bt, int64_t ldb, const f
 // in : uint8 [n, 3, wh, wh] (RGB planes, the loader's flattened layout, lib/dataloader.py:110-113)
 // out: float [10n, 227, 227, 3]; crop block k holds rows k*n .. (k+1)*n (lib/architecture.py:242-244)
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float scaled_pixel(unsigned char v)
+// counter-based generator of the stochastic mode (splitmix64 finaliser of seed + index): the same function in
+// hashgan_b200/encoder.py reproduces every draw on the host, so the stochastic path is testable against the oracle
+__host__ __device__ __forceinline__ uint64_t hg_mix(uint64_t seed, uint64_t idx)
 {
-    const float x = 2.0f * (float)v / 256.0f - 1.0f;  // main.py:146
-    return (x + 1.0f) * 255.99f / 2.0f;               // lib/util.py:13
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+constexpr uint64_t kStreamNoise = 0xD1B54A32D192ED03ull, kStreamDrop6 = 0xA24BAED4963EE407ull, kStreamDrop7 = 0x9FB21C651E98DF25ull;
+
+__device__ __forceinline__ float scaled_pixel(unsigned char v, float noise)
+{
+    const float x = 2.0f * (float)v / 256.0f - 1.0f + noise;  // main.py:146-147
+    return (x + 1.0f) * 255.99f / 2.0f;                       // lib/util.py:13
+}
+// de-quantisation noise of main.py:147, tf.random_uniform([B, 3*wh*wh], 0, 1/128): one draw per source pixel (shared by the 10 crops)
+__device__ __forceinline__ float pixel_noise(uint64_t seed, int64_t flat)
+{
+    if (seed == 0) return 0.0f;
+    return (float)(hg_mix(seed ^ kStreamNoise, (uint64_t)flat) >> 40) * (1.0f / 16777216.0f) * (1.0f / 128.0f);
 }
 
-__global__ void __launch_bounds__(256) prep_crops_kernel(const unsigned char* __restrict__ img, int n, int wh, int cs, float* __restrict__ out)
+// tf.nn.dropout(x, 0.5) of lib/architecture.py:369,377 (active at eval in the reference: no stage guard): keep with p = 0.5, scale by 2
+__global__ void __launch_bounds__(256) dropout_half_kernel(float* __restrict__ x, int64_t n, uint64_t seed)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        x[i] = (hg_mix(seed, (uint64_t)i) >> 63) ? 2.0f * x[i] : 0.0f;
+}
+
+__global__ void __launch_bounds__(256) prep_crops_kernel(const unsigned char* __restrict__ img, int n, int wh, int cs, float* __restrict__ out,
+                                                         uint64_t seed)
 {
     const int64_t total = (int64_t)10 * n * 227 * 227;
     const float scale = (float)wh / 256.0f;  // tf.image.resize_bilinear, align_corners=False, no half-pixel centres
@@ -52,9 +77,12 @@ __global__ void __launch_bounds__(256) prep_crops_kernel(const unsigned char* __
         if (cs == 4) o[3] = 0.0f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const unsigned char* p = img + ((int64_t)b * 3 + c) * wh * wh;
-            const float tl = scaled_pixel(p[y0 * wh + x0]), tr = scaled_pixel(p[y0 * wh + x1]);
-            const float bl = scaled_pixel(p[y1 * wh + x0]), br = scaled_pixel(p[y1 * wh + x1]);
+            const int64_t plane = ((int64_t)b * 3 + c) * wh * wh;
+            const unsigned char* p = img + plane;
+            const float tl = scaled_pixel(p[y0 * wh + x0], pixel_noise(seed, plane + y0 * wh + x0));
+            const float tr = scaled_pixel(p[y0 * wh + x1], pixel_noise(seed, plane + y0 * wh + x1));
+            const float bl = scaled_pixel(p[y1 * wh + x0], pixel_noise(seed, plane + y1 * wh + x0));
+            const float br = scaled_pixel(p[y1 * wh + x1], pixel_noise(seed, plane + y1 * wh + x1));
             const float top = tl + (tr - tl) * lx;
             const float bot = bl + (br - bl) * lx;
             o[c] = (top + (bot - top) * ly) - mean[c];
@@ -400,8 +428,8 @@ extern "C" int hg_transpose_f32(const float* d_in, int rows, int cols, float* d_
     return HG_OK;
 }
 
-extern "C" int hg_alexnet_encode(const uint8_t* d_images, int n, int wh, const HgAlexNetWeights* w, int hash_dim, unsigned flags, float* d_out,
-                                 void* d_workspace, size_t workspace_bytes, void* stream)
+static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgAlexNetWeights* w, int hash_dim, unsigned flags, float* d_out,
+                               void* d_workspace, size_t workspace_bytes, void* stream, uint64_t seed)
 {
     using namespace hg;
     if (n == 0) return HG_OK;
@@ -430,7 +458,7 @@ extern "C" int hg_alexnet_encode(const uint8_t* d_images, int n, int wh, const H
                   : launch_conv(src, w->conv_w[i], w->conv_b[i], dst, N, H, H, C, KH, KH, stride, pad, Cout, groups, st);
     };
     // crops -> A
-    prep_crops_kernel<<<grid_1d((int64_t)N * 227 * 227, 256), 256, 0, st>>>(d_images, n, wh, tc ? 4 : 3, A);
+    prep_crops_kernel<<<grid_1d((int64_t)N * 227 * 227, 256), 256, 0, st>>>(d_images, n, wh, tc ? 4 : 3, A, seed);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     // conv1 11x11/4 VALID 3->96 : A -> B [N,55,55,96]
@@ -473,12 +501,33 @@ extern "C" int hg_alexnet_encode(const uint8_t* d_images, int n, int wh, const H
     // fc6, fc7 (+ReLU), fc8 on the tensor cores
     if ((rc = gemm_tf32(cur, 9216, w->fc6_wt, 9216, w->fc6_b, other, 4096, N, 4096, 9216, 1, st)) != HG_OK) return rc;
     std::swap(cur, other);
+    if (seed) {
+        dropout_half_kernel<<<grid_1d((int64_t)N * 4096, 256), 256, 0, st>>>(cur, (int64_t)N * 4096, seed ^ kStreamDrop6);
+        count_launch();
+    }
     if ((rc = gemm_tf32(cur, 4096, w->fc7_wt, 4096, w->fc7_b, other, 4096, N, 4096, 4096, 1, st)) != HG_OK) return rc;
     std::swap(cur, other);
+    if (seed) {
+        dropout_half_kernel<<<grid_1d((int64_t)N * 4096, 256), 256, 0, st>>>(cur, (int64_t)N * 4096, seed ^ kStreamDrop7);
+        count_launch();
+    }
     if ((rc = gemm_tf32(cur, 4096, w->fc8_wt, 4096, w->fc8_b, other, hash_dim, N, hash_dim, 4096, 0, st)) != HG_OK) return rc;
     std::swap(cur, other);
     tanh_crop_mean_kernel<<<grid_1d((int64_t)n * hash_dim, 256), 256, 0, st>>>(cur, n, hash_dim, d_out);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     return HG_OK;
+}
+
+extern "C" int hg_alexnet_encode(const uint8_t* d_images, int n, int wh, const HgAlexNetWeights* w, int hash_dim, unsigned flags, float* d_out,
+                                 void* d_workspace, size_t workspace_bytes, void* stream)
+{
+    return alexnet_encode_impl(d_images, n, wh, w, hash_dim, flags, d_out, d_workspace, workspace_bytes, stream, 0);
+}
+
+extern "C" int hg_alexnet_encode_stochastic(const uint8_t* d_images, int n, int wh, const HgAlexNetWeights* w, int hash_dim, unsigned flags,
+                                            float* d_out, void* d_workspace, size_t workspace_bytes, uint64_t seed, void* stream)
+{
+    if (seed == 0) return hg::fail(HG_EINVAL, "hg_alexnet_encode_stochastic: seed must be non-zero (0 is the deterministic mode)");
+    return alexnet_encode_impl(d_images, n, wh, w, hash_dim, flags, d_out, d_workspace, workspace_bytes, stream, seed);
 }

@@ -18,7 +18,29 @@ import numpy as np
 
 from . import _native
 
-__all__ = ["AlexNetWeights", "AlexNetHashEncoder", "CONV_SHAPES", "WEIGHT_NAMES"]
+__all__ = ["AlexNetWeights", "AlexNetHashEncoder", "CONV_SHAPES", "WEIGHT_NAMES", "stochastic_draws"]
+
+_M64 = (1 << 64) - 1
+_STREAM_NOISE, _STREAM_DROP6, _STREAM_DROP7 = 0xD1B54A32D192ED03, 0xA24BAED4963EE407, 0x9FB21C651E98DF25
+
+
+def _mix(seed: int, idx: np.ndarray) -> np.ndarray:
+    """hg_mix of csrc/encoder.cu (splitmix64 finaliser of seed + golden * (idx + 1)) on uint64 arrays."""
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed & _M64) + np.uint64(0x9E3779B97F4A7C15) * (idx.astype(np.uint64) + np.uint64(1))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def stochastic_draws(seed: int, n: int, wh: int):
+    """The random draws hg_alexnet_encode_stochastic makes for a batch of n images with `seed`:
+    (noise [n, 3*wh*wh] float32 = main.py:147, keep6 [10n, 4096] bool, keep7 [10n, 4096] bool = architecture.py:369,377)."""
+    noise = (_mix(seed ^ _STREAM_NOISE, np.arange(n * 3 * wh * wh)) >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -24) * np.float32(1 / 128)
+    idx = np.arange(10 * n * 4096)
+    keep6 = (_mix(seed ^ _STREAM_DROP6, idx) >> np.uint64(63)).astype(bool).reshape(10 * n, 4096)
+    keep7 = (_mix(seed ^ _STREAM_DROP7, idx) >> np.uint64(63)).astype(bool).reshape(10 * n, 4096)
+    return noise.reshape(n, -1), keep6, keep7
 
 CONV_SHAPES = {"conv1": (11, 11, 3, 96), "conv2": (5, 5, 48, 256), "conv3": (3, 3, 256, 384), "conv4": (3, 3, 192, 384),
                "conv5": (3, 3, 192, 256)}
@@ -104,7 +126,8 @@ class AlexNetWeights:
 class AlexNetHashEncoder:
     """images (uint8, [B, 3*wh*wh] as the loader yields them, lib/dataloader.py:110-113) -> CUDA float32 [B, HASH_DIM]."""
 
-    def __init__(self, weights: AlexNetWeights, *, lrn: bool = True, device=None, conv_tf32: bool = False):
+    def __init__(self, weights: AlexNetWeights, *, lrn: bool = True, device=None, conv_tf32: bool = False, deterministic: bool = True,
+                 seed: int = 0):
         import torch
 
         if not torch.cuda.is_available():
@@ -114,6 +137,12 @@ class AlexNetHashEncoder:
         self.hash_dim = weights.hash_dim
         self.lrn = lrn
         self.conv_tf32 = conv_tf32  # opt-in: conv1-5 on tcgen05 (TF32) instead of fp32 CUDA cores
+        # deterministic=False: the reference's stochastic eval graph (de-quantisation noise main.py:147, dropout at eval
+        # architecture.py:369,377); every encode() call draws with a fresh seed derived from `seed` and the call count
+        self.deterministic = deterministic
+        self.seed = int(seed)
+        self.calls = 0
+        self.last_seed = 0
         self.lib = _native.lib()
         dev = self.device
         t = {k: torch.from_numpy(v).to(dev) for k, v in weights.tensors.items()}
@@ -175,8 +204,15 @@ class AlexNetHashEncoder:
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty((need,), dtype=torch.uint8, device=dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _native.check(self.lib.hg_alexnet_encode(x.data_ptr(), n, wh, C.byref(self._struct), self.hash_dim, flags, out.data_ptr(),
-                                                     self._ws.data_ptr(), self._ws.numel(), stream))
+            if self.deterministic:
+                _native.check(self.lib.hg_alexnet_encode(x.data_ptr(), n, wh, C.byref(self._struct), self.hash_dim, flags, out.data_ptr(),
+                                                         self._ws.data_ptr(), self._ws.numel(), stream))
+            else:
+                self.last_seed = int(_mix(self.seed ^ 0x5851F42D4C957F2D, np.asarray([self.calls]))[0]) or 1
+                self.calls += 1
+                _native.check(self.lib.hg_alexnet_encode_stochastic(x.data_ptr(), n, wh, C.byref(self._struct), self.hash_dim, flags,
+                                                                    out.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
+                                                                    C.c_uint64(self.last_seed), stream))
             x.record_stream(torch.cuda.current_stream(dev))
         return out
 

@@ -187,6 +187,17 @@ int hg_conv_weight_pack(const float* d_w_hwio, int KH, int KW, int Cg, int Cout,
 int hg_alexnet_encode(const uint8_t* d_images, int n, int wh, const HgAlexNetWeights* w, int hash_dim, unsigned flags,
                       float* d_out, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* The reference's STOCHASTIC evaluation graph: Model.normalize adds U(0, 1/128) de-quantisation noise to every pixel also at
+ * eval (main.py:147) and tf.nn.dropout(x, 0.5) after fc6 / fc7 has no stage guard (lib/architecture.py:369,377), so the
+ * reference's eval outputs are random.  hg_alexnet_encode is the expectation-free deterministic graph (no noise, no dropout);
+ * this entry point reproduces the stochastic one with a counter-based generator: draw(seed, stream, index) =
+ * splitmix64-finaliser(seed ^ stream + 0x9E3779B97F4A7C15 * (index + 1)), noise = top 24 bits * 2^-24 / 128 per source pixel
+ * (index = flat position in d_images), dropout keeps an activation iff the top bit is set (index = crop_row * 4096 + unit;
+ * crop rows in the crop-major order of lib/architecture.py:242-244).  hashgan_b200/encoder.py holds the same generator in
+ * NumPy, so tests feed identical draws to the fp32 oracle.  seed != 0. */
+int hg_alexnet_encode_stochastic(const uint8_t* d_images, int n, int wh, const HgAlexNetWeights* w, int hash_dim, unsigned flags,
+                                 float* d_out, void* d_workspace, size_t workspace_bytes, uint64_t seed, void* stream);
+
 /* out[c][r] = in[r][c] (fp32, [rows, cols] -> [cols, rows]); used once per model to transpose the fc weights. */
 int hg_transpose_f32(const float* d_in, int rows, int cols, float* d_out, void* stream);
 

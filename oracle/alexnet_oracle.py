@@ -9,7 +9,7 @@ on the CPU, one function per reference step:
     lib/util.py:12-21             preprocess_resize()    (x+1)*255.99/2, NCHW->NHWC, TF1 legacy bilinear to 256x256
     lib/architecture.py:215-249   ten_crop()             5 crops of the flipped image + 5 plain, minus the channel mean
     lib/architecture.py:253-359   conv/pool/LRN          HWIO weights, VALID/SAME, 2-group convs, LRN iff WGAN_SCALE == 0
-    lib/architecture.py:363-389   fc6-8, tanh, crop mean (dropout off = deterministic mode; fc rows in (h,w,c) order)
+    lib/architecture.py:363-389   fc6-8, tanh, crop mean (dropout masks injected explicitly or off; fc rows in (h,w,c) order)
 """
 from __future__ import annotations
 
@@ -81,14 +81,19 @@ def _lrn(x_nhwc):
     return F.local_response_norm(x_nhwc.permute(0, 3, 1, 2), size=5, alpha=1e-4, beta=0.75, k=1.0).permute(0, 2, 3, 1).contiguous()
 
 
-def encode(images_uint8, weights: dict, wh: int, lrn: bool = True, noise=None, return_pre_tanh: bool = False):
+def _dropout(x, keep):
+    # tf.nn.dropout(x, 0.5), lib/architecture.py:369,377: kept activations are scaled by 1 / keep_prob = 2; keep=None: off
+    return x if keep is None else x * torch.as_tensor(np.asarray(keep), dtype=torch.float32) * 2.0
+
+
+def encode(images_uint8, weights: dict, wh: int, lrn: bool = True, noise=None, return_pre_tanh: bool = False, keep6=None, keep7=None):
     """images_uint8: [B, 3*wh*wh] or [B, 3, wh, wh] (RGB planes).  weights: name -> array with the reference's names
     ('discriminator.conv1.weights', ..., 'discriminator.ACGANOutput.W').  Returns float32 [B, HASH_DIM]."""
     with torch.no_grad():
         x = torch.as_tensor(np.asarray(images_uint8)).reshape(len(images_uint8), -1)
         B = x.shape[0]
         g = lambda k: torch.as_tensor(np.asarray(weights[k], dtype=np.float32))
-        x = normalize(x, noise)
+        x = normalize(x, None if noise is None else torch.as_tensor(np.asarray(noise, dtype=np.float32)).reshape(B, -1))
         x = preprocess_resize(x, wh)
         x = ten_crop(x)
         x = _conv(x, g("discriminator.conv1.weights"), g("discriminator.conv1.biases"), 4, 0, 1)   # :253-258
@@ -104,8 +109,8 @@ def encode(images_uint8, weights: dict, wh: int, lrn: bool = True, noise=None, r
         x = _conv(x, g("discriminator.conv5.weights"), g("discriminator.conv5.biases"), 1, 1, 2)   # :339-351
         x = _pool(x)                                                                               # :354-359
         x = x.reshape(x.shape[0], -1)                                                              # (h, w, c) flatten, :367
-        x = F.relu(x @ g("discriminator.fc6.weights") + g("discriminator.fc6.biases"))              # :368-369 (dropout off)
-        x = F.relu(x @ g("discriminator.fc7.weights") + g("discriminator.fc7.biases"))              # :376-377
+        x = _dropout(F.relu(x @ g("discriminator.fc6.weights") + g("discriminator.fc6.biases")), keep6)   # :368-369
+        x = _dropout(F.relu(x @ g("discriminator.fc7.weights") + g("discriminator.fc7.biases")), keep7)   # :376-377
         fc8 = x @ g("discriminator.ACGANOutput.W") + g("discriminator.ACGANOutput.b")               # :381-382, lib/ops.py:287-302
         if return_pre_tanh:
             return fc8.reshape(10, B, -1).numpy()

@@ -131,3 +131,29 @@ def test_tensor_core_convolution_option():
     assert np.abs(got - ref).max() <= 3e-2
     margin = np.abs(want) > 0.1
     assert np.array_equal(got[margin] > 0, want[margin] > 0)
+
+
+def test_stochastic_mode_matches_the_oracle_with_the_same_draws():
+    """EVAL.DETERMINISTIC False = the reference's stochastic eval graph (noise main.py:147, dropout at eval
+    architecture.py:369,377).  The generator is counter based, so the same draws are handed to the fp32 oracle."""
+    from hashgan_b200.encoder import AlexNetHashEncoder, AlexNetWeights, stochastic_draws
+    from oracle import alexnet_oracle
+
+    w = AlexNetWeights.synthetic(48, seed=4)
+    img = np.random.default_rng(6).integers(0, 256, (5, 3 * 32 * 32), dtype=np.uint8)
+    enc = AlexNetHashEncoder(w, lrn=True, deterministic=False, seed=123)
+    got1 = enc(img).cpu().numpy()
+    s1 = enc.last_seed
+    got2 = enc(img).cpu().numpy()
+    s2 = enc.last_seed
+    assert s1 != s2 and np.abs(got1 - got2).max() > 1e-3            # a fresh draw per call
+    det = AlexNetHashEncoder(w, lrn=True)(img).cpu().numpy()
+    assert np.abs(got1 - det).max() > 1e-3                            # and not the deterministic graph
+    for seed, got in ((s1, got1), (s2, got2)):
+        noise, keep6, keep7 = stochastic_draws(seed, len(img), 32)
+        assert 0.0 <= noise.min() and noise.max() < 1 / 128 and abs(noise.mean() - 1 / 256) < 2e-4
+        assert abs(keep6.mean() - 0.5) < 0.01 and abs(keep7.mean() - 0.5) < 0.01 and (keep6 != keep7).mean() > 0.4
+        want = alexnet_oracle.encode(img, w.tensors, 32, lrn=True, noise=noise, keep6=keep6, keep7=keep7)
+        assert np.abs(got - want).max() <= 5e-3
+    again = AlexNetHashEncoder(w, lrn=True, deterministic=False, seed=123)(img).cpu().numpy()
+    assert np.array_equal(again, got1)                                # same seed, same call index: same output
