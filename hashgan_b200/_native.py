@@ -17,6 +17,7 @@ FLAG_NO_FALLBACK = 2
 FLAG_TIMING = 4
 ENC_LRN = 1
 ENC_CONV_TF32 = 2
+ENC_CONV_TF32X3 = 8
 MAX_BITS = 256
 
 _i64, _int, _u32, _vp, _sz = C.c_int64, C.c_int, C.c_uint, C.c_void_p, C.c_size_t

@@ -166,8 +166,10 @@ _DEFAULTS = {
     "EVAL": {                                            # additive, build-only
         "BINARIZE": True,        # sign() the hash outputs and rank by Hamming distance (the B200 hot path); False = rank the raw
                                  # outputs by inner product exactly as lib/metric.py:13-14 does (hg_ip_map)
-        "CONV_TF32": False,      # conv1-5 as implicit GEMM on the tensor cores (TF32 operands, fp32 accumulate): 6x faster than the
-                                 # fp32 CUDA-core convolutions, outputs within 3e-2 of the fp32 graph (code bits equal where |h| > 0.1)
+        "CONV": "tf32x3",        # conv1-5: "tf32x3" = implicit GEMM on the tensor cores with error-compensated TF32 (hi/lo split,
+                                 # fp32-grade accuracy); "fp32" = CUDA cores; "tf32" = plain TF32 operands (fastest, outputs
+                                 # within 3e-2 of the fp32 graph, code bits equal where |h| > 0.1)
+        "CONV_TF32": False,      # older spelling of CONV: "tf32"
         "TIE_BREAK": "index",    # (distance asc, database row asc) == np.argsort(kind='stable')
         "NUM_GPUS": 1,           # row-shard database and queries over this many GPUs (torchrun)
         "DETERMINISTIC": True,   # no de-quantisation noise (main.py:147), no eval-time dropout (architecture.py:369,377);

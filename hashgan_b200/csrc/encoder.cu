@@ -321,7 +321,10 @@ __global__ void __launch_bounds__(256) conv_weight_pack_kernel(const float* __re
         const int k = (int)(i % Kpad);
         const int co = (int)(i / Kpad);  // = g * Cog + n
         const int tap = k / Cgp, ci = k % Cgp;
-        out[i] = (tap < taps && ci < Cg) ? w[((int64_t)tap * Cg + ci) * Cout + co] : 0.0f;
+        const float v = (tap < taps && ci < Cg) ? w[((int64_t)tap * Cg + ci) * Cout + co] : 0.0f;
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);  // exactly a TF32 number
+        out[i] = hi;
+        out[total + i] = v - hi;  // remainder, used by the error-compensated (3xTF32) convolution
     }
 }
 
@@ -355,8 +358,8 @@ static int launch_conv(const float* in, const float* w, const float* bias, float
 static int conv_cgp(int Cg) { return (Cg + 3) & ~3; }  // channels per group as the tensor-core path lays them out
 static int conv_kpad(int KH, int KW, int Cg) { return (int)round_up((int64_t)KH * KW * conv_cgp(Cg), 32); }
 
-int conv_gemm_tf32(const float* in, const float* wt, const float* bias, float* out, int64_t M, int H, int W, int C, int c0, int Cg, int KH, int KW,
-                   int stride, int pad, int Ho, int Wo, int Kpad, int Cog, int ldc, cudaStream_t st);  // gemm_tf32.cu
+int conv_gemm_tf32(const float* in, const float* wt, const float* wt_lo, const float* bias, float* out, int64_t M, int H, int W, int C, int c0,
+                   int Cg, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, int Cog, int ldc, cudaStream_t st);  // gemm_tf32.cu
 static bool env_flag_implicit()
 {
     const char* v = getenv("HG_CONV_IM2COL");  // =1: the earlier explicit im2col + GEMM pair (kept for comparison)
@@ -365,7 +368,7 @@ static bool env_flag_implicit()
 
 // convolution on the tensor cores: implicit GEMM (default) or per group im2col -> gemm_tf32, (+bias, ReLU) straight into the NHWC output
 static int launch_conv_tf32(const float* in, const float* wt, const float* bias, float* out, float* col, int N, int H, int W, int C, int KH, int KW,
-                            int stride, int pad, int Cout, int groups, cudaStream_t st)
+                            int stride, int pad, int Cout, int groups, bool x3, cudaStream_t st)
 {
     const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
     const int Cg = C / groups, Cog = Cout / groups;  // C is the stored (padded) channel count: conv1 reads 4-channel crops
@@ -373,10 +376,11 @@ static int launch_conv_tf32(const float* in, const float* wt, const float* bias,
     const int64_t M = (int64_t)N * Ho * Wo;
     if (M >= (int64_t(1) << 31)) return fail(HG_EINVAL, "conv_tf32: batch too large");
     if ((Cg % 4) || (C % 4) || (reinterpret_cast<uintptr_t>(in) & 15)) return fail(HG_EINVAL, "conv_tf32: channels must be a multiple of 4");
-    if (env_flag_implicit()) {  // implicit GEMM: the A tiles are gathered inside the GEMM kernel, no im2col matrix
+    if (x3 || env_flag_implicit()) {  // implicit GEMM: the A tiles are gathered inside the GEMM kernel, no im2col matrix
+        const float* wt_lo = x3 ? wt + (size_t)Cout * Kpad : nullptr;  // hg_conv_weight_pack: [hi | lo]
         for (int g = 0; g < groups; ++g) {
-            int rc = conv_gemm_tf32(in, wt + (size_t)g * Cog * Kpad, bias + g * Cog, out + g * Cog, M, H, W, C, g * Cg, Cg, KH, KW, stride, pad, Ho, Wo,
-                                    Kpad, Cog, Cout, st);
+            int rc = conv_gemm_tf32(in, wt + (size_t)g * Cog * Kpad, wt_lo ? wt_lo + (size_t)g * Cog * Kpad : nullptr, bias + g * Cog, out + g * Cog, M, H,
+                                    W, C, g * Cg, Cg, KH, KW, stride, pad, Ho, Wo, Kpad, Cog, Cout, st);
             if (rc != HG_OK) return rc;
         }
         return HG_OK;
@@ -405,7 +409,7 @@ namespace hg { static size_t col_bytes(int n) { return (((size_t)n * 10 * 55 * 5
 extern "C" size_t hg_alexnet_workspace_bytes(int n, unsigned flags)
 {
     if (n <= 0) return 0;
-    return 2 * hg::buf_bytes(n) + ((flags & HG_ENC_CONV_TF32) ? hg::col_bytes(n) : 0);
+    return 2 * hg::buf_bytes(n) + ((flags & HG_ENC_CONV_TF32) ? hg::col_bytes(n) : 0);  // the im2col matrix only exists for HG_CONV_IM2COL=1
 }
 
 extern "C" int hg_conv_weight_pack(const float* d_w_hwio, int KH, int KW, int Cg, int Cout, int groups, float* d_out, void* stream)
@@ -440,8 +444,9 @@ static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgA
     for (int i = 0; i < 5; ++i)
         if (!w->conv_w[i] || !w->conv_b[i]) return fail(HG_EINVAL, "hg_alexnet_encode: conv%d weights missing", i + 1);
     if (!w->fc6_wt || !w->fc6_b || !w->fc7_wt || !w->fc7_b || !w->fc8_wt || !w->fc8_b) return fail(HG_EINVAL, "hg_alexnet_encode: fc weights missing");
-    if (flags & ~(unsigned)(HG_ENC_LRN | HG_ENC_CONV_TF32)) return fail(HG_EINVAL, "hg_alexnet_encode: unknown flag (only the deterministic mode is implemented)");
-    const bool tc = (flags & HG_ENC_CONV_TF32) != 0;
+    if (flags & ~(unsigned)(HG_ENC_LRN | HG_ENC_CONV_TF32 | HG_ENC_CONV_TF32X3)) return fail(HG_EINVAL, "hg_alexnet_encode: unknown flag");
+    const bool x3 = (flags & HG_ENC_CONV_TF32X3) != 0;
+    const bool tc = x3 || (flags & HG_ENC_CONV_TF32) != 0;
     if (tc)
         for (int i = 0; i < 5; ++i)
             if (!w->conv_wt[i]) return fail(HG_EINVAL, "hg_alexnet_encode: HG_ENC_CONV_TF32 needs conv_wt[%d] (hg_conv_weight_pack)", i);
@@ -454,7 +459,7 @@ static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgA
     int rc;
     // one convolution layer: fp32 on the CUDA cores (default, parity with the fp32 oracle to ~1e-5) or TF32 on tcgen05
     auto conv = [&](int i, const float* src, float* dst, int H, int C, int KH, int stride, int pad, int Cout, int groups) -> int {
-        return tc ? launch_conv_tf32(src, w->conv_wt[i], w->conv_b[i], dst, col, N, H, H, (C + 3) & ~3, KH, KH, stride, pad, Cout, groups, st)
+        return tc ? launch_conv_tf32(src, w->conv_wt[i], w->conv_b[i], dst, col, N, H, H, (C + 3) & ~3, KH, KH, stride, pad, Cout, groups, x3, st)
                   : launch_conv(src, w->conv_w[i], w->conv_b[i], dst, N, H, H, C, KH, KH, stride, pad, Cout, groups, st);
     };
     // crops -> A

@@ -166,17 +166,22 @@ struct ConvGemmArgs {
     int H, W, C, c0, Cg, KH, KW, stride, pad, Ho, Wo, Kpad, Cog, ldc;
 };
 
-constexpr int kConvStages = 3;
 __host__ __device__ constexpr int conv_tmem_cols(int BN) { return BN <= 64 ? 64 : (BN <= 128 ? 128 : 256); }
+// X3 = error-compensated TF32 ("3xTF32"): every fp32 operand is split into hi (its upper 19 bits, exactly a TF32 number) and
+// lo = x - hi; hi*hi + lo*hi + hi*lo accumulated in the fp32 accumulator reproduces the fp32 product to ~2^-21, so the
+// tensor-core convolution matches the fp32 graph like the CUDA-core one does.  Stage = [A hi][A lo][B hi][B lo].
+__host__ __device__ constexpr int conv_stages(int BN, bool X3) { return X3 ? (BN <= 128 ? 3 : 2) : 3; }
 
-template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, (BN <= 128 ? 2 : 1))
-conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, ConvGemmArgs a)
+template <int BN, bool X3>
+__global__ void __launch_bounds__(kGemmThreads, (!X3 && BN <= 128 ? 2 : 1))
+conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_blo, ConvGemmArgs a)
 {
     extern __shared__ __align__(1024) uint8_t csm[];
+    constexpr int kConvStages = conv_stages(BN, X3);
     constexpr uint32_t A_BYTES = kGemmBM * kGemmBK * 4;  // 16 KB
     constexpr uint32_t B_BYTES = BN * kGemmBK * 4;
-    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t A_ALL = (X3 ? 2 : 1) * A_BYTES;
+    constexpr uint32_t STAGE_BYTES = A_ALL + (X3 ? 2 : 1) * B_BYTES;
     const uint32_t base = (smem_u32(csm) + 1023u) & ~1023u;
     uint8_t* const base_ptr = csm + (base - smem_u32(csm));
     int2* const tab = reinterpret_cast<int2*>(base_ptr + kConvStages * STAGE_BYTES);  // per 16-byte K chunk: {input offset, ky | kx << 16}
@@ -217,8 +222,9 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, ConvGemmArgs a
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % kConvStages;
                 mbar_wait(&empty_bar[s], (uint32_t)(((kb / kConvStages) & 1) ^ 1));
-                mbar_arrive_expect_tx(&full_bar[s], B_BYTES);
-                tma_load_2d(base + s * STAGE_BYTES + A_BYTES, &tmap_b, smem_u32(&full_bar[s]), kb * kGemmBK, n0);
+                mbar_arrive_expect_tx(&full_bar[s], (X3 ? 2 : 1) * B_BYTES);
+                tma_load_2d(base + s * STAGE_BYTES + A_ALL, &tmap_b, smem_u32(&full_bar[s]), kb * kGemmBK, n0);
+                if (X3) tma_load_2d(base + s * STAGE_BYTES + A_ALL + B_BYTES, &tmap_blo, smem_u32(&full_bar[s]), kb * kGemmBK, n0);
             }
         }
     } else if (warp == 1) {
@@ -228,11 +234,17 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, ConvGemmArgs a
                 const int s = kb % kConvStages;
                 mbar_wait(&full_bar[s], (uint32_t)((kb / kConvStages) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+                const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_ALL;
                 const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sb);
 #pragma unroll
-                for (int k = 0; k < kGemmBK / 8; ++k)
+                for (int k = 0; k < kGemmBK / 8; ++k) {
                     umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                    if (X3) {
+                        const uint64_t alo = umma_desc_sw128(sa + A_BYTES), blo = umma_desc_sw128(sb + B_BYTES);
+                        umma_tf32(tmem_base, alo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                        umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc, 1u);
+                    }
+                }
                 umma_commit(&empty_bar[s]);
             }
             umma_commit(&tmem_full_bar);
@@ -275,7 +287,19 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, ConvGemmArgs a
             mbar_wait(&empty_bar[s], (uint32_t)(((kb / kConvStages) & 1) ^ 1));  // the loads above are already in flight
             uint8_t* sa = base_ptr + s * STAGE_BYTES;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(sa + soff[i]) = v[i];
+            for (int i = 0; i < 8; ++i) {
+                if (X3) {
+                    float4 hi, lo;
+                    hi.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u); lo.x = v[i].x - hi.x;
+                    hi.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u); lo.y = v[i].y - hi.y;
+                    hi.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u); lo.z = v[i].z - hi.z;
+                    hi.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u); lo.w = v[i].w - hi.w;
+                    *reinterpret_cast<float4*>(sa + soff[i]) = hi;
+                    *reinterpret_cast<float4*>(sa + A_BYTES + soff[i]) = lo;
+                } else {
+                    *reinterpret_cast<float4*>(sa + soff[i]) = v[i];
+                }
+            }
             fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
             __syncwarp();
             if (lane == 0) {
@@ -360,25 +384,26 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t K,
     return HG_OK;
 }
 
-template <int BN>
-static int launch_conv_gemm(const CUtensorMap& tb, const ConvGemmArgs& a, cudaStream_t st)
+template <int BN, bool X3>
+static int launch_conv_gemm(const CUtensorMap& tb, const CUtensorMap& tblo, const ConvGemmArgs& a, cudaStream_t st)
 {
-    const size_t smem = (size_t)kConvStages * (kGemmBM + BN) * kGemmBK * 4 + (size_t)(a.Kpad / 4) * sizeof(int2) + 1024;
+    const size_t smem = (size_t)conv_stages(BN, X3) * (X3 ? 2 : 1) * (kGemmBM + BN) * kGemmBK * 4 + (size_t)(a.Kpad / 4) * sizeof(int2) + 1024;
     static thread_local size_t configured = 0;
     if (smem > configured) {
-        HG_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HG_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     dim3 grid((unsigned)ceil_div(a.Cog, BN), (unsigned)ceil_div(a.M, kGemmBM));
-    conv_gemm_tf32_kernel<BN><<<grid, kGemmThreads, smem, st>>>(tb, a);
+    conv_gemm_tf32_kernel<BN, X3><<<grid, kGemmThreads, smem, st>>>(tb, tblo, a);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     return HG_OK;
 }
 
-// one channel group of a convolution layer; wt = this group's weights [Cog, Kpad] K-major (hg_conv_weight_pack)
-int conv_gemm_tf32(const float* in, const float* wt, const float* bias, float* out, int64_t M, int H, int W, int C, int c0, int Cg, int KH, int KW,
-                   int stride, int pad, int Ho, int Wo, int Kpad, int Cog, int ldc, cudaStream_t st)
+// one channel group of a convolution layer; wt = this group's weights [Cog, Kpad] K-major (hg_conv_weight_pack: upper 19
+// bits of every weight), wt_lo = the remainders for the error-compensated mode (NULL: plain TF32)
+int conv_gemm_tf32(const float* in, const float* wt, const float* wt_lo, const float* bias, float* out, int64_t M, int H, int W, int C, int c0,
+                   int Cg, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, int Cog, int ldc, cudaStream_t st)
 {
     if ((Cg % 4) || (C % 4) || (c0 % 4) || (reinterpret_cast<uintptr_t>(in) & 15) || (Kpad % kGemmBK))
         return fail(HG_EINVAL, "conv_gemm_tf32: channels must be multiples of 4, Kpad a multiple of %d", kGemmBK);
@@ -387,14 +412,23 @@ int conv_gemm_tf32(const float* in, const float* wt, const float* bias, float* o
     a.in = in; a.bias = bias; a.out = out; a.M = M; a.H = H; a.W = W; a.C = C; a.c0 = c0; a.Cg = Cg; a.KH = KH; a.KW = KW; a.stride = stride;
     a.pad = pad; a.Ho = Ho; a.Wo = Wo; a.Kpad = Kpad; a.Cog = Cog; a.ldc = ldc;
     const int BN = (Cog % 128 == 0) ? 128 : ((Cog % 192 == 0) ? 192 : ((Cog % 96 == 0) ? 96 : (Cog <= 64 ? 64 : 128)));
-    CUtensorMap tb;
+    CUtensorMap tb, tblo;
     int rc;
     if ((rc = make_map(&tb, wt, Cog, Kpad, Kpad, BN)) != HG_OK) return rc;
+    if ((rc = make_map(&tblo, wt_lo ? wt_lo : wt, Cog, Kpad, Kpad, BN)) != HG_OK) return rc;
+    if (wt_lo) {
+        switch (BN) {
+            case 64: return launch_conv_gemm<64, true>(tb, tblo, a, st);
+            case 96: return launch_conv_gemm<96, true>(tb, tblo, a, st);
+            case 192: return launch_conv_gemm<192, true>(tb, tblo, a, st);
+            default: return launch_conv_gemm<128, true>(tb, tblo, a, st);
+        }
+    }
     switch (BN) {
-        case 64: return launch_conv_gemm<64>(tb, a, st);
-        case 96: return launch_conv_gemm<96>(tb, a, st);
-        case 192: return launch_conv_gemm<192>(tb, a, st);
-        default: return launch_conv_gemm<128>(tb, a, st);
+        case 64: return launch_conv_gemm<64, false>(tb, tblo, a, st);
+        case 96: return launch_conv_gemm<96, false>(tb, tblo, a, st);
+        case 192: return launch_conv_gemm<192, false>(tb, tblo, a, st);
+        default: return launch_conv_gemm<128, false>(tb, tblo, a, st);
     }
 }
 

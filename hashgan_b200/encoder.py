@@ -127,7 +127,7 @@ class AlexNetHashEncoder:
     """images (uint8, [B, 3*wh*wh] as the loader yields them, lib/dataloader.py:110-113) -> CUDA float32 [B, HASH_DIM]."""
 
     def __init__(self, weights: AlexNetWeights, *, lrn: bool = True, device=None, conv_tf32: bool = False, deterministic: bool = True,
-                 seed: int = 0):
+                 seed: int = 0, conv: Optional[str] = None):
         import torch
 
         if not torch.cuda.is_available():
@@ -136,7 +136,14 @@ class AlexNetHashEncoder:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.hash_dim = weights.hash_dim
         self.lrn = lrn
-        self.conv_tf32 = conv_tf32  # opt-in: conv1-5 on tcgen05 (TF32) instead of fp32 CUDA cores
+        # conv1-5: "tf32x3" (default) = implicit GEMM on tcgen05 with error-compensated TF32 (fp32-grade accuracy, 4x faster
+        # than the CUDA cores); "fp32" = CUDA cores; "tf32" = plain TF32 operands (fastest, ~1e-3 relative error).
+        # conv_tf32=True is the older spelling of conv="tf32".
+        self.conv = conv if conv is not None else ("tf32" if conv_tf32 else "tf32x3")
+        if self.conv not in ("fp32", "tf32", "tf32x3"):
+            raise ValueError("conv must be 'fp32', 'tf32' or 'tf32x3'")
+        conv_tf32 = self.conv != "fp32"
+        self.conv_tf32 = conv_tf32
         # deterministic=False: the reference's stochastic eval graph (de-quantisation noise main.py:147, dropout at eval
         # architecture.py:369,377); every encode() call draws with a fresh seed derived from `seed` and the call count
         self.deterministic = deterministic
@@ -164,7 +171,7 @@ class AlexNetHashEncoder:
                     kh, kw, cg, cout = shp
                     groups = 1 if name in ("conv1", "conv3") else 2
                     kpad = ((kh * kw * ((cg + 3) // 4 * 4) + 31) // 32) * 32
-                    dst = torch.empty((cout * kpad,), dtype=torch.float32, device=dev)
+                    dst = torch.empty((2 * cout * kpad,), dtype=torch.float32, device=dev)  # [hi | lo], hg_conv_weight_pack
                     _native.check(self.lib.hg_conv_weight_pack(t[f"discriminator.{name}.weights"].data_ptr(), kh, kw, cg, cout, groups,
                                                                dst.data_ptr(), stream))
                     self._wt[name] = dst
@@ -199,7 +206,7 @@ class AlexNetHashEncoder:
         with torch.cuda.device(dev):
             x = x.to(dev, non_blocking=True).contiguous()
             out = torch.empty((n, self.hash_dim), dtype=torch.float32, device=dev)
-            flags = (_native.ENC_LRN if self.lrn else 0) | (_native.ENC_CONV_TF32 if self.conv_tf32 else 0)
+            flags = (_native.ENC_LRN if self.lrn else 0) | {"fp32": 0, "tf32": _native.ENC_CONV_TF32, "tf32x3": _native.ENC_CONV_TF32X3}[self.conv]
             need = self.lib.hg_alexnet_workspace_bytes(n, flags)
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty((need,), dtype=torch.uint8, device=dev)

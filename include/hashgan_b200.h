@@ -172,13 +172,15 @@ typedef struct HgAlexNetWeights {
 } HgAlexNetWeights;
 
 #define HG_ENC_LRN 1u        /* local response normalisation after pool1/pool2: on iff TRAIN.WGAN_SCALE == 0 (architecture.py:268,294) */
-#define HG_ENC_CONV_TF32 2u  /* opt-in: conv1-5 as im2col + tcgen05 TF32 GEMM (about 5x faster, ~1e-3 relative error) instead of fp32 CUDA cores */
+#define HG_ENC_CONV_TF32 2u  /* opt-in: conv1-5 as implicit GEMM on tcgen05 with plain TF32 operands (6x faster than the fp32 CUDA cores, ~1e-3 relative error) */
+#define HG_ENC_CONV_TF32X3 8u /* conv1-5 as implicit GEMM on tcgen05 with error-compensated TF32 (hi/lo split, 3 MMAs): fp32-grade accuracy */
 
 /* Workspace bytes for a batch of n images (10 n crops) with these flags. */
 size_t hg_alexnet_workspace_bytes(int n, unsigned flags);
 
 /* HWIO convolution weights [KH, KW, Cg, Cout] -> per-group K-major [groups][Cout/groups][Kpad] (channels per group padded
- * to a multiple of 4, Kpad = KH*KW*Cg4 rounded up to 32, zero padded): the B operand of the tensor-core convolution.  d_out holds Cout * Kpad floats. */
+ * to a multiple of 4, Kpad = KH*KW*Cg4 rounded up to 32, zero padded): the B operand of the tensor-core convolution.  d_out holds 2 * Cout * Kpad floats: first the upper 19 bits of
+ * every weight (exactly TF32), then the remainders w - hi used by the error-compensated mode (HG_ENC_CONV_TF32X3). */
 int hg_conv_weight_pack(const float* d_w_hwio, int KH, int KW, int Cg, int Cout, int groups, float* d_out, void* stream);
 
 /* d_images: uint8 [n, 3, wh, wh], RGB planes -- the loader's flattened batch (lib/dataloader.py:110-113), wh <= 256.

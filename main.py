@@ -40,7 +40,7 @@ def main(cfg):
         print("discriminator checkpoint restored: {} ({} tensors)".format(ckpt, len(names)))
     elif len(ckpt) > 0 and not cfg.EVAL.SYNTHETIC:
         raise SystemExit("{}.index not found (set EVAL.SYNTHETIC: True to evaluate without the trained checkpoint)".format(ckpt))
-    encoder = AlexNetHashEncoder(weights, lrn=(cfg.TRAIN.WGAN_SCALE == 0), conv_tf32=bool(cfg.EVAL.CONV_TF32),
+    encoder = AlexNetHashEncoder(weights, lrn=(cfg.TRAIN.WGAN_SCALE == 0), conv=("tf32" if cfg.EVAL.CONV_TF32 else cfg.EVAL.CONV),
                                  deterministic=bool(cfg.EVAL.DETERMINISTIC), seed=cfg.EVAL.SEED)
     if os.path.isdir(cfg.DATA.DATA_ROOT) and os.path.isdir(cfg.DATA.LIST_ROOT):
         dataloader = Dataloader(cfg.TRAIN.BATCH_SIZE, cfg.DATA.WIDTH_HEIGHT, cfg.DATA.LIST_ROOT, cfg.DATA.DATA_ROOT)
