@@ -61,7 +61,7 @@ class AlexNetWeightsStruct(C.Structure):
     """HgAlexNetWeights of include/hashgan_b200.h."""
     _fields_ = [("conv_w", C.c_void_p * 5), ("conv_b", C.c_void_p * 5),
                 ("fc6_wt", C.c_void_p), ("fc6_b", C.c_void_p), ("fc7_wt", C.c_void_p), ("fc7_b", C.c_void_p),
-                ("fc8_wt", C.c_void_p), ("fc8_b", C.c_void_p), ("conv_wt", C.c_void_p * 5)]
+                ("fc8_wt", C.c_void_p), ("fc8_b", C.c_void_p), ("conv_wt", C.c_void_p * 5), ("fc_wt3", C.c_void_p * 3)]
 
 
 _lib = None

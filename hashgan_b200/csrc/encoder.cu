@@ -359,7 +359,7 @@ static int conv_cgp(int Cg) { return (Cg + 3) & ~3; }  // channels per group as 
 static int conv_kpad(int KH, int KW, int Cg) { return (int)round_up((int64_t)KH * KW * conv_cgp(Cg), 32); }
 
 int conv_gemm_tf32(const float* in, const float* wt, const float* wt_lo, const float* bias, float* out, int64_t M, int H, int W, int C, int c0,
-                   int Cg, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, int Cog, int ldc, cudaStream_t st);  // gemm_tf32.cu
+                   int Cg, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, int Cog, int ldc, cudaStream_t st, int relu = 1);  // gemm_tf32.cu
 static bool env_flag_implicit()
 {
     const char* v = getenv("HG_CONV_IM2COL");  // =1: the earlier explicit im2col + GEMM pair (kept for comparison)
@@ -503,20 +503,26 @@ static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgA
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     std::swap(cur, other);
-    // fc6, fc7 (+ReLU), fc8 on the tensor cores
-    if ((rc = gemm_tf32(cur, 9216, w->fc6_wt, 9216, w->fc6_b, other, 4096, N, 4096, 9216, 1, st)) != HG_OK) return rc;
+    // fc6, fc7 (+ReLU), fc8 on the tensor cores.  In the error-compensated mode a dense layer is the 1x1 "convolution"
+    // of the implicit-GEMM kernel (H = W = 1, C = K): its producer warps split the activations into hi/lo on the fly.
+    const bool fc3 = x3 && w->fc_wt3[0] && w->fc_wt3[1] && w->fc_wt3[2];
+    auto dense = [&](const float* src, float* dst, const float* wt3, const float* wt, const float* bias, int K, int Nout, int relu) -> int {
+        if (fc3) return conv_gemm_tf32(src, wt3, wt3 + (size_t)Nout * K, bias, dst, N, 1, 1, K, 0, K, 1, 1, 1, 0, 1, 1, K, Nout, Nout, st, relu);
+        return gemm_tf32(src, K, wt, K, bias, dst, Nout, N, Nout, K, relu, st);
+    };
+    if ((rc = dense(cur, other, w->fc_wt3[0], w->fc6_wt, w->fc6_b, 9216, 4096, 1)) != HG_OK) return rc;
     std::swap(cur, other);
     if (seed) {
         dropout_half_kernel<<<grid_1d((int64_t)N * 4096, 256), 256, 0, st>>>(cur, (int64_t)N * 4096, seed ^ kStreamDrop6);
         count_launch();
     }
-    if ((rc = gemm_tf32(cur, 4096, w->fc7_wt, 4096, w->fc7_b, other, 4096, N, 4096, 4096, 1, st)) != HG_OK) return rc;
+    if ((rc = dense(cur, other, w->fc_wt3[1], w->fc7_wt, w->fc7_b, 4096, 4096, 1)) != HG_OK) return rc;
     std::swap(cur, other);
     if (seed) {
         dropout_half_kernel<<<grid_1d((int64_t)N * 4096, 256), 256, 0, st>>>(cur, (int64_t)N * 4096, seed ^ kStreamDrop7);
         count_launch();
     }
-    if ((rc = gemm_tf32(cur, 4096, w->fc8_wt, 4096, w->fc8_b, other, hash_dim, N, hash_dim, 4096, 0, st)) != HG_OK) return rc;
+    if ((rc = dense(cur, other, w->fc_wt3[2], w->fc8_wt, w->fc8_b, 4096, hash_dim, 0)) != HG_OK) return rc;
     std::swap(cur, other);
     tanh_crop_mean_kernel<<<grid_1d((int64_t)n * hash_dim, 256), 256, 0, st>>>(cur, n, hash_dim, d_out);
     count_launch();

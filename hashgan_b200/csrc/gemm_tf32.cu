@@ -164,6 +164,7 @@ struct ConvGemmArgs {
     float* out;         // [M, ldc], already offset to the group's first output channel
     int64_t M;
     int H, W, C, c0, Cg, KH, KW, stride, pad, Ho, Wo, Kpad, Cog, ldc;
+    int relu;  // 1: ReLU after the bias (convolutions, fc6, fc7); 0: linear (fc8)
 };
 
 __host__ __device__ constexpr int conv_tmem_cols(int BN) { return BN <= 64 ? 64 : (BN <= 128 ? 128 : 256); }
@@ -334,7 +335,8 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
 #pragma unroll
                     for (int t = 0; t < 4; ++t) {
                         const int n = n0 + c0 + j + t;
-                        o[t] = fmaxf(__uint_as_float(r[j + t]) + (n < a.Cog ? __ldg(a.bias + n) : 0.0f), 0.0f);
+                        const float x = __uint_as_float(r[j + t]) + (n < a.Cog ? __ldg(a.bias + n) : 0.0f);
+                        o[t] = a.relu ? fmaxf(x, 0.0f) : x;
                     }
                     if (vec) {
                         *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
@@ -403,14 +405,14 @@ static int launch_conv_gemm(const CUtensorMap& tb, const CUtensorMap& tblo, cons
 // one channel group of a convolution layer; wt = this group's weights [Cog, Kpad] K-major (hg_conv_weight_pack: upper 19
 // bits of every weight), wt_lo = the remainders for the error-compensated mode (NULL: plain TF32)
 int conv_gemm_tf32(const float* in, const float* wt, const float* wt_lo, const float* bias, float* out, int64_t M, int H, int W, int C, int c0,
-                   int Cg, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, int Cog, int ldc, cudaStream_t st)
+                   int Cg, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, int Cog, int ldc, cudaStream_t st, int relu)
 {
     if ((Cg % 4) || (C % 4) || (c0 % 4) || (reinterpret_cast<uintptr_t>(in) & 15) || (Kpad % kGemmBK))
         return fail(HG_EINVAL, "conv_gemm_tf32: channels must be multiples of 4, Kpad a multiple of %d", kGemmBK);
     if ((int64_t)M / ((int64_t)Ho * Wo) * H * W * C >= (int64_t(1) << 31)) return fail(HG_EINVAL, "conv_gemm_tf32: input too large for 32-bit offsets");
     ConvGemmArgs a{};
     a.in = in; a.bias = bias; a.out = out; a.M = M; a.H = H; a.W = W; a.C = C; a.c0 = c0; a.Cg = Cg; a.KH = KH; a.KW = KW; a.stride = stride;
-    a.pad = pad; a.Ho = Ho; a.Wo = Wo; a.Kpad = Kpad; a.Cog = Cog; a.ldc = ldc;
+    a.pad = pad; a.Ho = Ho; a.Wo = Wo; a.Kpad = Kpad; a.Cog = Cog; a.ldc = ldc; a.relu = relu;
     const int BN = (Cog % 128 == 0) ? 128 : ((Cog % 192 == 0) ? 192 : ((Cog % 96 == 0) ? 96 : (Cog <= 64 ? 64 : 128)));
     CUtensorMap tb, tblo;
     int rc;

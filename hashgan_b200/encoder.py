@@ -176,6 +176,14 @@ class AlexNetHashEncoder:
                                                                dst.data_ptr(), stream))
                     self._wt[name] = dst
                     st.conv_wt[i] = dst.data_ptr()
+                if self.conv == "tf32x3":  # dense layers error-compensated too: [K, N] is HWIO with a 1x1 window
+                    for i, name in enumerate(("discriminator.fc6.weights", "discriminator.fc7.weights", "discriminator.ACGANOutput.W")):
+                        src = t[name]
+                        k_in, n_out = int(src.shape[0]), int(src.shape[1])
+                        dst = torch.empty((2 * n_out * k_in,), dtype=torch.float32, device=dev)
+                        _native.check(self.lib.hg_conv_weight_pack(src.data_ptr(), 1, 1, k_in, n_out, 1, dst.data_ptr(), stream))
+                        self._wt[f"fc3_{i}"] = dst
+                        st.fc_wt3[i] = dst.data_ptr()
             torch.cuda.synchronize(dev)
         st.fc6_wt, st.fc6_b = self._wt["fc6"].data_ptr(), t["discriminator.fc6.biases"].data_ptr()
         st.fc7_wt, st.fc7_b = self._wt["fc7"].data_ptr(), t["discriminator.fc7.biases"].data_ptr()

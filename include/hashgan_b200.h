@@ -168,12 +168,14 @@ typedef struct HgAlexNetWeights {
     const float* fc6_wt; const float* fc6_b;
     const float* fc7_wt; const float* fc7_b;
     const float* fc8_wt; const float* fc8_b;
-    const float* conv_wt[5];  /* optional (HG_ENC_CONV_TF32): hg_conv_weight_pack of conv_w[i] */
+    const float* conv_wt[5];  /* tensor-core convolutions: hg_conv_weight_pack of conv_w[i] */
+    const float* fc_wt3[3];   /* optional, HG_ENC_CONV_TF32X3: hg_conv_weight_pack(W, 1, 1, K, N, 1) of the fc6 / fc7 / fc8 matrices
+                               * [K, N]; when present the dense layers also run error-compensated (fp32-grade end to end) */
 } HgAlexNetWeights;
 
 #define HG_ENC_LRN 1u        /* local response normalisation after pool1/pool2: on iff TRAIN.WGAN_SCALE == 0 (architecture.py:268,294) */
 #define HG_ENC_CONV_TF32 2u  /* opt-in: conv1-5 as implicit GEMM on tcgen05 with plain TF32 operands (6x faster than the fp32 CUDA cores, ~1e-3 relative error) */
-#define HG_ENC_CONV_TF32X3 8u /* conv1-5 as implicit GEMM on tcgen05 with error-compensated TF32 (hi/lo split, 3 MMAs): fp32-grade accuracy */
+#define HG_ENC_CONV_TF32X3 8u /* conv1-5 (and fc6-8 when fc_wt3 is set) as implicit GEMM on tcgen05 with error-compensated TF32 (hi/lo split, 3 MMAs): fp32-grade accuracy */
 
 /* Workspace bytes for a batch of n images (10 n crops) with these flags. */
 size_t hg_alexnet_workspace_bytes(int n, unsigned flags);

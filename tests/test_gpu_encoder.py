@@ -159,22 +159,21 @@ def test_stochastic_mode_matches_the_oracle_with_the_same_draws():
     assert np.array_equal(again, got1)                                # same seed, same call index: same output
 
 
-def test_error_compensated_tensor_core_convolution_is_fp32_grade():
-    """conv='tf32x3': conv1-5 as implicit GEMM on tcgen05 with hi/lo-split TF32 operands (3 MMAs per product).  It must
-    agree with the fp32 CUDA-core convolutions as closely as those agree with the fp32 oracle (the TF32 fc layers are
-    common to both), i.e. pass the DEFAULT path's bounds."""
+def test_error_compensated_tensor_core_path_is_fp32_grade():
+    """conv='tf32x3' (the default): conv1-5 AND fc6-8 as implicit GEMM on tcgen05 with hi/lo-split TF32 operands (3 MMAs
+    per product).  The whole encoder then agrees with the fp32 oracle an order of magnitude better than the paths whose
+    dense layers use plain TF32."""
     from hashgan_b200.encoder import AlexNetHashEncoder, AlexNetWeights
     from oracle import alexnet_oracle
 
     w = AlexNetWeights.synthetic(64, seed=3)
     img = np.random.default_rng(5).integers(0, 256, (9, 3 * 32 * 32), dtype=np.uint8)
     want = alexnet_oracle.encode(img, w.tensors, 32, lrn=True)
-    ref = AlexNetHashEncoder(w, lrn=True, conv="fp32")(img).cpu().numpy()
-    got = AlexNetHashEncoder(w, lrn=True, conv="tf32x3")(img).cpu().numpy()
-    plain = AlexNetHashEncoder(w, lrn=True, conv="tf32")(img).cpu().numpy()
-    assert np.abs(got - want).max() <= 5e-3
-    margin = np.abs(want) > 0.02
-    assert np.array_equal(got[margin] > 0, want[margin] > 0)
-    assert np.abs(got - ref).max() <= 1e-3                               # the convolutions themselves: fp32-grade (the shared
-                                                                         # TF32 fc layers turn last-bit differences into ~1e-4)
-    assert np.abs(got - ref).max() < 0.2 * np.abs(plain - ref).max()     # and clearly tighter than plain TF32
+    err = {c: np.abs(AlexNetHashEncoder(w, lrn=True, conv=c)(img).cpu().numpy() - want).max() for c in ("tf32x3", "fp32", "tf32")}
+    assert err["tf32x3"] <= 5e-4          # fp32 summation-order noise only
+    assert err["fp32"] <= 5e-3            # fp32 convolutions + plain-TF32 dense layers (the north_star's split)
+    assert err["tf32"] <= 3e-2            # plain TF32 everywhere
+    assert err["tf32x3"] < 0.25 * err["fp32"]
+    got = AlexNetHashEncoder(w, lrn=True)(img).cpu().numpy()      # default == tf32x3
+    margin = np.abs(want) > 2e-3
+    assert np.array_equal(got[margin] > 0, want[margin] > 0)      # code bits equal except where |h| < 2e-3
