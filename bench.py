@@ -209,7 +209,7 @@ def main():
     sym, exchange = None, "none"
     if world > 1:
         exchange = "NCCL all-gather of packed rows"
-        if os.environ.get("HG_EXCHANGE", "push") != "nccl":
+        if os.environ.get("HG_EXCHANGE", "push") != "nccl" and wl.b % 32 == 0:  # the fused kernel packs whole code words
             try:
                 from hashgan_b200.sharding import SymmetricRows
 

@@ -62,6 +62,23 @@ def test_exact_on_dyadic_grid(hb, b, ndb, nq, L, R):
     assert abs(got - maps_oracle.exact_mean_ap(ref_ap)) <= 1e-12
 
 
+def test_query_chunks_are_invisible(hb):
+    """A workspace that holds the keys of only a few queries at a time: same rows, inner products and AP."""
+    from hashgan_b200 import _native
+
+    rng = np.random.default_rng(77)
+    b, ndb, nq, L, R = 32, 9001, 41, 5, 300
+    db = NS(output=_grid(rng, ndb, b), label=_one_hot(rng, ndb, L))
+    q = NS(output=_grid(rng, nq, b), label=_one_hot(rng, nq, L))
+    one = _native.lib().hg_ip_map_workspace_bytes(1, ndb, b, L, R)
+    small = hb.MAPs(R, binarize=False, workspace_limit=one * 6 + 512)   # chunks of ~6 queries
+    ap_s, ids_s, ips_s = small.per_query_ap(db, q, want_ids=True)
+    ap, ids, ips = hb.MAPs(R, binarize=False).per_query_ap(db, q, want_ids=True)
+    assert np.array_equal(ids_s, ids) and np.array_equal(ips_s, ips) and np.array_equal(ap_s, ap)
+    ref_ap, ref_ids, _ = _oracle(db, q, R)
+    assert np.array_equal(ids, ref_ids) and np.max(np.abs(ap - ref_ap)) <= 1e-12
+
+
 def test_pm1_codes_rank_like_the_hamming_path(hb):
     """On {-1,+1} codes ip = b - 2 d_H: the real-valued mode must return the very ranking of the binarised hot path."""
     from hashgan_b200.synthetic import make_workload
