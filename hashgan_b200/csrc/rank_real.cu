@@ -333,7 +333,10 @@ static RealPlan make_real_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R,
     p.smem = p.smem_sort ? (size_t)R * 16 : 0;
     const size_t per_query = (size_t)p.key_stride * 4 + (p.smem_sort ? 0 : (size_t)R * 16);
     int64_t chunk = std::min<int64_t>(nq, 592);  // 2 resident CTAs x 148 SMs x 2 rounds
-    if (ws_bytes) chunk = std::min<int64_t>(nq, (int64_t)((ws_bytes - 1024) / per_query));
+    if (ws_bytes) {
+        if (ws_bytes < per_query + 1024) return p;  // not even one query fits
+        chunk = std::min<int64_t>(nq, (int64_t)((ws_bytes - 1024) / per_query));
+    }
     if (chunk <= 0) return p;
     p.chunk = chunk;
     size_t off = 0;
@@ -341,7 +344,15 @@ static RealPlan make_real_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R,
     p.off_keys = take((size_t)chunk * p.key_stride * 4);
     if (!p.smem_sort) { p.off_a = take((size_t)chunk * R * 8); p.off_b = take((size_t)chunk * R * 8); }
     p.total = off;
-    p.ok = true;
+    while (ws_bytes && p.total > ws_bytes && chunk > 1) {  // 256-byte rounding of the sub-buffers: shrink until it fits
+        --chunk;
+        p.chunk = chunk;
+        off = 0;
+        p.off_keys = take((size_t)chunk * p.key_stride * 4);
+        if (!p.smem_sort) { p.off_a = take((size_t)chunk * R * 8); p.off_b = take((size_t)chunk * R * 8); }
+        p.total = off;
+    }
+    p.ok = !(ws_bytes && p.total > ws_bytes);
     return p;
 }
 
