@@ -7,11 +7,14 @@
 // (A columns hold 2 T_q - b split over two int8 values, B columns hold 1), so the accumulator's SIGN is the answer
 // and the epilogue never subtracts:
 //
-//   per CTA: 256 queries (two 128-row A operands + their threshold columns, loaded once by TMA) x one database split
-//   warp 0      TMA producer: per 128-row database tile the int8 tile (B operand, swizzled) and the packed rows
-//               (code + label words, for the rare path) into a ring of stages
-//   warp 1      TMEM allocator (256 columns = 2 query halves x 128; two CTAs share an SM) and MMA issuer
-//   warps 2..9  epilogue: thread <-> query (TMEM lane).  tcgen05.ld ... .pack::16b brings two accumulators per
+//   per CTA: 256 queries (two 128-row A operands + their threshold columns, loaded once by TMA) x a PAIR of adjacent
+//            database splits (a 128-row B tile = 64 rows of each split, so every bin keeps one writer)
+//   warp 0      TMA producer: per tile the int8 rows (B operand, swizzled) and the packed rows (code + label words,
+//               for the rare path) of both splits into a ring of stages
+//   warp 1      TMEM allocator (256 columns = 2 query halves x 128; two CTAs share an SM) and MMA issuer; the two
+//               query halves hand their accumulators back and forth independently
+//   warps 2..17 epilogue: thread <-> query (TMEM lane), warp <-> (32 queries, one split = 64 accumulator columns).
+//               tcgen05.ld ... .pack::16b brings two accumulators per
 //               register (|ip'| <= 384 fits 16 bits); one PRMT with sign replication turns two registers into four
 //               0x00/0xFF bytes, one LOP3 drops them into the hit mask: 0.5 integer op per pair.  The accumulator is
 //               then handed back to the MMA warp and the ~R/Ndb hits of the tile are walked in row order: distance
