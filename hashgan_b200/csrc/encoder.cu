@@ -271,46 +271,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
     }
 }
 
-// ---- tensor-core convolution (opt-in, HG_ENC_CONV_TF32): explicit im2col + the tcgen05 TF32 GEMM -------------------
-// A[m, k] with m = (n, oy, ox) and k = (ky, kx, ci) of one channel group, rows padded with zeros to Kpad (multiple of 32)
-// One warp per output row; the (tap, channel-chunk) decomposition of every float4 column is tabulated once per CTA in
-// shared memory, so the inner loop is table lookup + bounds test + one 16-byte load + one 16-byte store.
-__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ in, int N, int H, int W, int C, int c0, int Cg, int KH, int KW,
-                                                      int stride, int pad, int Ho, int Wo, int Kpad, float* __restrict__ out)
-{
-    extern __shared__ int2 tab[];  // per float4 column: {input offset (floats) relative to the window origin, ky | kx << 16}; x = -1: zero padding
-    const int K = KH * KW * Cg;
-    const int k4n = Kpad / 4;
-    for (int j = threadIdx.x; j < k4n; j += blockDim.x) {
-        const int k = j * 4;
-        if (k < K) {
-            const int ci = k % Cg, kx = (k / Cg) % KW, ky = k / (Cg * KW);
-            tab[j] = make_int2((ky * W + kx) * C + ci, ky | (kx << 16));
-        } else {
-            tab[j] = make_int2(-1, 0);
-        }
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t M = (int64_t)N * Ho * Wo;
-    for (int64_t m = (int64_t)blockIdx.x * 8 + warp; m < M; m += (int64_t)gridDim.x * 8) {
-        const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho);
-        const int64_t n = m / ((int64_t)Wo * Ho);
-        const int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
-        const float* src = in + ((n * H + iy0) * W + ix0) * C + c0;
-        float4* dst = reinterpret_cast<float4*>(out + m * Kpad);
-        for (int j = lane; j < k4n; j += 32) {
-            const int2 t = tab[j];
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t.x >= 0) {
-                const int iy = iy0 + (t.y & 0xffff), ix = ix0 + (t.y >> 16);
-                if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float4*>(src + t.x));
-            }
-            dst[j] = v;
-        }
-    }
-}
-
+// ---- tensor-core convolution: implicit GEMM (gemm_tf32.cu) -------------------------------------------------------------
 // HWIO weights [KH*KW*Cg, Cout] -> per group K-major [groups][Cog][Kpad] (zero padded) for the GEMM's B operand
 // (input channels per group are padded from Cg to Cgp -- conv1: 3 -> 4 -- so that every tap is a whole number of float4)
 __global__ void __launch_bounds__(256) conv_weight_pack_kernel(const float* __restrict__ w, int taps, int Cg, int Cgp, int Cout, int Kpad,
@@ -360,38 +321,20 @@ static int conv_kpad(int KH, int KW, int Cg) { return (int)round_up((int64_t)KH 
 
 int conv_gemm_tf32(const float* in, const float* wt, const float* wt_lo, const float* bias, float* out, int64_t M, int H, int W, int C, int c0,
                    int Cg, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, int Cog, int ldc, cudaStream_t st, int relu = 1);  // gemm_tf32.cu
-static bool env_flag_implicit()
-{
-    const char* v = getenv("HG_CONV_IM2COL");  // =1: the earlier explicit im2col + GEMM pair (kept for comparison)
-    return !(v && v[0] == '1');
-}
-
-// convolution on the tensor cores: implicit GEMM (default) or per group im2col -> gemm_tf32, (+bias, ReLU) straight into the NHWC output
-static int launch_conv_tf32(const float* in, const float* wt, const float* bias, float* out, float* col, int N, int H, int W, int C, int KH, int KW,
-                            int stride, int pad, int Cout, int groups, bool x3, cudaStream_t st)
+// convolution on the tensor cores: one implicit GEMM per channel group (+bias, ReLU) straight into the NHWC output;
+// x3 = error-compensated TF32 (weights pre-split by hg_conv_weight_pack: [hi | lo])
+static int launch_conv_tf32(const float* in, const float* wt, const float* bias, float* out, int N, int H, int W, int C, int KH, int KW, int stride,
+                            int pad, int Cout, int groups, bool x3, cudaStream_t st)
 {
     const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
     const int Cg = C / groups, Cog = Cout / groups;  // C is the stored (padded) channel count: conv1 reads 4-channel crops
     const int Kpad = conv_kpad(KH, KW, Cg);
     const int64_t M = (int64_t)N * Ho * Wo;
     if (M >= (int64_t(1) << 31)) return fail(HG_EINVAL, "conv_tf32: batch too large");
-    if ((Cg % 4) || (C % 4) || (reinterpret_cast<uintptr_t>(in) & 15)) return fail(HG_EINVAL, "conv_tf32: channels must be a multiple of 4");
-    if (x3 || env_flag_implicit()) {  // implicit GEMM: the A tiles are gathered inside the GEMM kernel, no im2col matrix
-        const float* wt_lo = x3 ? wt + (size_t)Cout * Kpad : nullptr;  // hg_conv_weight_pack: [hi | lo]
-        for (int g = 0; g < groups; ++g) {
-            int rc = conv_gemm_tf32(in, wt + (size_t)g * Cog * Kpad, wt_lo ? wt_lo + (size_t)g * Cog * Kpad : nullptr, bias + g * Cog, out + g * Cog, M, H,
-                                    W, C, g * Cg, Cg, KH, KW, stride, pad, Ho, Wo, Kpad, Cog, Cout, st);
-            if (rc != HG_OK) return rc;
-        }
-        return HG_OK;
-    }
-    const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
+    const float* wt_lo = x3 ? wt + (size_t)Cout * Kpad : nullptr;
     for (int g = 0; g < groups; ++g) {
-        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, 8), (int64_t)sms * 32);
-        im2col_kernel<<<grid, 256, sizeof(int2) * (Kpad / 4), st>>>(in, N, H, W, C, g * Cg, Cg, KH, KW, stride, pad, Ho, Wo, Kpad, col);
-        count_launch();
-        HG_CUDA_TRY(cudaGetLastError());
-        int rc = gemm_tf32(col, Kpad, wt + (size_t)g * Cog * Kpad, Kpad, bias + g * Cog, out + g * Cog, Cout, (int)M, Cog, Kpad, 1, st);
+        int rc = conv_gemm_tf32(in, wt + (size_t)g * Cog * Kpad, wt_lo ? wt_lo + (size_t)g * Cog * Kpad : nullptr, bias + g * Cog, out + g * Cog, M, H, W,
+                                C, g * Cg, Cg, KH, KW, stride, pad, Ho, Wo, Kpad, Cog, Cout, st);
         if (rc != HG_OK) return rc;
     }
     return HG_OK;
@@ -403,13 +346,12 @@ static size_t buf_bytes(int n) { return (((size_t)n * 10 * 55 * 55 * 96 * sizeof
 
 }  // namespace hg
 
-// im2col buffer of the tensor-core convolution: the largest A matrix, conv1's [10n*55*55, 512] (11 x 11 taps x 4 channels = 484, padded to 512)
-namespace hg { static size_t col_bytes(int n) { return (((size_t)n * 10 * 55 * 55 * 512 * sizeof(float)) + 255) & ~size_t(255); } }
 
 extern "C" size_t hg_alexnet_workspace_bytes(int n, unsigned flags)
 {
     if (n <= 0) return 0;
-    return 2 * hg::buf_bytes(n) + ((flags & HG_ENC_CONV_TF32) ? hg::col_bytes(n) : 0);  // the im2col matrix only exists for HG_CONV_IM2COL=1
+    (void)flags;
+    return 2 * hg::buf_bytes(n);
 }
 
 extern "C" int hg_conv_weight_pack(const float* d_w_hwio, int KH, int KW, int Cg, int Cout, int groups, float* d_out, void* stream)
@@ -454,12 +396,11 @@ static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgA
     const bool lrn = (flags & HG_ENC_LRN) != 0;
     float* A = static_cast<float*>(d_workspace);
     float* B = reinterpret_cast<float*>(static_cast<char*>(d_workspace) + buf_bytes(n));
-    float* col = reinterpret_cast<float*>(static_cast<char*>(d_workspace) + 2 * buf_bytes(n));
     const int N = 10 * n;
     int rc;
     // one convolution layer: fp32 on the CUDA cores (default, parity with the fp32 oracle to ~1e-5) or TF32 on tcgen05
     auto conv = [&](int i, const float* src, float* dst, int H, int C, int KH, int stride, int pad, int Cout, int groups) -> int {
-        return tc ? launch_conv_tf32(src, w->conv_wt[i], w->conv_b[i], dst, col, N, H, H, (C + 3) & ~3, KH, KH, stride, pad, Cout, groups, x3, st)
+        return tc ? launch_conv_tf32(src, w->conv_wt[i], w->conv_b[i], dst, N, H, H, (C + 3) & ~3, KH, KH, stride, pad, Cout, groups, x3, st)
                   : launch_conv(src, w->conv_w[i], w->conv_b[i], dst, N, H, H, C, KH, KH, stride, pad, Cout, groups, st);
     };
     // crops -> A
