@@ -163,6 +163,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload == "C3":
+        raise SystemExit("C3 is the encoder config (a parity-test case, not a bench line): run scripts/encoder_probe.py 128 [tf32x3|tf32|fp32] "
+                         "or python main.py --cfg config/cifar_evaluation_synthetic.yaml --gpus 0")
     if args.impl == "reference":
         return run_reference(args)
 
