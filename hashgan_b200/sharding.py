@@ -3,8 +3,9 @@ CUDA_VISIBLE_DEVICES), so this layer is new.
 
 One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch; gloo on CPU for the tests):
   1. the database is row-sharded: rank g holds rows [start_g, start_g + n_g) and packs them locally;
-  2. ONE all-gather of the packed rows (code words + label words in one tensor) -- rank order is the
-     global database row order, which preserves the (distance, row) tie rule;
+  2. ONE exchange of the packed rows (code words + label words in one tensor) -- rank order is the global database
+     row order, which preserves the (distance, row) tie rule.  On CUDA the exchange is fused into the pack kernel
+     (SymmetricRows: peer-memory stores into every rank's buffer + one barrier); otherwise one all-gather;
   3. queries are row-sharded: each rank ranks its own queries against the full packed database;
   4. the per-query APs are all-gathered so every rank computes the same mean in the same order
      (lib/metric.py:24).
