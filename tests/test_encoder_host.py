@@ -1,0 +1,41 @@
+"""Host-side pieces of the encoder that need no GPU: the counter-based generator of the stochastic mode (it must stay
+bit-identical to hg_mix in csrc/encoder.cu -- the GPU test feeds its draws to the oracle) and the weight contract."""
+import numpy as np
+import pytest
+
+from hashgan_b200.encoder import CONV_SHAPES, WEIGHT_NAMES, AlexNetWeights, _mix, stochastic_draws
+
+
+def test_generator_known_answers():
+    # seed 0 is the published splitmix64 sequence: 0xE220A8397B1DCDAF, 0x6E789E6AA1B965F4, 0x06C45D188009454F
+    assert [int(x) for x in _mix(0, np.arange(3))] == [0xE220A8397B1DCDAF, 0x6E789E6AA1B965F4, 0x06C45D188009454F]
+    assert [int(x) for x in _mix(12345, np.array([0, 1, 1 << 40]))] == [0x22118258A9D111A0, 0x346EDCE5F713F8ED, 0x62EC45759FCCD821]
+    noise, keep6, keep7 = stochastic_draws(7, 1, 4)
+    assert np.allclose(noise[0, :2], [0.0029440815560519695, 0.006381911225616932], rtol=0, atol=1e-9)
+    assert keep6[0, :8].astype(int).tolist() == [0, 0, 0, 0, 1, 1, 1, 1]
+    assert keep7[0, :8].astype(int).tolist() == [1, 0, 0, 0, 1, 1, 1, 1]
+
+
+def test_draw_statistics_match_the_reference_distributions():
+    noise, keep6, keep7 = stochastic_draws(99, 8, 32)
+    assert noise.shape == (8, 3072) and keep6.shape == keep7.shape == (80, 4096)
+    assert noise.min() >= 0.0 and noise.max() < 1 / 128                       # tf.random_uniform(0, 1/128), main.py:147
+    assert abs(noise.mean() - 1 / 256) < 1e-4 and abs(noise.var() - (1 / 128) ** 2 / 12) < 1e-7
+    assert abs(keep6.mean() - 0.5) < 5e-3 and abs(keep7.mean() - 0.5) < 5e-3   # keep_prob 0.5, architecture.py:369,377
+    assert abs((keep6 == keep7).mean() - 0.5) < 5e-3                           # the two layers draw independently
+    n2, _, _ = stochastic_draws(100, 8, 32)
+    assert abs(np.corrcoef(noise.ravel(), n2.ravel())[0, 1]) < 0.02            # and so do different seeds
+
+
+def test_weight_contract():
+    w = AlexNetWeights.synthetic(48, seed=0)
+    assert set(w.tensors) == set(WEIGHT_NAMES(48))
+    assert w.tensors["discriminator.conv2.weights"].shape == CONV_SHAPES["conv2"] == (5, 5, 48, 256)
+    assert w.tensors["discriminator.ACGANOutput.W"].shape == (4096, 48)
+    bad = dict(w.tensors)
+    bad["discriminator.fc6.weights"] = np.zeros((4096, 9216), np.float32)
+    with pytest.raises(ValueError, match="expected shape"):
+        AlexNetWeights(bad, 48)
+    del bad["discriminator.fc6.weights"]
+    with pytest.raises(KeyError):
+        AlexNetWeights(bad, 48)
