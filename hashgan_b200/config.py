@@ -171,7 +171,8 @@ _DEFAULTS = {
                                  # within 3e-2 of the fp32 graph, code bits equal where |h| > 0.1)
         "CONV_TF32": False,      # older spelling of CONV: "tf32"
         "TIE_BREAK": "index",    # (distance asc, database row asc) == np.argsort(kind='stable')
-        "NUM_GPUS": 1,           # row-shard database and queries over this many GPUs (torchrun)
+        "NUM_GPUS": 1,           # informational: the GPU count comes from the launcher (torchrun --nproc-per-node N main.py ...);
+                                 # evaluate() shards database and queries by rows over the ranks it finds
         "DETERMINISTIC": True,   # no de-quantisation noise (main.py:147), no eval-time dropout (architecture.py:369,377);
                                  # False = the reference's stochastic eval graph, draws seeded by EVAL.SEED
         "SYNTHETIC": False,      # seeded synthetic images / weights when the data and checkpoints are absent

@@ -20,6 +20,13 @@ def main(cfg):
     from hashgan_b200.encoder import AlexNetHashEncoder, AlexNetWeights
     from hashgan_b200.evaluate import evaluate
 
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world > 1:  # torchrun: one process per GPU, database and queries sharded by rows (EVAL.NUM_GPUS documents the intent)
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     if not cfg.TRAIN.EVALUATE_MODE:
         raise SystemExit("hashgan_b200 implements the evaluation path only: set TRAIN.EVALUATE_MODE: True")
     if cfg.MODEL.D_ARCHITECTURE != "ALEXNET":
@@ -50,7 +57,10 @@ def main(cfg):
     else:
         raise SystemExit("{} / {} not found (set EVAL.SYNTHETIC: True for seeded synthetic images)".format(cfg.DATA.DATA_ROOT, cfg.DATA.LIST_ROOT))
     map_val = evaluate(encoder, dataloader, cfg)
-    print('map_val: {}'.format(map_val))
+    if rank == 0:
+        print('map_val: {}'.format(map_val))
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 

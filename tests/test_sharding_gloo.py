@@ -85,6 +85,78 @@ def test_two_rank_sharded_map_equals_single_process(tmp_path, c_oracle, ndb, nq)
     assert float(outs[0]["val"]) == float(outs[1]["val"])
 
 
+def _eval_cfg(db_size, test_size, batch, b, L, R):
+    from types import SimpleNamespace as NS
+
+    return NS(MODEL=NS(HASH_DIM=b), DATA=NS(DB_SIZE=db_size, TEST_SIZE=test_size, LABEL_DIM=L, MAP_R=R), TRAIN=NS(BATCH_SIZE=batch),
+              EVAL=NS(SEED=3, BINARIZE=True))
+
+
+def _fake_encoder(wh, b):
+    proj = np.random.default_rng(11).normal(size=(3 * wh * wh, b)).astype(np.float32)
+    return lambda image: torch.from_numpy(np.tanh((np.asarray(image, dtype=np.float32) / 255.0 - 0.5) @ proj))
+
+
+def _eval_worker(rank, world, port, sizes, out_dir):
+    sys.path.insert(0, helpers.ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hashgan_b200.dataloader import SyntheticDataloader
+        from hashgan_b200.evaluate import evaluate
+        from hashgan_b200.sharding import ShardedMAPs
+        from oracle import maps_oracle
+
+        db_size, test_size, batch, wh, b, L, R = sizes
+        co = helpers.COracle()
+        W, LW = (b + 31) // 32, (L + 31) // 32
+
+        def pack_rows(out, lab):
+            rows = np.concatenate([maps_oracle.pack_sign_bits(np.asarray(out)), maps_oracle.pack_label_bits(np.asarray(lab))], 1)
+            return torch.from_numpy(np.ascontiguousarray(rows).view(np.int32))
+
+        def rank_fn(q_rows, db_rows, b_, L_, R_):
+            qn, dn = q_rows.numpy().view(np.uint32), db_rows.numpy().view(np.uint32)
+            ap = np.empty(len(qn), dtype=np.float64)
+            qc, ql = np.ascontiguousarray(qn[:, :W]), np.ascontiguousarray(qn[:, W:W + LW])
+            dc, dl_ = np.ascontiguousarray(dn[:, :W]), np.ascontiguousarray(dn[:, W:W + LW])
+            assert co.lib.hgo_hamming_map(qc.ctypes.data, ql.ctypes.data, len(qn), dc.ctypes.data, dl_.ctypes.data, len(dn), b_, L_, R_,
+                                          ap.ctypes.data, None, None, None, 1) == 0
+            return torch.from_numpy(ap)
+
+        loader = SyntheticDataloader(batch, wh, L, {"database": db_size, "test": test_size}, seed=5)
+        val = evaluate(_fake_encoder(wh, b), loader, _eval_cfg(db_size, test_size, batch, b, L, R),
+                       metric=ShardedMAPs(R, pack_rows=pack_rows, rank_fn=rank_fn))
+        np.savez(os.path.join(out_dir, f"eval{rank}.npz"), val=val)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("db_size,test_size,batch", [(203, 37, 16), (64, 16, 16), (50, 40, 32)])
+def test_sharded_evaluate_equals_single_process(tmp_path, c_oracle, db_size, test_size, batch):
+    """evaluate() under a process group: contiguous blocks of batches per rank, `size` truncation on the last block,
+    identical shuffle on every rank -> the single-process value, bit for bit (also with more ranks than batches)."""
+    from types import SimpleNamespace as NS
+    from hashgan_b200.dataloader import SyntheticDataloader
+    from hashgan_b200.evaluate import forward_all
+
+    wh, b, L, R, world = 4, 40, 5, 30, 2
+    port = _free_port()
+    mp.spawn(_eval_worker, args=(world, port, (db_size, test_size, batch, wh, b, L, R), str(tmp_path)), nprocs=world, join=True)
+    cfg = _eval_cfg(db_size, test_size, batch, b, L, R)
+    loader = SyntheticDataloader(batch, wh, L, {"database": db_size, "test": test_size}, seed=5)
+    enc = _fake_encoder(wh, b)
+    np.random.seed(cfg.EVAL.SEED)  # the shuffle the sharded run used
+    db = forward_all(enc, loader.db_gen, db_size, cfg)
+    te = forward_all(enc, loader.test_gen, test_size, cfg)
+    assert db.output.shape == (db_size, b) and te.output.shape == (test_size, b)
+    ref_ap, _, _, _ = c_oracle.hamming_map(NS(output=db.output.numpy(), label=db.label), NS(output=te.output.numpy(), label=te.label), R)
+    want = float(np.mean(ref_ap[~np.isnan(ref_ap)]))
+    vals = [float(np.load(tmp_path / f"eval{r}.npz")["val"]) for r in range(world)]
+    assert vals[0] == vals[1] == want
+
+
 def test_shard_bounds_cover_everything():
     from hashgan_b200.sharding import shard_bounds
 
