@@ -125,3 +125,34 @@ def test_restore_order_of_the_reference(tmp_path):
     tfc.write_checkpoint(prefix, bad)
     with pytest.raises(ValueError, match="checkpoint shape"):
         AlexNetWeights.synthetic(48, seed=1).override_from_tf_checkpoint(prefix)
+
+
+def test_round_trip_property(tmp_path):
+    """Randomised round trips (hypothesis): arbitrary variable names (prefix compression, restart points, multi-block
+    index), ranks 0..4, every supported dtype."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    dtypes = [np.float32, np.float64, np.int32, np.int64, np.uint8, np.int8, np.int16, np.float16, np.bool_]
+    names = st.text(alphabet="abcdefghij./_0123456789", min_size=1, max_size=24)
+    shapes = st.lists(st.integers(0, 5), min_size=0, max_size=4)
+    counter = [0]
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.dictionaries(names, st.tuples(st.sampled_from(range(len(dtypes))), shapes, st.integers(0, 2 ** 31)), min_size=1, max_size=20),
+           st.integers(1, 7))
+    def run(spec, per_block):
+        tensors = {}
+        for name, (di, shape, seed) in spec.items():
+            rng = np.random.default_rng(seed)
+            a = (rng.normal(size=shape) * 100).astype(dtypes[di]) if dtypes[di] is not np.bool_ else rng.random(shape) < 0.5
+            tensors[name] = np.asarray(a)
+        counter[0] += 1
+        prefix = str(tmp_path / f"p{counter[0]}.ckpt")
+        tfc.write_checkpoint(prefix, tensors, entries_per_block=per_block)
+        got = tfc.read_checkpoint(prefix)
+        assert set(got) == set(tensors)
+        for k, a in tensors.items():
+            assert got[k].dtype == a.dtype and got[k].shape == a.shape and np.array_equal(got[k], a)
+        assert {k: v[1] for k, v in tfc.list_variables(prefix).items()} == {k: tuple(a.shape) for k, a in tensors.items()}
+
+    run()
