@@ -39,3 +39,31 @@ def test_weight_contract():
     del bad["discriminator.fc6.weights"]
     with pytest.raises(KeyError):
         AlexNetWeights(bad, 48)
+
+
+def test_alexnet_npy_import_follows_the_reference_dict_layout(tmp_path):
+    """lib/architecture.py:199: net_data = np.load(path, encoding='latin1').item(); net_data[layer][0|1] = weights | biases
+    for conv1-5, fc6, fc7 (fc8 is replaced by the hash layer, lib/ops.py `linear` initialisation)."""
+    rng = np.random.default_rng(2)
+    net = {}
+    for layer, shape in list(CONV_SHAPES.items()) + [("fc6", (9216, 4096)), ("fc7", (4096, 4096))]:
+        if layer.startswith("fc"):
+            shape = (shape[0] // 64, shape[1] // 64)  # keep the fixture small; shapes are validated below with full-size arrays
+        net[layer] = [rng.standard_normal(shape).astype(np.float32), rng.standard_normal(shape[-1]).astype(np.float32)]
+    net["fc8"] = [np.zeros((4, 1000), np.float32), np.zeros(1000, np.float32)]  # present in bvlc_alexnet.npy, unused by the hash head
+    path = str(tmp_path / "reference_pretrain.npy")
+    np.save(path, np.array(net, dtype=object), allow_pickle=True)
+    with pytest.raises(ValueError, match="fc6"):          # the reduced fc fixture must be rejected: shapes are part of the contract
+        AlexNetWeights.from_alexnet_npy(path, 64)
+    net["fc6"] = [np.zeros((9216, 4096), np.float32), np.ones(4096, np.float32)]
+    net["fc7"] = [np.zeros((4096, 4096), np.float32), np.ones(4096, np.float32)]
+    np.save(path, np.array(net, dtype=object), allow_pickle=True)
+    w = AlexNetWeights.from_alexnet_npy(path, 64, seed=3)
+    for layer in CONV_SHAPES:
+        assert np.array_equal(w.tensors[f"discriminator.{layer}.weights"], net[layer][0])
+        assert np.array_equal(w.tensors[f"discriminator.{layer}.biases"], net[layer][1])
+    assert np.array_equal(w.tensors["discriminator.fc7.biases"], np.ones(4096, np.float32))
+    W8 = w.tensors["discriminator.ACGANOutput.W"]
+    lim = np.sqrt(2.0 / (4096 + 64)) * np.sqrt(3.0)                      # Glorot uniform, lib/ops.py:213-218
+    assert W8.shape == (4096, 64) and np.abs(W8).max() <= lim and W8.std() > 0.4 * lim
+    assert not w.tensors["discriminator.ACGANOutput.b"].any()
