@@ -190,11 +190,13 @@ def get_default_config() -> CfgNode:
 config = get_default_config()
 
 
-def update_and_inference_config(cfg_file, cfg: CfgNode | None = None, make_dirs: bool = True) -> CfgNode:
+def update_and_inference_config(cfg_file, cfg: CfgNode | None = None, make_dirs: bool = True, opts=None) -> CfgNode:
     """lib/config.py:55-68.  With cfg=None it updates and returns the module-level `config` like the
-    reference does."""
+    reference does.  `opts` (additive): KEY VALUE pairs merged AFTER the yaml file, i.e. command-line overrides win."""
     c = config if cfg is None else cfg
     c.merge_from_file(cfg_file)
+    if opts:
+        c.merge_from_list(list(opts))
     c.DATA.IMAGE_DIR = os.path.join(c.DATA.OUTPUT_DIR, "images")
     c.DATA.MODEL_DIR = os.path.join(c.DATA.OUTPUT_DIR, "models")
     c.DATA.LOG_DIR = os.path.join(c.DATA.OUTPUT_DIR, "logs")

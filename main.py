@@ -75,9 +75,7 @@ if __name__ == "__main__":
 
     from hashgan_b200.config import config, update_and_inference_config
 
-    if args.opts:
-        config.merge_from_list(args.opts)
-    config = update_and_inference_config(args.cfg)
+    config = update_and_inference_config(args.cfg, opts=args.opts)  # KEY VALUE overrides are merged after the yaml file
     pprint(config)
     with open(os.path.join(config.DATA.OUTPUT_DIR, 'config.txt'), 'w') as fh:
         pprint(config, fh)

@@ -112,3 +112,15 @@ def test_every_reference_yaml_loads_and_defaults_match(tmp_path):
         assert c[node][key] == want and type(c[node][key]) is type(want), (node, key)
         checked += 1
     assert checked >= 35
+
+
+def test_command_line_overrides_win_over_the_yaml(tmp_path):
+    """main.py's trailing KEY VALUE pairs are merged after the yaml file (derived keys follow them)."""
+    from hashgan_b200.config import get_default_config, update_and_inference_config
+
+    y = tmp_path / "c.yaml"
+    y.write_text("DATA:\n    DB_SIZE: 5400\n    WIDTH_HEIGHT: 32\n    OUTPUT_DIR: '%s'\n" % (tmp_path / "out"))
+    c = update_and_inference_config(str(y), get_default_config(), opts=["DATA.DB_SIZE", "54000", "DATA.WIDTH_HEIGHT", "64"])
+    assert c.DATA.DB_SIZE == 54000 and c.DATA.WIDTH_HEIGHT == 64 and c.DATA.OUTPUT_DIM == 3 * 64 * 64
+    c2 = update_and_inference_config(str(y), get_default_config())
+    assert c2.DATA.DB_SIZE == 5400 and c2.DATA.OUTPUT_DIM == 3 * 32 * 32
