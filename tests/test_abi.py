@@ -67,3 +67,27 @@ def test_mean_matches_numpy_bitwise():
             assert np.isnan(out.value)
         else:
             assert out.value == float(np.mean(kept)), n
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/hashgan_b200.h must be usable from C (the drop-in boundary is a C ABI): compile a C99 translation unit that
+    includes it with -pedantic, link it against libhashgan_b200.so and call a host-only entry point."""
+    import shutil
+    import subprocess
+
+    from hashgan_b200 import _native
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "hashgan_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '    if (hg_code_words(64) != 2 || hg_label_words(81) != 3 || hg_row_words(64, 10) != 4 || hg_row_words(64, 81) != 8) return 1;\n'
+                   '    if (hg_crc32c("123456789", 9, 0) != 0xE3069283u) return 2;\n'
+                   '    printf("%d\\n", hg_version());\n    return 0;\n}\n')
+    exe = tmp_path / "abi"
+    lib_dir = os.path.dirname(_native.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(helpers.ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", lib_dir, "-lhashgan_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip()
+    assert int(out) >= 100
