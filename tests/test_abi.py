@@ -91,3 +91,24 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
                     "-L", lib_dir, "-lhashgan_b200", f"-Wl,-rpath,{lib_dir}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip()
     assert int(out) >= 100
+
+
+def test_row_layout_rules():
+    """hg_row_words: rows hold the code and label words, code words stay vector-loadable, and every 33..128-bit hash length
+    gets 16- or 32-byte rows (what the tensor-core select stages by TMA) for every supported label width."""
+    lib = _native.lib()
+    for b in list(range(1, 257)):
+        W = lib.hg_code_words(b)
+        assert W == ((b + 31) // 32 if b <= 128 else 8)
+        for L in (1, 10, 32, 33, 64, 65, 81, 96, 128):
+            LW, Wr = lib.hg_label_words(L), lib.hg_row_words(b, L)
+            assert LW == (L + 31) // 32 and Wr >= W + LW
+            if W == 2:
+                assert Wr % 2 == 0
+            if W in (4, 8):
+                assert Wr % 4 == 0
+            if 32 < b <= 128:
+                assert Wr in (4, 8) and lib.hg_select_backend(b, L) in (64, 128)
+            else:
+                assert lib.hg_select_backend(b, L) == 0
+    assert lib.hg_code_words(0) == 0 and lib.hg_code_words(257) == 0 and lib.hg_label_words(129) == 0 and lib.hg_row_words(64, 0) == 0
