@@ -107,14 +107,21 @@ class AlexNetWeights:
         return cls(t, hash_dim)
 
 
-    def override_from_tf_checkpoint(self, prefix: str, verify: bool = True) -> list:
+    def override_from_tf_checkpoint(self, prefix: str, verify: bool = True, allow_partial: bool = False) -> list:
         """The reference's restore order (main.py:187-195): variables first take their .npy / initial values
         (lib/architecture.py:199), then `Saver.restore(session, D_PRETRAINED_MODEL_PATH)` overwrites every discriminator
-        variable the checkpoint holds.  Returns the names that were overridden; a checkpoint tensor whose shape does not
-        match the graph raises, as the restore op does."""
+        variable.  tf.train.Saver.restore raises NotFoundError when the checkpoint lacks a variable of the graph, so a
+        checkpoint that misses (or renames) any of WEIGHT_NAMES(hash_dim) raises KeyError here as well -- it must not be
+        evaluated with the initial values of that tensor.  `allow_partial=True` (tests, fine-tuning experiments) restores the
+        intersection instead.  Returns the names that were overridden; a checkpoint tensor whose shape does not match the
+        graph raises, as the restore op does."""
         from . import tf_checkpoint
 
         have = tf_checkpoint.list_variables(prefix)
+        missing = [n for n in self.tensors if n not in have]
+        if missing and not allow_partial:
+            raise KeyError(f"checkpoint {prefix} lacks {len(missing)} variable(s) of the evaluation graph: {missing} "
+                           "(tf.train.Saver.restore fails the same way, main.py:193); pass allow_partial=True to restore the rest")
         names = [n for n in self.tensors if n in have]
         for name, a in tf_checkpoint.read_checkpoint(prefix, names, verify=verify).items():
             if tuple(a.shape) != tuple(self.tensors[name].shape):

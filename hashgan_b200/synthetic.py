@@ -1,19 +1,25 @@
 """Seeded synthetic inputs of the shapes BASELINE.json names.
 
-Codes are uniform random {-1,+1} float32 (or class-correlated), labels follow the statistics of the
-reference's list files (data_list/cifar10: exactly balanced 10-way one-hot; data_list/nuswide_81:
-81-way multi-label, mean 2.43 labels per image, top class frequencies .36/.26/.23/.17/.17).  Nothing
-here reads /root/reference; the NUS-WIDE class frequencies below are summary statistics measured from
-data_list/nuswide_81/database.txt during the survey.
+Codes are uniform random {-1,+1} float32 (or class-correlated).  Labels:
+  C1      the REAL label rows of the reference's data_list/cifar10/{database,test}.txt (10-way one-hot, exactly balanced);
+  C5      bootstrap (seeded, with replacement) of the REAL rows of data_list/nuswide_81/database.txt (168,692 rows, 81-way
+          multi-label, mean 2.43 labels per image) and the rows of test.txt for the queries -- label co-occurrence is kept;
+  C2, C4  one-hot draws from the generator, as the survey specifies.
+Nothing here reads /root/reference: the label matrices ship bit-packed in hashgan_b200/data/label_rows.npz (made by
+oracle/gen_label_rows.py in the build container).  `multi_hot_labels` (independent per-class rates measured from the same
+list) remains for label widths other than 81 and for the synthetic image loader.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
+from functools import lru_cache
 from types import SimpleNamespace
 
 import numpy as np
 
-__all__ = ["Workload", "WORKLOADS", "make_workload", "pm1_codes", "one_hot_labels", "multi_hot_labels", "proto_codes"]
+__all__ = ["Workload", "WORKLOADS", "make_workload", "pm1_codes", "one_hot_labels", "multi_hot_labels", "proto_codes",
+           "real_label_rows", "list_labels"]
 
 
 @dataclass(frozen=True)
@@ -24,15 +30,15 @@ class Workload:
     b: int
     L: int
     R: int
-    labels: str  # "onehot" | "nuswide"
+    labels: str  # "onehot" (generator) | "cifar10" (real rows) | "nuswide" (bootstrap of the real rows)
     seed: int
     note: str = ""
 
 
 # C1..C5 of SURVEY.md section 8 (C3 is the encoder workload and lives in hashgan_b200.encoder)
 WORKLOADS = {
-    "C1": Workload("C1", 1000, 54000, 32, 10, 54000, "onehot", 1, "cifar_evaluation.yaml shape, MODEL.HASH_DIM=32, MAP_R=DB_SIZE"),
-    "C1_64": Workload("C1_64", 1000, 54000, 64, 10, 54000, "onehot", 11, "cifar_evaluation.yaml as shipped (HASH_DIM default 64)"),
+    "C1": Workload("C1", 1000, 54000, 32, 10, 54000, "cifar10", 1, "cifar_evaluation.yaml shape, MODEL.HASH_DIM=32, MAP_R=DB_SIZE"),
+    "C1_64": Workload("C1_64", 1000, 54000, 64, 10, 54000, "cifar10", 11, "cifar_evaluation.yaml as shipped (HASH_DIM default 64)"),
     "C2": Workload("C2", 10000, 100000, 48, 10, 5000, "onehot", 2, "48-bit codes: 2 words with 16 zero pad bits"),
     "C4": Workload("C4", 10000, 1000000, 64, 10, 5000, "onehot", 4, "headline: 10k queries x 1M database, 64-bit, mAP@5000"),
     "C5": Workload("C5", 5000, 2000000, 128, 81, 5000, "nuswide", 5, "NUS-WIDE_81-shaped multi-label, 128-bit"),
@@ -80,6 +86,25 @@ def multi_hot_labels(rng: np.random.Generator, n: int, L: int = 81) -> np.ndarra
     return lab
 
 
+@lru_cache(maxsize=None)
+def real_label_rows(dataset: str, split: str) -> np.ndarray:
+    """Label matrix [n, L] (int64 0/1) of the reference's list file data_list/<dataset>/<split>.txt, from the committed
+    bit-packed copy (oracle/gen_label_rows.py)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "label_rows.npz")
+    with np.load(path) as z:
+        bits, L = z[f"{dataset}/{split}_bits"], int(z[f"{dataset}/{split}_L"])
+    return np.unpackbits(bits, axis=1)[:, :L].astype(np.int64)
+
+
+def list_labels(rng: np.random.Generator, dataset: str, split: str, n: int) -> np.ndarray:
+    """n label rows of a reference list: the rows themselves (in list order) while n fits, else a seeded bootstrap with
+    replacement (C5's 2M database rows are resampled from the 168,692 real ones)."""
+    rows = real_label_rows(dataset, split)
+    if n <= rows.shape[0]:
+        return rows[:n].copy()
+    return rows[rng.integers(0, rows.shape[0], n)]
+
+
 def proto_codes(rng: np.random.Generator, lab: np.ndarray, b: int, flip: float, proto: np.ndarray | None = None):
     """Class-correlated codes: prototype of the (first) class with i.i.d. bit flips; returns (codes, proto)."""
     L = lab.shape[1]
@@ -103,6 +128,12 @@ def make_workload(name_or_wl, *, nq: int | None = None, ndb: int | None = None, 
     if wl.labels == "onehot":
         db_lab = one_hot_labels(r_db_l, ndb, wl.L)
         q_lab = one_hot_labels(r_q_l, nq, wl.L)
+    elif wl.labels == "cifar10" and wl.L == 10:
+        db_lab = list_labels(r_db_l, "cifar10", "database", ndb)
+        q_lab = list_labels(r_q_l, "cifar10", "test", nq)
+    elif wl.labels == "nuswide" and wl.L == 81:
+        db_lab = list_labels(r_db_l, "nuswide_81", "database", ndb)
+        q_lab = list_labels(r_q_l, "nuswide_81", "test", nq)
     else:
         db_lab = multi_hot_labels(r_db_l, ndb, wl.L)
         q_lab = multi_hot_labels(r_q_l, nq, wl.L)

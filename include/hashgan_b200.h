@@ -133,6 +133,11 @@ int64_t hg_launch_count(int reset);
  * D2H copy of d_ap (synchronises `stream`).  *map_out = NaN when every query was skipped. */
 int hg_mean_ap(const double* d_ap, int64_t nq, double* map_out, int64_t* n_used, void* stream);
 
+/* Host-only half of hg_mean_ap: lib/metric.py:24 (`np.mean(np.array(apx))`) on a HOST vector of per-query APs --
+ * NaN entries are the queries the reference skips (lib/metric.py:22-23), the kept ones are summed with NumPy's
+ * pairwise scheme so the result is bit-identical to np.mean.  Needs no GPU (tests/test_abi.py pins it against NumPy). */
+int hg_mean_ap_host(const double* h_ap, int64_t nq, double* map_out, int64_t* n_used);
+
 /* End-to-end convenience with HOST buffers == MAPs(R).get_maps_by_feature(database, query)
  * (lib/metric.py:12-24, call site main.py:164).  Copies features/labels H2D (pinned staging, chunked and
  * overlapped with packing), ranks, copies the per-query AP back.  Device memory is taken from a cached

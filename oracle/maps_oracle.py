@@ -6,8 +6,8 @@ legs may import this module.  The product path (hashgan_b200.metric) never does.
 This is a NumPy restatement of the reference's metric, thuml/HashGAN
 ``lib/metric.py:12-24`` (``MAPs.get_maps_by_feature``).  Parity is PINNED: the
 restatement is checked against (a) the unmodified reference imported from
-/root/reference in the build container (tests/test_oracle_vs_reference.py, skipped
-where the reference is not mounted) and (b) golden vectors generated from the
+/root/reference in the build container (tests/test_oracle.py::test_restatement_equals_unmodified_reference,
+skipped where the reference is not mounted) and (b) golden vectors generated from the
 unmodified reference by oracle/gen_golden.py and committed under tests/golden/.
 
 Reference line map

@@ -26,6 +26,21 @@ def test_library_exports_every_declared_symbol():
         assert name in _native.SIGNATURES, f"{name} has no ctypes signature in hashgan_b200/_native.py"
 
 
+def test_header_declares_every_exported_symbol():
+    """The other direction: nothing is exported (and nothing is bound in _native.py) that include/hashgan_b200.h does not declare."""
+    import shutil
+    import subprocess
+
+    declared = set(_declared_symbols())
+    assert set(_native.SIGNATURES) <= declared, sorted(set(_native.SIGNATURES) - declared)
+    if shutil.which("nm") is None:
+        pytest.skip("nm not available")
+    out = subprocess.run(["nm", "-D", "--defined-only", _native.LIB_PATH], check=True, capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-1].startswith("hg_")}
+    assert exported, "no hg_* symbols exported"
+    assert exported <= declared, f"exported but not declared in the header: {sorted(exported - declared)}"
+
+
 def test_version_and_word_counts():
     lib = _native.lib()
     assert lib.hg_version() >= 100

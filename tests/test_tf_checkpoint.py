@@ -115,12 +115,21 @@ def test_restore_order_of_the_reference(tmp_path):
     ck["discriminator.conv1.weights/Adam"] = np.zeros((11, 11, 3, 96), np.float32)
     prefix = str(tmp_path / "D_1.ckpt")
     tfc.write_checkpoint(prefix, ck)
-    names = base.override_from_tf_checkpoint(prefix)
+    # fc6 / fc7 are missing: tf.train.Saver.restore (main.py:193) raises NotFoundError, so must we
+    with pytest.raises(KeyError, match="lacks 4 variable"):
+        AlexNetWeights.synthetic(48, seed=1).override_from_tf_checkpoint(prefix)
+    names = base.override_from_tf_checkpoint(prefix, allow_partial=True)
     assert sorted(names) == sorted(k for k in ck if k in trained.tensors)
     for k in base.tensors:
         src = trained if k in names else AlexNetWeights.synthetic(48, seed=1)
         assert np.array_equal(base.tensors[k], src.tensors[k])
-    bad = dict(ck)
+    full = dict(trained.tensors)
+    full["discriminator.Output.W"] = ck["discriminator.Output.W"]
+    tfc.write_checkpoint(prefix, full)
+    strict = AlexNetWeights.synthetic(48, seed=1)
+    assert sorted(strict.override_from_tf_checkpoint(prefix)) == sorted(trained.tensors)   # complete checkpoint: strict mode passes
+    assert all(np.array_equal(strict.tensors[k], trained.tensors[k]) for k in trained.tensors)
+    bad = dict(full)
     bad["discriminator.ACGANOutput.W"] = np.zeros((4096, 64), np.float32)  # HASH_DIM mismatch
     tfc.write_checkpoint(prefix, bad)
     with pytest.raises(ValueError, match="checkpoint shape"):
