@@ -18,6 +18,7 @@ FLAG_TIMING = 4
 ENC_LRN = 1
 ENC_CONV_TF32 = 2
 ENC_CONV_TF32X3 = 8
+ENC_TIMING = 16
 MAX_BITS = 256
 
 _i64, _int, _u32, _vp, _sz = C.c_int64, C.c_int, C.c_uint, C.c_void_p, C.c_size_t
@@ -53,6 +54,8 @@ SIGNATURES = {
     "hg_alexnet_encode_stochastic": (_int, [_vp, _int, _int, _vp, _int, _u32, _vp, _vp, _sz, C.c_uint64, _vp]),
     "hg_transpose_f32": (_int, [_vp, _int, _int, _vp, _vp]),
     "hg_popc_peak": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), _int, _vp]),
+    "hg_i8_peak": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), _int, _vp]),
+    "hg_alexnet_phase_ms": (_int, [C.POINTER(C.c_float)]),
 }
 
 

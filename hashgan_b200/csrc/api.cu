@@ -323,6 +323,9 @@ extern "C" int hg_maps_by_feature_host(const float* h_db_feat, const void* h_db_
     const size_t o_qr = take(sizeof(uint32_t) * (size_t)nq * Wr);
     const size_t o_ap = take(sizeof(double) * (size_t)nq);
     const size_t o_bad = take(256);
+    const int64_t n_sample = chunks.sample_n_seg * chunks.sample_seg_rows;
+    const size_t o_sf = take(sizeof(float) * (size_t)n_sample * b);
+    const size_t o_sr = take(sizeof(uint32_t) * (size_t)n_sample * Wr);
     const size_t o_ws = take(ws_bytes);
     int rc = hg::arena_reserve(a, off, (size_t)nq + 8);
     if (rc != HG_OK) return rc;
@@ -334,6 +337,12 @@ extern "C" int hg_maps_by_feature_host(const float* h_db_feat, const void* h_db_
     uint32_t* d_qr = reinterpret_cast<uint32_t*>(base + o_qr);
     double* d_ap = reinterpret_cast<double*>(base + o_ap);
     int* d_bad = reinterpret_cast<int*>(base + o_bad);
+    // an error return must not leave copies from the caller's buffers in flight (they may be freed right after the call)
+    struct Drain {
+        hg::Arena& a;
+        bool armed;
+        ~Drain() { if (armed) { cudaStreamSynchronize(a.copy_stream); cudaStreamSynchronize(a.stream); (void)cudaGetLastError(); } }
+    } drain{a, true};
 
     HG_CUDA_TRY(cudaMemsetAsync(d_bad, 0, 256, st));
     HG_CUDA_TRY(cudaMemcpyAsync(d_qf, h_q_feat, sizeof(float) * (size_t)nq * b, cudaMemcpyHostToDevice, st));
@@ -379,6 +388,17 @@ extern "C" int hg_maps_by_feature_host(const float* h_db_feat, const void* h_db_
     }
     // the copy stream must not overtake the previous call's reads of these buffers: both streams were drained by
     // the synchronize at the end of that call
+    if (n_sample > 0) {
+        // threshold sample: the plan's segments, spread over the whole database, gathered by ONE strided copy ahead of the
+        // chunks (C4: 16k rows = 4 MB) and packed (code words only matter: the label pointer is not needed for the estimate)
+        float* d_sf = reinterpret_cast<float*>(base + o_sf);
+        uint32_t* d_sr = reinterpret_cast<uint32_t*>(base + o_sr);
+        const size_t seg_bytes = sizeof(float) * (size_t)chunks.sample_seg_rows * b;
+        HG_CUDA_TRY(cudaMemcpy2DAsync(d_sf, seg_bytes, h_db_feat, sizeof(float) * (size_t)chunks.sample_seg_stride * b, seg_bytes,
+                                      (size_t)chunks.sample_n_seg, cudaMemcpyHostToDevice, st));
+        if ((rc = hg_pack_rows(d_sf, b, nullptr, lab_elem_bytes, n_sample, b, L, d_sr, nullptr, st)) != HG_OK) return rc;
+        pipe.ch.sample_packed = d_sr;
+    }
     if (pipe.pinned)
         for (int k = 0; k < pipe.ch.K; ++k)
             if ((rc = pipe.issue(k)) != HG_OK) return rc;
@@ -388,6 +408,7 @@ extern "C" int hg_maps_by_feature_host(const float* h_db_feat, const void* h_db_
     int* h_bad = reinterpret_cast<int*>(a.pinned_ap + nq);
     HG_CUDA_TRY(cudaMemcpyAsync(h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     HG_CUDA_TRY(cudaStreamSynchronize(st));
+    drain.armed = false;  // every chunk event was waited on by `st`: both streams are idle
     if (*h_bad) return hg::fail(HG_ELABEL, "hg_maps_by_feature_host: labels must be 0/1");
     if (h_ap_out) memcpy(h_ap_out, a.pinned_ap, sizeof(double) * (size_t)nq);
     return hg_mean_ap_host(a.pinned_ap, nq, map_out, nullptr);

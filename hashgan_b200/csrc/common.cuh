@@ -44,6 +44,12 @@ struct MapChunks {
     static constexpr int kMax = 64;
     int K = 0;
     int64_t row_lo[kMax], row_hi[kMax];
+    // threshold sample drawn over the WHOLE database (the caller copies and packs these rows before chunk 0): n_seg
+    // segments of seg_rows rows, segment i = database rows [i * seg_stride, i * seg_stride + seg_rows); 0 = no sample
+    // (the plan ranks the whole database for its estimate, or the exact path was forced)
+    int64_t sample_n_seg = 0, sample_seg_stride = 0;
+    int sample_seg_rows = 0;
+    const uint32_t* sample_packed = nullptr;  // [sample_n_seg * sample_seg_rows, Wr] packed rows, valid on the stream before prepare(0)
 };
 typedef int (*PrepareRowsFn)(void* user, int chunk, int64_t row_lo, int64_t row_hi, cudaStream_t st);
 int plan_chunks(int64_t nq, int64_t ndb, int b, int L, int64_t R, int k_req, MapChunks* out, size_t* ws_bytes);

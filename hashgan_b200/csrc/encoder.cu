@@ -374,10 +374,55 @@ extern "C" int hg_transpose_f32(const float* d_in, int rows, int cols, float* d_
     return HG_OK;
 }
 
+namespace hg {
+// HG_ENC_TIMING: events at the stage boundaries of one encode call; stage k of the call is credited to a category
+struct EncTimer {
+    static constexpr int kMaxMarks = 40;
+    cudaEvent_t ev[kMaxMarks] = {};
+    int cat[kMaxMarks] = {};
+    int n = 0;
+    bool created = false, armed = false;
+    int ensure()
+    {
+        if (!created) {
+            for (int i = 0; i < kMaxMarks; ++i) HG_CUDA_TRY(cudaEventCreate(&ev[i]));
+            created = true;
+        }
+        return HG_OK;
+    }
+    // everything enqueued since the previous mark belongs to category c (first call: c is ignored)
+    void mark(int c, cudaStream_t st)
+    {
+        if (armed && n < kMaxMarks) { cat[n] = c; cudaEventRecord(ev[n], st); ++n; }
+    }
+};
+static EncTimer& enc_timer()
+{
+    static thread_local EncTimer t;
+    return t;
+}
+enum { kEncPrep = 0, kEncConv, kEncPool, kEncDense, kEncTail };
+}  // namespace hg
+
+extern "C" int hg_alexnet_phase_ms(float out[5])
+{
+    hg::EncTimer& t = hg::enc_timer();
+    if (!out || !t.created || !t.armed || t.n < 2) return hg::fail(HG_EINVAL, "hg_alexnet_phase_ms: no timed hg_alexnet_encode call on this thread");
+    HG_CUDA_TRY(cudaEventSynchronize(t.ev[t.n - 1]));
+    for (int i = 0; i < 5; ++i) out[i] = 0.f;
+    for (int i = 1; i < t.n; ++i) {
+        float ms = 0.f;
+        HG_CUDA_TRY(cudaEventElapsedTime(&ms, t.ev[i - 1], t.ev[i]));
+        out[t.cat[i]] += ms;
+    }
+    return HG_OK;
+}
+
 static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgAlexNetWeights* w, int hash_dim, unsigned flags, float* d_out,
                                void* d_workspace, size_t workspace_bytes, void* stream, uint64_t seed)
 {
     using namespace hg;
+    int rc0;
     if (n == 0) return HG_OK;
     if (n < 0 || wh <= 0 || wh > 256) return fail(HG_EINVAL, "hg_alexnet_encode: bad n=%d / wh=%d", n, wh);
     if (hash_dim <= 0 || hash_dim > 256) return fail(HG_EINVAL, "hg_alexnet_encode: unsupported HASH_DIM=%d (1..256)", hash_dim);
@@ -386,13 +431,21 @@ static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgA
     for (int i = 0; i < 5; ++i)
         if (!w->conv_w[i] || !w->conv_b[i]) return fail(HG_EINVAL, "hg_alexnet_encode: conv%d weights missing", i + 1);
     if (!w->fc6_wt || !w->fc6_b || !w->fc7_wt || !w->fc7_b || !w->fc8_wt || !w->fc8_b) return fail(HG_EINVAL, "hg_alexnet_encode: fc weights missing");
-    if (flags & ~(unsigned)(HG_ENC_LRN | HG_ENC_CONV_TF32 | HG_ENC_CONV_TF32X3)) return fail(HG_EINVAL, "hg_alexnet_encode: unknown flag");
+    if (flags & ~(unsigned)(HG_ENC_LRN | HG_ENC_CONV_TF32 | HG_ENC_CONV_TF32X3 | HG_ENC_TIMING)) return fail(HG_EINVAL, "hg_alexnet_encode: unknown flag");
     const bool x3 = (flags & HG_ENC_CONV_TF32X3) != 0;
     const bool tc = x3 || (flags & HG_ENC_CONV_TF32) != 0;
     if (tc)
         for (int i = 0; i < 5; ++i)
             if (!w->conv_wt[i]) return fail(HG_EINVAL, "hg_alexnet_encode: HG_ENC_CONV_TF32 needs conv_wt[%d] (hg_conv_weight_pack)", i);
     cudaStream_t st = (cudaStream_t)stream;
+    EncTimer& tm = enc_timer();
+    tm.armed = false;
+    tm.n = 0;
+    if (flags & HG_ENC_TIMING) {
+        if ((rc0 = tm.ensure()) != HG_OK) return rc0;
+        tm.armed = true;
+    }
+    tm.mark(kEncPrep, st);
     const bool lrn = (flags & HG_ENC_LRN) != 0;
     float* A = static_cast<float*>(d_workspace);
     float* B = reinterpret_cast<float*>(static_cast<char*>(d_workspace) + buf_bytes(n));
@@ -407,8 +460,10 @@ static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgA
     prep_crops_kernel<<<grid_1d((int64_t)N * 227 * 227, 256), 256, 0, st>>>(d_images, n, wh, tc ? 4 : 3, A, seed);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
+    tm.mark(kEncPrep, st);
     // conv1 11x11/4 VALID 3->96 : A -> B [N,55,55,96]
     if ((rc = conv(0, A, B, 227, 3, 11, 4, 0, 96, 1)) != HG_OK) return rc;
+    tm.mark(kEncConv, st);
     // pool1 : B -> A [N,27,27,96]
     maxpool3s2_kernel<<<grid_1d((int64_t)N * 27 * 27 * 96, 256), 256, 0, st>>>(B, N, 55, 55, 96, 27, 27, A);
     count_launch();
@@ -420,8 +475,10 @@ static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgA
         std::swap(cur, other);
     }
     HG_CUDA_TRY(cudaGetLastError());
+    tm.mark(kEncPool, st);
     // conv2 5x5 SAME, 2 groups 48->128 : -> [N,27,27,256]
     if ((rc = conv(1, cur, other, 27, 96, 5, 1, 2, 256, 2)) != HG_OK) return rc;
+    tm.mark(kEncConv, st);
     std::swap(cur, other);
     maxpool3s2_kernel<<<grid_1d((int64_t)N * 13 * 13 * 256, 256), 256, 0, st>>>(cur, N, 27, 27, 256, 13, 13, other);
     count_launch();
@@ -432,17 +489,20 @@ static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgA
         std::swap(cur, other);
     }
     HG_CUDA_TRY(cudaGetLastError());
+    tm.mark(kEncPool, st);
     // conv3 3x3 SAME 256->384, conv4 3x3 SAME 2 groups 192->192, conv5 3x3 SAME 2 groups 192->128
     if ((rc = conv(2, cur, other, 13, 256, 3, 1, 1, 384, 1)) != HG_OK) return rc;
     std::swap(cur, other);
     if ((rc = conv(3, cur, other, 13, 384, 3, 1, 1, 384, 2)) != HG_OK) return rc;
     std::swap(cur, other);
     if ((rc = conv(4, cur, other, 13, 384, 3, 1, 1, 256, 2)) != HG_OK) return rc;
+    tm.mark(kEncConv, st);
     std::swap(cur, other);
     // pool5 -> [N,6,6,256] == [N, 9216] in (h, w, c) order, the row order of the fc6 weights
     maxpool3s2_kernel<<<grid_1d((int64_t)N * 6 * 6 * 256, 256), 256, 0, st>>>(cur, N, 13, 13, 256, 6, 6, other);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
+    tm.mark(kEncPool, st);
     std::swap(cur, other);
     // fc6, fc7 (+ReLU), fc8 on the tensor cores.  In the error-compensated mode a dense layer is the 1x1 "convolution"
     // of the implicit-GEMM kernel (H = W = 1, C = K): its producer warps split the activations into hi/lo on the fly.
@@ -465,9 +525,11 @@ static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgA
     }
     if ((rc = dense(cur, other, w->fc_wt3[2], w->fc8_wt, w->fc8_b, 4096, hash_dim, 0)) != HG_OK) return rc;
     std::swap(cur, other);
+    tm.mark(kEncDense, st);
     tanh_crop_mean_kernel<<<grid_1d((int64_t)n * hash_dim, 256), 256, 0, st>>>(cur, n, hash_dim, d_out);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
+    tm.mark(kEncTail, st);
     return HG_OK;
 }
 

@@ -948,7 +948,8 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
                    const MapChunks* chunks = nullptr, PrepareRowsFn prepare = nullptr, void* user = nullptr)
 {
     // Chunked mode (host pipeline): the database rows of chunk k become valid when prepare(k) has been enqueued
-    // on `st`; thresholds are estimated from a sample of chunk 0, select runs chunk by chunk behind the copies.
+    // on `st`; thresholds are estimated from the caller's sample block (segments spread over the whole database, copied
+    // ahead of chunk 0), select runs chunk by chunk behind the copies.
     int K = (chunks && prepare) ? chunks->K : 1;
     int64_t sample_stride = pl.seg_stride, sample_nseg = pl.n_seg, sample_rows = pl.sample_rows;
     int sample_spc = pl.seg_per_chunk, sample_chunks = pl.n_chunks;
@@ -960,18 +961,21 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
         }
         return HG_OK;
     };
+    const uint32_t* hist_rows = db_rows;   // rows the threshold sample is read from
+    int64_t hist_ndb = pl.ndb;
     if (K > 1) {
-        if (pl.sample_rows >= pl.ndb || (flags & HG_FLAG_FORCE_EXACT)) {
+        if (pl.sample_rows >= pl.ndb || (flags & HG_FLAG_FORCE_EXACT) || !chunks->sample_packed) {
             int prc = prepare_upto(K);  // the estimate needs the whole database: no overlap possible
             if (prc != HG_OK) return prc;
             K = 1;
         } else {
-            const int64_t avail_tiles = (chunks->row_hi[0] - chunks->row_lo[0]) / pl.TILE;  // chunk 0 = whole splits = whole tiles
-            sample_nseg = std::min<int64_t>(pl.n_seg, std::max<int64_t>(1, avail_tiles));
-            sample_stride = std::max<int64_t>(1, avail_tiles / sample_nseg) * pl.TILE;
-            sample_rows = sample_nseg * pl.TILE;
-            sample_spc = (int)ceil_div(sample_nseg, std::max<int64_t>(1, std::min<int64_t>(sample_nseg, pl.n_chunks)));
-            sample_chunks = (int)ceil_div(sample_nseg, sample_spc);
+            // the caller gathered the plan's sample segments (spread over the WHOLE database, lib/dataloader.py:93-94 leaves the
+            // row order to the caller: a class-sorted database must not bias the thresholds) into one contiguous block
+            hist_rows = chunks->sample_packed;
+            hist_ndb = chunks->sample_n_seg * chunks->sample_seg_rows;
+            sample_nseg = chunks->sample_n_seg;
+            sample_stride = chunks->sample_seg_rows;  // contiguous segments
+            sample_rows = hist_ndb;
             int prc = prepare_upto(1);
             if (prc != HG_OK) return prc;
         }
@@ -1013,7 +1017,7 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
         // 1. sampled histogram
         HG_CUDA_TRY(cudaMemsetAsync(hist_s, 0, sizeof(uint32_t) * (size_t)pl.nq * nb, st));
         HistParams hp{};
-        hp.q_rows = q_rows; hp.db_rows = db_rows; hp.nq = pl.nq; hp.ndb = pl.ndb; hp.b = pl.b; hp.Wr = pl.Wr;
+        hp.q_rows = q_rows; hp.db_rows = hist_rows; hp.nq = pl.nq; hp.ndb = hist_ndb; hp.b = pl.b; hp.Wr = pl.Wr;
         hp.n_active = nullptr; hp.qlist = nullptr;
         hp.seg_stride = sample_stride; hp.n_seg = sample_nseg; hp.seg_rows = pl.TILE; hp.seg_per_chunk = sample_spc;
         hp.out = hist_s; hp.out_chunks = 1;
@@ -1154,6 +1158,12 @@ int plan_chunks(int64_t nq, int64_t ndb, int b, int L, int64_t R, int k_req, Map
         ++kk;
     }
     out->K = std::max(1, kk);
+    out->sample_n_seg = 0; out->sample_seg_stride = 0; out->sample_seg_rows = 0; out->sample_packed = nullptr;
+    if (out->K > 1 && pl.sample_rows < pl.ndb) {  // every sampled segment is a full tile (make_plan)
+        out->sample_n_seg = pl.n_seg;
+        out->sample_seg_stride = pl.seg_stride;
+        out->sample_seg_rows = pl.TILE;
+    }
     return HG_OK;
 }
 

@@ -526,4 +526,98 @@ int umma_select_launch(const UmmaSelectArgs& a_in, cudaStream_t st)
     return (a.W == 4 && a.Wr == 8) ? launch_umma<128, 2>(tq, tdb, trows, tqx, tbx, a, st) : launch_umma<128, 0>(tq, tdb, trows, tqx, tbx, a, st);
 }
 
+
+// ---- int8 tcgen05 peak (roofline denominator of the tensor view) -----------------------------------------------------
+// One CTA per SM keeps its operands resident in shared memory (A 128 x 128 B, B 256 x 128 B, SWIZZLE_128B K-major) and one
+// thread issues `iters` x 4 back-to-back tcgen05.mma kind::i8 (M = 128, N = 256, K = 32) alternating between two
+// accumulators in tensor memory: nothing but the tensor pipe is exercised.
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int iters, uint32_t seed, uint32_t* __restrict__ sink)
+{
+    extern __shared__ __align__(1024) uint8_t psm[];
+    const uint32_t base = (smem_u32(psm) + 1023u) & ~1023u;
+    uint8_t* const ptr = psm + (base - smem_u32(psm));
+    __shared__ __align__(8) uint64_t done_bar;
+    __shared__ uint32_t tmem_slot;
+    constexpr uint32_t A_BYTES = 128 * 128, B_BYTES = 256 * 128;
+    for (uint32_t i = threadIdx.x; i < (A_BYTES + B_BYTES) / 4; i += blockDim.x) {
+        uint32_t x = (i + seed) * 2654435761u;
+        x ^= x >> 15;
+        reinterpret_cast<uint32_t*>(ptr)[i] = (x & 0x01010101u) * 0xFEu ^ 0xFFFFFFFFu;  // bytes of +1 / -1
+    }
+    fence_proxy_async();
+    if (threadIdx.x == 0) { mbar_init(&done_bar, 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    if (threadIdx.x == 0) {
+        constexpr uint32_t idesc = umma_idesc_i8(128, 256);
+        const uint64_t adesc = umma_desc_kmajor(base, 128), bdesc = umma_desc_kmajor(base + A_BYTES, 128);
+        for (int it = 0; it < iters; ++it) {
+            const uint32_t acc = tmem + (uint32_t)((it & 1) * 256);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_i8(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)(it > 1 || k != 0));
+        }
+        umma_commit(&done_bar);
+        mbar_wait(&done_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t r[16];
+        tmem_ld_32cols_pack16(tmem, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (sink && r[0] == 0x12345678u && r[5] == 0x9ABCDEFu) sink[blockIdx.x] = r[1];  // keeps the accumulators observable
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+int i8_peak(double* ops_per_s, double* ms_out, int iters, cudaStream_t st)
+{
+    const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
+    if (iters <= 0) iters = 8192;
+    const size_t smem = 128 * 128 + 256 * 128 + 1024;
+    HG_CUDA_TRY(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t* sink = nullptr;
+    HG_CUDA_TRY(cudaMalloc(&sink, sizeof(uint32_t) * sms));
+    cudaEvent_t e0, e1;
+    HG_CUDA_TRY(cudaEventCreate(&e0));
+    HG_CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    count_launch(4);
+    i8_peak_kernel<<<sms, 128, smem, st>>>(iters / 4 + 1, 1u, sink);  // warm-up
+    for (int rep = 0; rep < 3; ++rep) {
+        HG_CUDA_TRY(cudaEventRecord(e0, st));
+        i8_peak_kernel<<<sms, 128, smem, st>>>(iters, 7u + rep, sink);
+        HG_CUDA_TRY(cudaEventRecord(e1, st));
+        HG_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        HG_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    HG_CUDA_TRY(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *ops_per_s = 2.0 * 128.0 * 256.0 * 32.0 * 4.0 * (double)iters * (double)sms / ((double)best * 1e-3);
+    if (ms_out) *ms_out = best;
+    return HG_OK;
+}
+
 }  // namespace hg
+
+extern "C" int hg_i8_peak(double* ops_per_s, double* ms_out, int iters, void* stream)
+{
+    if (!ops_per_s) return hg::fail(HG_EINVAL, "hg_i8_peak: bad arguments");
+    if (!hg::device_facts().ok) return hg::fail(HG_ECUDA, "hg_i8_peak: no CUDA device");
+    return hg::i8_peak(ops_per_s, ms_out, iters, (cudaStream_t)stream);
+}

@@ -50,14 +50,19 @@ class Dataset:
         return np.asarray(imgs), self._label[np.asarray(index)]
 
 
-def _epoch(n_samples, batch_size, fetch):
-    """lib/dataloader.py:90-114"""
+def _epoch(n_samples, batch_size, fetch, batch_range=None):
+    """lib/dataloader.py:90-114.  `batch_range` = (lo, hi) (additive, multi-GPU evaluation): only batches lo <= i < hi of the
+    epoch are fetched and yielded -- the permutation is drawn in full, so every rank sees the same epoch, but a rank never
+    decodes the images of another rank's block."""
     perm = np.arange(n_samples)
     np.random.shuffle(perm)
     pos = 0
-    for _ in range(int(math.ceil(n_samples / batch_size))):
+    lo, hi = batch_range if batch_range is not None else (0, None)
+    for i in range(int(math.ceil(n_samples / batch_size))):
         start = pos
         pos += batch_size
+        if i < lo or (hi is not None and i >= hi):
+            continue
         if pos > n_samples:  # wrap around: the last batch is completed from the head of the permutation
             idx = np.concatenate([perm[start:], perm[:pos - n_samples]])
         else:
@@ -76,7 +81,7 @@ class Dataloader:
 
     def data_generator(self, split):
         ds = Dataset(os.path.join(self.data_root, split + ".txt"), self.image_root, self.width_height)
-        return lambda: _epoch(ds.n_samples, self.batch_size, ds.data)
+        return lambda batch_range=None: _epoch(ds.n_samples, self.batch_size, ds.data, batch_range)
 
     @property
     def train_gen(self):
@@ -124,7 +129,7 @@ class SyntheticDataloader:
 
     def data_generator(self, split):
         imgs, lab = self._split(split)
-        return lambda: _epoch(len(imgs), self.batch_size, lambda idx: (imgs[idx], lab[idx]))
+        return lambda batch_range=None: _epoch(len(imgs), self.batch_size, lambda idx: (imgs[idx], lab[idx]), batch_range)
 
     test_gen = property(lambda self: self.data_generator("test"))
     db_gen = property(lambda self: self.data_generator("database"))

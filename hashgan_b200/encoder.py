@@ -157,6 +157,7 @@ class AlexNetHashEncoder:
         self.seed = int(seed)
         self.calls = 0
         self.last_seed = 0
+        self.timing = False  # True: per-stage CUDA events in the next calls (hg_alexnet_phase_ms; bench.py)
         self.lib = _native.lib()
         dev = self.device
         t = {k: torch.from_numpy(v).to(dev) for k, v in weights.tensors.items()}
@@ -222,6 +223,8 @@ class AlexNetHashEncoder:
             x = x.to(dev, non_blocking=True).contiguous()
             out = torch.empty((n, self.hash_dim), dtype=torch.float32, device=dev)
             flags = (_native.ENC_LRN if self.lrn else 0) | {"fp32": 0, "tf32": _native.ENC_CONV_TF32, "tf32x3": _native.ENC_CONV_TF32X3}[self.conv]
+            if self.timing:
+                flags |= _native.ENC_TIMING
             need = self.lib.hg_alexnet_workspace_bytes(n, flags)
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty((need,), dtype=torch.uint8, device=dev)

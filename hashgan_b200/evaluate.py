@@ -51,7 +51,15 @@ def forward_all(encoder, data_generator, size, cfg, shard=None):
 
     lo, hi, row_lo, row_hi = _block(size, cfg.TRAIN.BATCH_SIZE, shard)
     outputs, labels = [], []
-    for i, (image, label) in enumerate(data_generator()):
+    first, batches = 0, None
+    if shard is not None:
+        try:  # this package's loaders skip the fetch (image decode) of other ranks' batches; any other generator is filtered below
+            batches, first = data_generator(batch_range=(lo, hi)), lo
+        except TypeError:
+            batches = None
+    if batches is None:
+        batches = data_generator()
+    for i, (image, label) in enumerate(batches, start=first):
         if i >= hi:
             break
         if i < lo:
@@ -88,7 +96,10 @@ def evaluate(encoder, dataloader, cfg, metric=None, group=None):
         q_counts = [(lambda t: t[3] - t[2])(_block(cfg.DATA.TEST_SIZE, B, (r, world))) for r in range(world)]
         if metric is None:
             on_gpu = getattr(db.output, "is_cuda", False)
-            metric = ShardedMAPs(cfg.DATA.MAP_R, group, db_counts=db_counts, query_counts=q_counts, symmetric=bool(on_gpu))
+            # EVAL.BINARIZE False = the reference's literal ranking of the raw tanh outputs (lib/metric.py:13-14), sharded as well
+            binarize = bool(getattr(ev, "BINARIZE", True))
+            metric = ShardedMAPs(cfg.DATA.MAP_R, group, db_counts=db_counts, query_counts=q_counts, symmetric=bool(on_gpu) and binarize,
+                                 binarize=binarize)
         else:
             if getattr(metric, "db_counts", None) is None:
                 metric.db_counts = db_counts

@@ -110,9 +110,11 @@ class SymmetricRows:
                 self.bufs.append(t)
         self.step = 0
 
-    def pack(self, feat, lab, row_lo: int, bad_flag=None):
+    def pack(self, feat, lab, row_lo: int, bad_flag=None, expect_rows: Optional[int] = None):
         """Packs this rank's rows [row_lo, row_lo + n) into every rank's buffer; returns this rank's full buffer,
-        valid on the current stream once the call returns (kernel + barrier are enqueued)."""
+        valid on the current stream once the call returns (kernel + barrier are enqueued).  `expect_rows`: the row count
+        the other ranks assume for this rank (db_counts[rank]) -- a different block would leave rows of the symmetric
+        buffer unwritten or overlapping a neighbour's, so it raises instead."""
         import ctypes as C
 
         import torch
@@ -126,6 +128,8 @@ class SymmetricRows:
             f = metric._features_to_device(torch, feat, self.device)
             t, nbytes = metric._labels_to_device(torch, lab, self.device)
             n = int(f.shape[0])
+            if expect_rows is not None and n != int(expect_rows):
+                raise ValueError(f"rank {self.rank} holds {n} database rows but db_counts says {int(expect_rows)}")
             if int(f.shape[1]) != self.b or int(t.shape[1]) != self.L or t.shape[0] != n or row_lo + n > self.ndb:
                 raise ValueError("block does not fit the symmetric database buffer")
             off = int(row_lo) * self.Wr * 4
@@ -141,11 +145,14 @@ class SymmetricRows:
 
 class ShardedMAPs:
     """mAP@R over a process group.  ``get_maps_by_feature(database_shard, query_shard)`` takes THIS rank's
-    contiguous row blocks (rank order == global row order) and returns the global mAP on every rank."""
+    contiguous row blocks (rank order == global row order) and returns the global mAP on every rank.
+    ``binarize=False`` ranks the raw features by inner product (lib/metric.py:13-14 literally; EVAL.BINARIZE False): the
+    database features are all-gathered next to the packed label rows and every rank runs hg_ip_map on its queries."""
 
     def __init__(self, r: int, group=None, *, device=None, flags: int = 0,
                  pack_rows: Optional[Callable] = None, rank_fn: Optional[Callable] = None,
-                 db_counts: Optional[Sequence[int]] = None, query_counts: Optional[Sequence[int]] = None, symmetric: bool = False):
+                 db_counts: Optional[Sequence[int]] = None, query_counts: Optional[Sequence[int]] = None, symmetric: bool = False,
+                 binarize: bool = True, rank_real_fn: Optional[Callable] = None):
         # symmetric: fuse the exchange into the pack kernel (SymmetricRows; needs db_counts and the CUDA packers)
         self.symmetric = bool(symmetric)
         self._sym = None
@@ -155,43 +162,89 @@ class ShardedMAPs:
         self.group = group
         self.device = device
         self.flags = flags
+        self.binarize = bool(binarize)
         self._pack_rows = pack_rows
         self._rank_fn = rank_fn
+        self._rank_real_fn = rank_real_fn
         self.last_counts: Sequence[int] = ()
+        self.exchange = "none"
 
     def _hooks(self):
         from . import metric
 
-        pack = self._pack_rows or (lambda out, lab: metric.pack_rows(out, lab, self.device))
+        pack = self._pack_rows or (lambda out, lab, bad=None: metric.pack_rows(out, lab, self.device, bad))
 
         def rank(q_rows, db_rows, b, L, R):
             ap, _, _, _ = metric.hamming_map_device(q_rows, db_rows, b, L, R, flags=self.flags)
             return ap
 
-        return pack, (self._rank_fn or rank)
+        def rank_real(q_feat, q_rows, db_feat, db_rows, b, L, R):
+            ap, _, _, _ = metric.ip_map_device(q_feat, q_rows, db_feat, db_rows, b, L, R)
+            return ap
+
+        return pack, (self._rank_fn or rank), (self._rank_real_fn or rank_real)
 
     def per_query_ap_device(self, database, query):
         """Global per-query AP vector (rank order) as a tensor on the compute device."""
-        pack, rank = self._hooks()
+        pack, rank, rank_real = self._hooks()
+        dist = _dist()
         b = int(database.output.shape[1])
         L = int(database.label.shape[1])
-        q_rows = pack(query.output, query.label)
-        if self.symmetric and self.db_counts is not None and self._pack_rows is None and b % 32 == 0:
-            dist = _dist()
-            counts = [int(c) for c in self.db_counts]
-            ndb_all, my_rank = sum(counts), dist.get_rank(self.group)
-            if self._sym is None or (self._sym.ndb, self._sym.b, self._sym.L) != (ndb_all, b, L):
-                self._sym = SymmetricRows(ndb_all, b, L, q_rows.device, self.group)
-            db_rows = self._sym.pack(database.output, database.label, sum(counts[:my_rank]))   # pack + exchange in one kernel
+        injected = self._pack_rows is not None
+        if injected:
+            q_rows = pack(query.output, query.label)
+            bad = None
         else:
-            db_rows_local = pack(database.output, database.label)
+            from . import metric
+
+            torch = metric._torch()
+            device = metric._require_cuda(torch, self.device)
+            bad = torch.zeros((1,), dtype=torch.int32, device=device)
+            q_rows = pack(query.output, query.label, bad)
+        my_rank = dist.get_rank(self.group)
+        db_rows = None
+        if self.symmetric and self.db_counts is not None and not injected and b % 32 == 0:
+            counts = [int(c) for c in self.db_counts]
+            ndb_all = sum(counts)
+            try:
+                if self._sym is None or (self._sym.ndb, self._sym.b, self._sym.L) != (ndb_all, b, L):
+                    self._sym = SymmetricRows(ndb_all, b, L, q_rows.device, self.group)
+            except (ImportError, RuntimeError, AttributeError) as exc:  # no symmetric memory / no P2P on this box: all-gather instead
+                import warnings
+
+                warnings.warn(f"symmetric memory unavailable ({exc}); exchanging the packed rows with an all-gather")
+                self.symmetric, self._sym = False, None
+            if self._sym is not None:
+                db_rows = self._sym.pack(database.output, database.label, sum(counts[:my_rank]), bad, expect_rows=counts[my_rank])  # pack + exchange in one kernel
+                self.exchange = "push"
+        if db_rows is None:
+            db_rows_local = pack(database.output, database.label) if injected else pack(database.output, database.label, bad)
             db_rows, counts = gather_rows(db_rows_local, self.group, self.db_counts)   # the ONE exchange step: packed code + label words
+            self.exchange = "all-gather"
         self.last_counts = counts
         ndb = int(db_rows.shape[0])
         if self.R > ndb:
             raise ValueError(f"operands could not be broadcast together: R={self.R} exceeds the database size {ndb}")
-        ap_local = rank(q_rows, db_rows, b, L, int(self.R))
-        return gather_vector(ap_local, self.group, self.query_counts)
+        if self.binarize:
+            ap_local = rank(q_rows, db_rows, b, L, int(self.R))
+        else:
+            if injected:
+                import torch as _t
+
+                as_t = lambda x: x if isinstance(x, _t.Tensor) else _t.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np.float32))  # noqa: E731
+                db_feat_local, q_feat = as_t(database.output), as_t(query.output)
+            else:
+                db_feat_local = metric._features_to_device(torch, database.output, device)
+                q_feat = metric._features_to_device(torch, query.output, device)
+            db_feat, _ = gather_rows(db_feat_local, self.group, counts)   # the raw features travel too (ndb x b float32)
+            ap_local = rank_real(q_feat, q_rows, db_feat, db_rows, b, L, int(self.R))
+        out = gather_vector(ap_local, self.group, self.query_counts)
+        if bad is not None:
+            # a label that is not 0/1 on ANY rank fails the call on EVERY rank (MAPs raises ValueError for the same input)
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=self.group)
+            if int(bad.item()) != 0:
+                raise ValueError("labels must be 0/1 integers (lib/metric.py:17-19 is only defined for 0/1 labels)")
+        return out
 
     def get_maps_by_feature(self, database, query):
         ap = self.per_query_ap_device(database, query).cpu().numpy()

@@ -180,6 +180,7 @@ typedef struct HgAlexNetWeights {
 
 #define HG_ENC_LRN 1u        /* local response normalisation after pool1/pool2: on iff TRAIN.WGAN_SCALE == 0 (architecture.py:268,294) */
 #define HG_ENC_CONV_TF32 2u  /* opt-in: conv1-5 as implicit GEMM on tcgen05 with plain TF32 operands (6x faster than the fp32 CUDA cores, ~1e-3 relative error) */
+#define HG_ENC_TIMING 16u    /* record CUDA events between the stages of this call (diagnostics): hg_alexnet_phase_ms */
 #define HG_ENC_CONV_TF32X3 8u /* conv1-5 (and fc6-8 when fc_wt3 is set) as implicit GEMM on tcgen05 with error-compensated TF32 (hi/lo split, 3 MMAs): fp32-grade accuracy */
 
 /* Workspace bytes for a batch of n images (10 n crops) with these flags. */
@@ -213,6 +214,16 @@ int hg_transpose_f32(const float* d_in, int rows, int cols, float* d_out, void* 
 /* Integer-pipe microbenchmark: measured XOR+POPC word-ops per second of this GPU (the binding roofline
  * of the Hamming kernel).  Runs `iters` dependent-free popc chains on every SM. */
 int hg_popc_peak(double* wordops_per_s, double* ms, int iters, void* stream);
+
+/* Tensor-pipe microbenchmark: measured int8 tcgen05.mma throughput (multiply + add = 2 ops) of this GPU -- every SM issues
+ * `iters` x 4 back-to-back tcgen05.mma kind::i8 (M 128, N 256, K 32) on resident shared-memory tiles; best of 3 launches
+ * (iters <= 0: 8192).  The denominator of bench.py's roofline.tensor for the tensor-core select kernel. */
+int hg_i8_peak(double* ops_per_s, double* ms, int iters, void* stream);
+
+/* Milliseconds of the stages of the last hg_alexnet_encode[_stochastic] call made with HG_ENC_TIMING on this thread
+ * (synchronises on its last event): out = { crops (main.py:144-148, lib/util.py:12-21, architecture.py:215-249), conv1-5,
+ * max-pool + LRN, fc6-8 (+ dropout), tanh + crop mean }. */
+int hg_alexnet_phase_ms(float out[5]);
 
 #ifdef __cplusplus
 }

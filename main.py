@@ -47,6 +47,9 @@ def main(cfg):
         print("discriminator checkpoint restored: {} ({} tensors)".format(ckpt, len(names)))
     elif len(ckpt) > 0 and not cfg.EVAL.SYNTHETIC:
         raise SystemExit("{}.index not found (set EVAL.SYNTHETIC: True to evaluate without the trained checkpoint)".format(ckpt))
+    elif len(ckpt) > 0 and rank == 0:
+        print("WARNING: MODEL.D_PRETRAINED_MODEL_PATH = {} was NOT found; EVAL.SYNTHETIC is set, so the hash head is evaluated with "
+              "its INITIAL weights (map_val is not the trained model's)".format(ckpt), file=sys.stderr)
     encoder = AlexNetHashEncoder(weights, lrn=(cfg.TRAIN.WGAN_SCALE == 0), conv=("tf32" if cfg.EVAL.CONV_TF32 else cfg.EVAL.CONV),
                                  deterministic=bool(cfg.EVAL.DETERMINISTIC), seed=cfg.EVAL.SEED)
     if os.path.isdir(cfg.DATA.DATA_ROOT) and os.path.isdir(cfg.DATA.LIST_ROOT):
@@ -58,6 +61,11 @@ def main(cfg):
         raise SystemExit("{} / {} not found (set EVAL.SYNTHETIC: True for seeded synthetic images)".format(cfg.DATA.DATA_ROOT, cfg.DATA.LIST_ROOT))
     map_val = evaluate(encoder, dataloader, cfg)
     if rank == 0:
+        # the reference ranks the raw crop-averaged tanh outputs by inner product (lib/metric.py:13-14); the B200 hot path
+        # (EVAL.BINARIZE True, the default) ranks their signs by Hamming distance -- identical on +-1 codes only
+        print('ranking: {}'.format('Hamming distance on sign-binarised codes (EVAL.BINARIZE True; set it False for the reference\'s '
+                                   'real-valued inner-product ranking)' if cfg.EVAL.BINARIZE else
+                                   'real-valued inner product of the raw outputs (EVAL.BINARIZE False, lib/metric.py:13-14)'))
         print('map_val: {}'.format(map_val))
     if world > 1:
         dist.destroy_process_group()
@@ -68,15 +76,21 @@ if __name__ == "__main__":
     sys.path.append(os.getcwd())
     parser = argparse.ArgumentParser(description='HashGAN evaluation on B200')
     parser.add_argument('--cfg', '--config', required=True, type=str, metavar="FILE", help="path to yaml config")
-    parser.add_argument('--gpus', default='0', type=str)
+    parser.add_argument('--gpus', default=None, type=str)
     parser.add_argument('opts', nargs=argparse.REMAINDER, help="KEY VALUE overrides, e.g. EVAL.SYNTHETIC True DATA.DB_SIZE 2048")
     args = parser.parse_args()
-    os.environ["CUDA_VISIBLE_DEVICES"] = args.gpus
+    under_torchrun = int(os.environ.get("WORLD_SIZE", "1")) > 1
+    if args.gpus is not None:
+        os.environ["CUDA_VISIBLE_DEVICES"] = args.gpus       # main.py:263
+    elif not under_torchrun:
+        os.environ["CUDA_VISIBLE_DEVICES"] = "0"              # the reference's default (--gpus 0)
+    # under torchrun without --gpus every rank keeps all GPUs visible and picks LOCAL_RANK
 
     from hashgan_b200.config import config, update_and_inference_config
 
     config = update_and_inference_config(args.cfg, opts=args.opts)  # KEY VALUE overrides are merged after the yaml file
-    pprint(config)
-    with open(os.path.join(config.DATA.OUTPUT_DIR, 'config.txt'), 'w') as fh:
-        pprint(config, fh)
+    if int(os.environ.get("RANK", "0")) == 0:                 # one copy of the config, not one per rank
+        pprint(config)
+        with open(os.path.join(config.DATA.OUTPUT_DIR, 'config.txt'), 'w') as fh:
+            pprint(config, fh)
     sys.exit(main(config))

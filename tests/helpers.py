@@ -56,46 +56,4 @@ def golden_names(golden):
     return [str(x) for x in golden["cases"]]
 
 
-class COracle:
-    """ctypes wrapper of oracle/_build/libhamming_oracle.so (built by __graft_entry__.build_oracle)."""
-
-    def __init__(self):
-        import __graft_entry__ as entry
-
-        self.lib = C.CDLL(entry.build_oracle())
-        i64, vp = C.c_int64, C.c_void_p
-        self.lib.hgo_pack_sign_f32.argtypes = [vp, i64, C.c_int, vp]
-        self.lib.hgo_pack_labels_i64.argtypes = [vp, i64, C.c_int, vp]
-        self.lib.hgo_hamming_map.argtypes = [vp, vp, i64, vp, vp, i64, C.c_int, C.c_int, i64, vp, vp, vp, vp, C.c_int]
-
-    def pack_sign(self, feat):
-        feat = np.ascontiguousarray(feat, dtype=np.float32)
-        n, b = feat.shape
-        out = np.zeros((n, (b + 31) // 32), dtype=np.uint32)
-        assert self.lib.hgo_pack_sign_f32(feat.ctypes.data, n, b, out.ctypes.data) == 0
-        return out
-
-    def pack_labels(self, lab):
-        lab = np.ascontiguousarray(lab, dtype=np.int64)
-        n, L = lab.shape
-        out = np.zeros((n, (L + 31) // 32), dtype=np.uint32)
-        assert self.lib.hgo_pack_labels_i64(lab.ctypes.data, n, L, out.ctypes.data) == 0
-        return out
-
-    def hamming_map(self, db, q, R, want_ids=False, threads=0):
-        """db / q: records with +-1 .output and 0/1 .label.  Returns (ap, rel, ids, dist)."""
-        b, L = db.output.shape[1], db.label.shape[1]
-        dbc, qc = self.pack_sign(db.output), self.pack_sign(q.output)
-        dbl, ql = self.pack_labels(db.label), self.pack_labels(q.label)
-        nq, ndb = len(qc), len(dbc)
-        ap = np.empty(nq, dtype=np.float64)
-        rel = np.empty(nq, dtype=np.int64)
-        ids = np.empty((nq, R), dtype=np.uint32) if want_ids else None
-        dist = np.empty((nq, R), dtype=np.uint16) if want_ids else None
-        rc = self.lib.hgo_hamming_map(qc.ctypes.data, ql.ctypes.data, nq, dbc.ctypes.data, dbl.ctypes.data, ndb, b, L, R,
-                                      ap.ctypes.data, rel.ctypes.data,
-                                      ids.ctypes.data if want_ids else None, dist.ctypes.data if want_ids else None, threads)
-        if rc == 2:
-            raise ValueError("R exceeds the database size")
-        assert rc == 0, rc
-        return ap, rel, ids, dist
+from oracle.c_oracle import COracle  # noqa: E402,F401  (ctypes view of oracle/hamming_oracle.c)

@@ -85,6 +85,79 @@ def test_two_rank_sharded_map_equals_single_process(tmp_path, c_oracle, ndb, nq)
     assert float(outs[0]["val"]) == float(outs[1]["val"])
 
 
+def _real_worker(rank, world, port, ndb, nq, b, L, R, seed, out_dir):
+    sys.path.insert(0, helpers.ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from types import SimpleNamespace as NS
+        from hashgan_b200.sharding import ShardedMAPs, row_shard
+        from oracle import maps_oracle
+
+        rng = np.random.default_rng(seed)
+        dbf = np.tanh(rng.normal(size=(ndb, b))).astype(np.float32)
+        qf = np.tanh(rng.normal(size=(nq, b))).astype(np.float32)
+        dl = np.eye(L, dtype=np.int64)[rng.integers(0, L, ndb)]
+        ql = np.eye(L, dtype=np.int64)[rng.integers(0, L, nq)]
+        lo, hi = row_shard(ndb, rank, world)
+        qlo, qhi = row_shard(nq, rank, world)
+        LW = (L + 31) // 32
+
+        def pack_rows(out, lab):  # only the label words matter on the real-valued path
+            return torch.from_numpy(np.ascontiguousarray(maps_oracle.pack_label_bits(np.asarray(lab))).view(np.int32))
+
+        def unpack(rows):
+            bits = np.unpackbits(rows.numpy().view(np.uint8), axis=1, bitorder="little")[:, :L]
+            return bits.astype(np.int64)
+
+        def rank_real_fn(q_feat, q_rows, db_feat, db_rows, b_, L_, R_):
+            return torch.from_numpy(maps_oracle.per_query_ap(db_feat.numpy(), unpack(db_rows), q_feat.numpy(), unpack(q_rows), R_, tie="stable"))
+
+        m = ShardedMAPs(R, pack_rows=pack_rows, rank_real_fn=rank_real_fn, binarize=False)
+        ap = m.per_query_ap_device(NS(output=dbf[lo:hi], label=dl[lo:hi]), NS(output=qf[qlo:qhi], label=ql[qlo:qhi])).numpy()
+        np.savez(os.path.join(out_dir, f"real{rank}.npz"), ap=ap, dbf=dbf, qf=qf, dl=dl, ql=ql)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_real_valued_ranking_equals_single_process(tmp_path):
+    """EVAL.BINARIZE False under a process group: the raw features are all-gathered next to the packed label rows
+    and ranked by inner product -- the single-process per-query APs, bit for bit, on every rank."""
+    from oracle import maps_oracle
+
+    ndb, nq, b, L, R, seed, world = 301, 23, 16, 5, 50, 9, 2
+    port = _free_port()
+    mp.spawn(_real_worker, args=(world, port, ndb, nq, b, L, R, seed, str(tmp_path)), nprocs=world, join=True)
+    outs = [np.load(tmp_path / f"real{r}.npz") for r in range(world)]
+    o = outs[0]
+    want = maps_oracle.per_query_ap(o["dbf"], o["dl"], o["qf"], o["ql"], R, tie="stable")
+    for r in range(world):
+        assert np.array_equal(outs[r]["ap"], want, equal_nan=True)
+
+
+def test_batch_range_skips_the_fetch_of_other_ranks_batches():
+    """forward_all(shard=...) asks the loader for its block only: images outside [lo, hi) are never fetched, and the
+    batches it gets are the ones the full epoch yields at those positions."""
+    from hashgan_b200 import dataloader as dl
+
+    fetched = []
+
+    def fetch(idx):
+        fetched.append(np.array(idx))
+        return np.zeros((len(idx), 2, 2, 3), np.uint8) + np.asarray(idx, np.uint8)[:, None, None, None], np.asarray(idx)[:, None]
+
+    np.random.seed(4)
+    full = list(dl._epoch(50, 8, fetch))
+    n_full = len(fetched)
+    fetched.clear()
+    np.random.seed(4)
+    part = list(dl._epoch(50, 8, fetch, batch_range=(2, 5)))
+    assert n_full == 7 and len(fetched) == 3 and len(part) == 3
+    for (a, la), (b_, lb) in zip(part, full[2:5]):
+        assert np.array_equal(a, b_) and np.array_equal(la, lb)
+
+
 def _eval_cfg(db_size, test_size, batch, b, L, R):
     from types import SimpleNamespace as NS
 
