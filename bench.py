@@ -192,13 +192,9 @@ def _enc_images(n, seed=3):
 
 def _enc_oracle(images, weights, lrn=True):
     """oracle/alexnet_oracle.py (PyTorch fp32 restatement of lib/architecture.py:196-392) on the host CPU."""
-    import torch
-
     from oracle import alexnet_oracle
 
-    w = {k: torch.from_numpy(v) for k, v in weights.tensors.items()}
-    with torch.no_grad():
-        return alexnet_oracle.encode(torch.from_numpy(images), w, 32, lrn=lrn).numpy()
+    return np.asarray(alexnet_oracle.encode(np.asarray(images), weights.tensors, 32, lrn=lrn))
 
 
 def run_encoder_reference(args):

@@ -41,6 +41,7 @@ SIGNATURES = {
     "hg_select_backend": (_int, [_int, _int]),
     "hg_ip_map_workspace_bytes": (_sz, [_i64, _i64, _int, _int, _i64]),
     "hg_ip_map": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hg_relevant_totals": (_int, [_vp, _i64, _vp, _i64, _int, _int, _vp, _vp]),
     "hg_launch_count": (_i64, [_int]),
     "hg_mean_ap": (_int, [_vp, _i64, C.POINTER(C.c_double), C.POINTER(_i64), _vp]),
     "hg_mean_ap_host": (_int, [_vp, _i64, C.POINTER(C.c_double), C.POINTER(_i64)]),

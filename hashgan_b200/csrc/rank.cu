@@ -261,7 +261,11 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(HistParams p)
                 uint32_t v[W];
                 load_code<W>(tile + j * Wr, v);
                 const int d = hamming<W>(qw, v);
-                h[d * kHistThreads + tid] += 1;
+                // a reduction without a result (ATOMS.POPC.INC with no destination): the column is private to this thread, the
+                // point is that nothing waits for the value -- a plain `+= 1` chains load -> add -> store per row.  Measured
+                // on B200 (C4): 0.164 -> 0.139 ms.  (The AP kernel's counters need the old value back; there the atomic with
+                // a result is 2x SLOWER than load/add/store -- measured 0.43 -> 0.85 ms -- so it keeps the plain form.)
+                atomicAdd(&h[d * kHistThreads + tid], 1u);
             }
         }
     }

@@ -16,11 +16,12 @@
 //   warps 2..17 epilogue: thread <-> query (TMEM lane), warp <-> (32 queries, one split = 64 accumulator columns).
 //               tcgen05.ld ... .pack::16b brings two accumulators per
 //               register (|ip'| <= 384 fits 16 bits); one PRMT with sign replication turns two registers into four
-//               0x00/0xFF bytes, one LOP3 drops them into the hit mask: 0.5 integer op per pair.  The accumulator is
+//               0x00/0xFF bytes (ALU pipe), one multiply-add drops them into the hit mask (FMA pipe, hit_mask32): 0.25 + 0.25
+//               integer op per pair on two different pipes.  The accumulator is
 //               then handed back to the MMA warp and the ~R/Ndb hits of the tile are walked in row order: distance
 //               recomputed from the packed words (POPC), relevance from the label words, entry appended to the
 //               thread's private bin exactly as select_kernel does.
-// The PRMT/LOP3 gather leaves accumulator column 4i+k of a 32-column group at mask bit 8k+i; expand_db_kernel stores
+// The PRMT / multiply-add gather leaves accumulator column 4i+k of a 32-column group at mask bit 8k+i; expand_db_kernel stores
 // the int8 database rows of every 32-row group in the inverse order, so that mask bit j IS row j of the group.
 // The bins, thresholds, AP kernel and exactness guard are shared with the POPC path (rank.cu).
 #include "umma.cuh"
@@ -191,16 +192,20 @@ __device__ __forceinline__ uint32_t sign_bytes(uint32_t a, uint32_t b, uint32_t 
     return d;
 }
 
-// 32 accumulator columns -> 32-bit mask of the NEGATIVE ones (bit 8k+i = column 4i+k)
-__device__ __forceinline__ uint32_t miss_mask32(uint32_t taddr, uint32_t sel)
+// 32 accumulator columns -> 32-bit mask of the NON-NEGATIVE ones, the hits (bit 8k+i = column 4i+k).
+// p_i = the four sign-replicated bytes (0xFF = negative) of columns 4i .. 4i+3.  The eight words are merged on the FMA pipe
+// instead of the (binding) ALU pipe: a byte of ones is 2^8 - 1, so p_i = 255 * M_i with M_i the 0x01-per-byte word of the
+// negative columns, and X = sum_i p_i << i = 255 * M (mod 2^32) with M the mask of the negative columns.  255^-1 mod 2^32 is
+// -0x01010101, hence M = -X * 0x01010101 and the hit mask ~M = -M - 1 = X * 0x01010101 - 1: eight multiply-adds in all.
+__device__ __forceinline__ uint32_t hit_mask32(uint32_t taddr, uint32_t sel)
 {
     uint32_t r[16];
     tmem_ld_32cols_pack16(taddr, r);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    uint32_t miss = 0;
+    uint32_t x = sign_bytes(r[0], r[1], sel);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) miss |= sign_bytes(r[2 * i], r[2 * i + 1], sel) & (0x01010101u << i);
-    return miss;
+    for (int i = 1; i < 8; ++i) x += sign_bytes(r[2 * i], r[2 * i + 1], sel) << i;
+    return x * 0x01010101u - 1u;
 }
 
 // One CTA = 256 queries x TWO adjacent database splits (bins).  A 128-row B tile holds 64 rows of the first split
@@ -353,13 +358,13 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
             mbar_wait_a(tfull_a, tph);          // MMAs of tile t are complete
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t* srows = reinterpret_cast<const uint32_t*>(stage_rows + s * STAGE_BYTES);
-            const uint32_t m0 = miss_mask32(tmem_row, sel);
-            const uint32_t m1 = miss_mask32(tmem_row + 32u, sel);
+            const uint32_t m0 = hit_mask32(tmem_row, sel);
+            const uint32_t m1 = hit_mask32(tmem_row + 32u, sel);
             // the accumulators are consumed: let the MMA warp start the next tile while the hits are written out
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive_a(tempty_a);
-            uint32_t h0 = ~m0 & live, h1 = ~m1 & live;
+            uint32_t h0 = m0 & live, h1 = m1 & live;
             if (t >= nfull) {  // last tile(s) of the split: drop the rows that do not exist
                 const int left = nrows32 - t * kUmmaHalfRows;
                 h0 &= left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));

@@ -28,7 +28,7 @@ import numpy as np
 
 from . import _native
 
-__all__ = ["MAPs", "MAPs_CQ", "pack_rows", "hamming_map_device", "ip_map_device"]
+__all__ = ["MAPs", "MAPs_CQ", "pack_rows", "hamming_map_device", "ip_map_device", "relevant_totals_device"]
 
 # One call of hg_hamming_map handles a query chunk whose workspace stays under this many bytes.
 DEFAULT_WORKSPACE_LIMIT = 24 << 30
@@ -238,6 +238,18 @@ def ip_map_device(q_feat, q_rows, db_feat, db_rows, b: int, L: int, R: int, *, w
     return ap, ids, ips, rel
 
 
+def relevant_totals_device(q_rows, db_rows, b: int, L: int):
+    """Relevant rows of the whole database per query (C ABI: hg_relevant_totals): int32 CUDA tensor [Nq]."""
+    torch = _torch()
+    lib = _native.lib()
+    device = db_rows.device
+    with torch.cuda.device(device):
+        total = torch.empty((int(q_rows.shape[0]),), dtype=torch.int32, device=device)
+        _native.check(lib.hg_relevant_totals(q_rows.data_ptr(), int(q_rows.shape[0]), db_rows.data_ptr(), int(db_rows.shape[0]), b, L,
+                                             total.data_ptr(), _stream_ptr(torch, device)))
+    return total
+
+
 class _Record:
     __slots__ = ("output", "label")
 
@@ -389,6 +401,37 @@ class MAPs:
         if want_ids:
             return ap_h, ids.cpu().numpy().astype(np.int64) & 0xFFFFFFFF, ips.cpu().numpy()
         return ap_h
+
+    def precision_recall(self, database, query):
+        """precision@R, recall@R and mAP@R on ONE ranking (the reference reports mAP only).  Per query, with
+        rel = relevant rows inside the top-R (lib/metric.py:20) and total = relevant rows in the whole database under the same
+        relevance test (lib/metric.py:17-19):  precision = rel / R,  recall = rel / total (NaN when the database holds no
+        relevant row for the query).  Returns a dict: 'precision' / 'recall' / 'mAP' are means (recall over the queries that
+        have a relevant row at all, mAP as lib/metric.py:22-24), 'per_query' holds the vectors (ap, rel, total)."""
+        torch = _torch()
+        database, query = _as_record(database), _as_record(query)
+        device, bad, db_rows, q_rows, b, L = self._pack_all(database, query)
+        R = int(self.R)
+        with torch.cuda.device(device):
+            if self.binarize:
+                ap, _, _, rel = hamming_map_device(q_rows, db_rows, b, L, R, flags=self.flags, want_rel=True, workspace_limit=self.workspace_limit)
+            else:
+                db_f = _features_to_device(torch, database.output, device)
+                q_f = _features_to_device(torch, query.output, device)
+                ap, _, _, rel = ip_map_device(q_f, q_rows, db_f, db_rows, b, L, R, want_rel=True, workspace_limit=self.workspace_limit)
+            total = relevant_totals_device(q_rows, db_rows, b, L)
+            ap_h, rel_h, total_h = ap.cpu().numpy(), rel.cpu().numpy().astype(np.int64), total.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        if int(bad.item()) != 0:
+            raise ValueError("labels must be 0/1 integers (lib/metric.py:17-19 is only defined for 0/1 labels)")
+        precision = rel_h / float(R)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            recall = np.where(total_h > 0, rel_h / np.maximum(total_h, 1), np.nan)
+        kept = ap_h[~np.isnan(ap_h)]
+        has = ~np.isnan(recall)
+        return {"precision": np.float64(np.mean(precision)) if len(precision) else np.float64("nan"),
+                "recall": np.float64(np.mean(recall[has])) if has.any() else np.float64("nan"),
+                "mAP": np.mean(kept) if len(kept) else np.float64("nan"), "R": R,
+                "per_query": {"ap": ap_h, "rel": rel_h, "total": total_h, "precision": precision, "recall": recall}}
 
     def get_maps_by_feature(self, database, query):
         """mAP@R; same call and return type (numpy.float64) as lib/metric.py:12-24."""

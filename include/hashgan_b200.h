@@ -133,6 +133,14 @@ int64_t hg_launch_count(int reset);
  * D2H copy of d_ap (synchronises `stream`).  *map_out = NaN when every query was skipped. */
 int hg_mean_ap(const double* d_ap, int64_t nq, double* map_out, int64_t* n_used, void* stream);
 
+/* Relevant rows of the WHOLE database per query: d_total[q] = #{ rows r : labels(q) & labels(r) != 0 } -- the relevance test of
+ * lib/metric.py:17-19 applied to every row instead of the top-R.  With hg_hamming_map's d_rel (relevant rows inside the top-R,
+ * lib/metric.py:20) it gives the companions of mAP@R on the same ranking:
+ *     precision@R = rel / R          recall@R = rel / total.
+ * Packed rows as produced by hg_pack_rows (only the label words are read).  d_total: [nq] uint32. */
+int hg_relevant_totals(const uint32_t* d_q_rows, int64_t nq, const uint32_t* d_db_rows, int64_t ndb, int b, int L, uint32_t* d_total,
+                       void* stream);
+
 /* Host-only half of hg_mean_ap: lib/metric.py:24 (`np.mean(np.array(apx))`) on a HOST vector of per-query APs --
  * NaN entries are the queries the reference skips (lib/metric.py:22-23), the kept ones are summed with NumPy's
  * pairwise scheme so the result is bit-identical to np.mean.  Needs no GPU (tests/test_abi.py pins it against NumPy). */
