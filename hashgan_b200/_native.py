@@ -19,6 +19,7 @@ ENC_LRN = 1
 ENC_CONV_TF32 = 2
 ENC_CONV_TF32X3 = 8
 ENC_TIMING = 16
+ENC_FUSED_STAGE1 = 32
 MAX_BITS = 256
 
 _i64, _int, _u32, _vp, _sz = C.c_int64, C.c_int, C.c_uint, C.c_void_p, C.c_size_t
@@ -39,6 +40,7 @@ SIGNATURES = {
     "hg_hamming_map_stats": (_int, [_vp, _sz, _i64, _i64, _int, _int, _i64, C.POINTER(_i64), _vp]),
     "hg_hamming_map_phase_ms": (_int, [C.POINTER(C.c_float)]),
     "hg_select_backend": (_int, [_int, _int]),
+    "hg_select_backend_for": (_int, [_i64, _i64, _int, _int, _i64]),
     "hg_ip_map_workspace_bytes": (_sz, [_i64, _i64, _int, _int, _i64]),
     "hg_ip_map": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hg_relevant_totals": (_int, [_vp, _i64, _vp, _i64, _int, _int, _vp, _vp]),
@@ -51,6 +53,8 @@ SIGNATURES = {
     "hg_gemm_tf32": (_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _int, _int, _int, _int, _vp]),
     "hg_alexnet_workspace_bytes": (_sz, [_int, _u32]),
     "hg_conv_weight_pack": (_int, [_vp, _int, _int, _int, _int, _int, _vp, _vp]),
+    "hg_conv1_fused_floats": (_sz, [_int]),
+    "hg_conv1_fused_pack": (_int, [_vp, _int, _vp, _vp]),
     "hg_alexnet_encode": (_int, [_vp, _int, _int, _vp, _int, _u32, _vp, _vp, _sz, _vp]),
     "hg_alexnet_encode_stochastic": (_int, [_vp, _int, _int, _vp, _int, _u32, _vp, _vp, _sz, C.c_uint64, _vp]),
     "hg_transpose_f32": (_int, [_vp, _int, _int, _vp, _vp]),
@@ -65,7 +69,8 @@ class AlexNetWeightsStruct(C.Structure):
     """HgAlexNetWeights of include/hashgan_b200.h."""
     _fields_ = [("conv_w", C.c_void_p * 5), ("conv_b", C.c_void_p * 5),
                 ("fc6_wt", C.c_void_p), ("fc6_b", C.c_void_p), ("fc7_wt", C.c_void_p), ("fc7_b", C.c_void_p),
-                ("fc8_wt", C.c_void_p), ("fc8_b", C.c_void_p), ("conv_wt", C.c_void_p * 5), ("fc_wt3", C.c_void_p * 3)]
+                ("fc8_wt", C.c_void_p), ("fc8_b", C.c_void_p), ("conv_wt", C.c_void_p * 5), ("fc_wt3", C.c_void_p * 3),
+                ("conv1_fused", C.c_void_p), ("conv1_fused_wh", C.c_int)]
 
 
 _lib = None

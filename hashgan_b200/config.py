@@ -175,6 +175,7 @@ _DEFAULTS = {
                                  # evaluate() shards database and queries by rows over the ranks it finds
         "DETERMINISTIC": True,   # no de-quantisation noise (main.py:147), no eval-time dropout (architecture.py:369,377);
                                  # False = the reference's stochastic eval graph, draws seeded by EVAL.SEED
+        "PRECISION_RECALL": False,  # also print precision@R / recall@R of the same ranking (MAPs.precision_recall; single process)
         "SYNTHETIC": False,      # seeded synthetic images / weights when the data and checkpoints are absent
         "SEED": 0,
     },

@@ -74,6 +74,7 @@ struct UmmaSelectArgs {
     const uint8_t* qx;   // [round_up(nq, 256), 32] threshold columns of the A operand
     const uint8_t* bx;   // [128, 32] threshold columns of the B operand (constant)
     uint32_t prmt_sel;   // PRMT selector of the epilogue's sign gather
+    int rows_paired;     // set by the launcher: 2-word packed rows are staged as 16-byte row pairs
 };
 int umma_select_kp(int b, int Wr);  // int8 row bytes (64 / 128), 0 = shape not supported by the tensor-core path
 int umma_expand_q(const uint32_t* rows, int64_t n, int b, int Wr, int KP, uint8_t* out, cudaStream_t st);

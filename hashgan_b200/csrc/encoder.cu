@@ -316,6 +316,10 @@ static int launch_conv(const float* in, const float* w, const float* bias, float
     return HG_OK;
 }
 
+// encoder_stage1.cu
+bool stage1_supported(int wh);
+int stage1_launch(const unsigned char* img, int n, int wh, const float* wfused, const float* bias, float* out, uint64_t seed, bool lrn, cudaStream_t st);
+
 static int conv_cgp(int Cg) { return (Cg + 3) & ~3; }  // channels per group as the tensor-core path lays them out
 static int conv_kpad(int KH, int KW, int Cg) { return (int)round_up((int64_t)KH * KW * conv_cgp(Cg), 32); }
 
@@ -431,7 +435,7 @@ static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgA
     for (int i = 0; i < 5; ++i)
         if (!w->conv_w[i] || !w->conv_b[i]) return fail(HG_EINVAL, "hg_alexnet_encode: conv%d weights missing", i + 1);
     if (!w->fc6_wt || !w->fc6_b || !w->fc7_wt || !w->fc7_b || !w->fc8_wt || !w->fc8_b) return fail(HG_EINVAL, "hg_alexnet_encode: fc weights missing");
-    if (flags & ~(unsigned)(HG_ENC_LRN | HG_ENC_CONV_TF32 | HG_ENC_CONV_TF32X3 | HG_ENC_TIMING)) return fail(HG_EINVAL, "hg_alexnet_encode: unknown flag");
+    if (flags & ~(unsigned)(HG_ENC_LRN | HG_ENC_CONV_TF32 | HG_ENC_CONV_TF32X3 | HG_ENC_TIMING | HG_ENC_FUSED_STAGE1)) return fail(HG_EINVAL, "hg_alexnet_encode: unknown flag");
     const bool x3 = (flags & HG_ENC_CONV_TF32X3) != 0;
     const bool tc = x3 || (flags & HG_ENC_CONV_TF32) != 0;
     if (tc)
@@ -456,23 +460,33 @@ static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgA
         return tc ? launch_conv_tf32(src, w->conv_wt[i], w->conv_b[i], dst, N, H, H, (C + 3) & ~3, KH, KH, stride, pad, Cout, groups, x3, st)
                   : launch_conv(src, w->conv_w[i], w->conv_b[i], dst, N, H, H, C, KH, KH, stride, pad, Cout, groups, st);
     };
-    // crops -> A
-    prep_crops_kernel<<<grid_1d((int64_t)N * 227 * 227, 256), 256, 0, st>>>(d_images, n, wh, tc ? 4 : 3, A, seed);
-    count_launch();
-    HG_CUDA_TRY(cudaGetLastError());
-    tm.mark(kEncPrep, st);
-    // conv1 11x11/4 VALID 3->96 : A -> B [N,55,55,96]
-    if ((rc = conv(0, A, B, 227, 3, 11, 4, 0, 96, 1)) != HG_OK) return rc;
-    tm.mark(kEncConv, st);
-    // pool1 : B -> A [N,27,27,96]
-    maxpool3s2_kernel<<<grid_1d((int64_t)N * 27 * 27 * 96, 256), 256, 0, st>>>(B, N, 55, 55, 96, 27, 27, A);
-    count_launch();
+    const bool fused1 = (flags & HG_ENC_FUSED_STAGE1) != 0;
+    if (fused1 && (!w->conv1_fused || w->conv1_fused_wh != wh || !stage1_supported(wh)))
+        return fail(HG_EINVAL, "hg_alexnet_encode: HG_ENC_FUSED_STAGE1 needs conv1_fused packed for wh=%d (hg_conv1_fused_pack; have wh=%d)", wh,
+                    w->conv1_fused ? w->conv1_fused_wh : 0);
     float* cur = A;
     float* other = B;
-    if (lrn) {
-        lrn_kernel<<<grid_1d((int64_t)N * 27 * 27 * 96, 256), 256, 0, st>>>(cur, (int64_t)N * 27 * 27, 96, other);
+    if (fused1) {
+        // images -> pool1 (+LRN) output [N,27,27,96] in one kernel: no crop tensor, no conv1 output tensor
+        if ((rc = stage1_launch(d_images, n, wh, w->conv1_fused, w->conv_b[0], A, seed, lrn, st)) != HG_OK) return rc;
+        tm.mark(kEncConv, st);
+    } else {
+        // crops -> A
+        prep_crops_kernel<<<grid_1d((int64_t)N * 227 * 227, 256), 256, 0, st>>>(d_images, n, wh, tc ? 4 : 3, A, seed);
         count_launch();
-        std::swap(cur, other);
+        HG_CUDA_TRY(cudaGetLastError());
+        tm.mark(kEncPrep, st);
+        // conv1 11x11/4 VALID 3->96 : A -> B [N,55,55,96]
+        if ((rc = conv(0, A, B, 227, 3, 11, 4, 0, 96, 1)) != HG_OK) return rc;
+        tm.mark(kEncConv, st);
+        // pool1 : B -> A [N,27,27,96]
+        maxpool3s2_kernel<<<grid_1d((int64_t)N * 27 * 27 * 96, 256), 256, 0, st>>>(B, N, 55, 55, 96, 27, 27, A);
+        count_launch();
+        if (lrn) {
+            lrn_kernel<<<grid_1d((int64_t)N * 27 * 27 * 96, 256), 256, 0, st>>>(cur, (int64_t)N * 27 * 27, 96, other);
+            count_launch();
+            std::swap(cur, other);
+        }
     }
     HG_CUDA_TRY(cudaGetLastError());
     tm.mark(kEncPool, st);

@@ -85,6 +85,10 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
     {
         const char* be = getenv("HG_SELECT_BACKEND");
         if (!(be && be[0] == 'p')) p.umma_kp = umma_select_kp(b, p.Wr);  // "popc" forces the POPC kernel
+        // b <= 32 costs the POPC kernel ONE word-op per pair, and a top-R that is a large part of the database (C1: R = Ndb)
+        // makes every pair a candidate -- the tensor-core kernel's advantage is the cheap rejection of non-candidates, so it
+        // only takes short codes when the top-R is sparse
+        if (p.umma_kp == 32 && R * 8 > ndb && !(be && be[0] == 'u')) p.umma_kp = 0;
     }
     int64_t target_ctas = (int64_t)sms * env_int("HG_SELECT_CTAS_PER_SM", kSelectCtasPerSm) * ctas_mult;
     int64_t units = p.nqt;
@@ -99,7 +103,7 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
         // (rows of its pair + a fixed start-up), so the launch takes ceil(CTAs / slots) rounds of the longest pair.
         // Pick the pair count with the shortest makespan instead of a fixed wave count: a grid of 4.05 waves would
         // leave the last 0.05 wave running alone.
-        const int64_t slots = (int64_t)sms * 2;
+        const int64_t slots = (int64_t)sms * (p.umma_kp > 128 ? 1 : 2);
         const int64_t startup_rows = 768;  // A-operand load + TMEM allocation + pipeline fill, in database rows
         double best = 1e300;
         for (int64_t cand = 1; cand <= 2 * P0 + 8; ++cand) {
@@ -118,6 +122,15 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
     // candidate budget per query, spread evenly over the bins
     const int64_t all_rows = (int64_t)p.P * SL;
     int64_t capq = std::min<int64_t>(all_rows, std::max<int64_t>(6 * R, R + 16384));
+    {
+        // The budget is spread EVENLY over the bins, but a database stored class by class (the caller defines the row order,
+        // lib/dataloader.py:93-94 only shuffles inside evaluate()) concentrates a query's candidates in the few splits that
+        // hold its class.  Address space is cheap (only the entries really written cost bandwidth): up to 4x the budget while
+        // the list area stays below 6 GB, so that a class covering >= 7 % of the rows still fits its bins; anything more
+        // concentrated takes the exact path (correct, slower; hg_hamming_map_stats reports the count).
+        const int64_t mult = std::max<int64_t>(1, std::min<int64_t>(4, (int64_t)((6.0 * (double)(1ull << 30)) / (4.0 * (double)nq * (double)capq))));
+        capq = std::min<int64_t>(all_rows, capq * mult);
+    }
     int64_t cap = round_up(ceil_div(capq, p.P), 8);
     cap = std::min<int64_t>(cap, SL);
     while (cap * p.P < R) cap += 8;  // the exact path reuses the list area and needs R entries per query
@@ -1236,6 +1249,12 @@ extern "C" int hg_select_backend(int b, int L)
     const char* be = getenv("HG_SELECT_BACKEND");
     if (be && be[0] == 'p') return 0;
     return hg::umma_select_kp(b, Wr);
+}
+
+extern "C" int hg_select_backend_for(int64_t nq, int64_t ndb, int b, int L, int64_t R)
+{
+    const hg::Plan pl = hg::make_plan(nq, ndb, b, L, R);
+    return pl.ok ? pl.umma_kp : -1;
 }
 
 extern "C" int hg_hamming_map_stats(const void* d_workspace, size_t workspace_bytes, int64_t nq, int64_t ndb, int b, int L, int64_t R,

@@ -33,10 +33,17 @@ namespace hg {
 
 constexpr int kUmmaEpiWarps = 16;
 constexpr int kUmmaThreads = 32 * (2 + kUmmaEpiWarps);
-template <int KP> struct UmmaCfg { static constexpr int S = (KP == 64 ? 4 : 3); };  // ring depth: two CTAs must fit one SM
+// KP = int8 bytes per code row: 32 (b <= 32), 64 (b <= 64), 128 (b <= 128), 256 (b <= 256: two 128-byte K blocks).
+template <int KP> struct UmmaCfg {
+    static constexpr int S = (KP <= 64 ? 4 : 3);              // ring depth: two CTAs must fit one SM (one CTA for KP = 256)
+    static constexpr int KB = (KP > 128 ? KP / 128 : 1);      // K blocks of one operand row
+    static constexpr int KW = KP / KB;                        // bytes of a K block = swizzle width (32 / 64 / 128)
+    static constexpr int CTAS = (KP > 128 ? 1 : 2);           // resident CTAs per SM
+    static constexpr int QW = (KP > 128 ? 8 : 4);             // code words a query keeps in registers
+    static constexpr uint32_t ROWS_BYTES = 128u * (KP > 128 ? 12u : 8u) * 4u;  // packed-row bytes per stage (Wr <= 8, 12 for b > 128)
+};
 constexpr int kUmmaHalfRows = 64;  // database rows per split and tile (a B tile = two of these)
-constexpr uint32_t kUmmaRowsMax = 128 * 8 * 4;  // packed-row bytes per stage (Wr <= 8)
-constexpr int kUmmaXBytes = 32;                 // threshold K step: one UMMA_K of int8 columns, SWIZZLE_32B rows
+constexpr int kUmmaXBytes = 32;    // threshold K step: one UMMA_K of int8 columns, SWIZZLE_32B rows
 
 __host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N)
 {
@@ -146,29 +153,31 @@ __global__ void __launch_bounds__(256) expand_db_kernel(const uint32_t* __restri
     }
 }
 
-// threshold columns: qx[slot] = 32 int8, the first two sum to 2 T - b = -(b - 2 T)  (never-hit rows: -128, -128);
-// bx = 128 rows of (1, 1, 0, ...).  ip' = ip + (2 T - b) >= 0  <=>  d_H <= T.
+// threshold columns: qx[slot] = 32 int8, the first four sum to 2 T - b = -(b - 2 T), each part within [-64, 64] for
+// b <= 256 (never-hit rows: 4 x -128 = -512 < -b); bx = 128 rows of (1, 1, 1, 1, 0, ...).
+// ip' = ip + (2 T - b) >= 0  <=>  d_H <= T.
 __global__ void __launch_bounds__(256) thr_columns_kernel(const int* __restrict__ thr, int64_t nq, int64_t nq_pad, int b, uint8_t* __restrict__ qx,
                                                           uint8_t* __restrict__ bx)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nq_pad) {
-        int c0 = -128, c1 = -128;
+        uint32_t word = 0x80808080u;
         if (i < nq) {
             const int T = thr[i];
             if (T >= 0) {
-                const int v = 2 * T - b;  // in [-b, b], |v| <= 128
-                c0 = v >> 1;              // floor
-                c1 = v - c0;
+                const int v = 2 * T - b;  // in [-b, b]; floor((v + k) / 4), k = 0..3, sum to v
+                word = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) word |= (uint32_t)(((v + k) >> 2) & 0xFF) << (8 * k);
             }
         }
         uint4* dst = reinterpret_cast<uint4*>(qx + i * 32);
-        dst[0] = make_uint4((uint32_t)(c0 & 0xFF) | ((uint32_t)(c1 & 0xFF) << 8), 0, 0, 0);
+        dst[0] = make_uint4(word, 0, 0, 0);
         dst[1] = make_uint4(0, 0, 0, 0);
     }
     if (i < 128) {
         uint4* dst = reinterpret_cast<uint4*>(bx + i * 32);
-        dst[0] = make_uint4(0x0101u, 0, 0, 0);
+        dst[0] = make_uint4(0x01010101u, 0, 0, 0);
         dst[1] = make_uint4(0, 0, 0, 0);
     }
 }
@@ -214,19 +223,23 @@ __device__ __forceinline__ uint32_t hit_mask32(uint32_t taddr, uint32_t sel)
 // that sees its rows in ascending order.
 // MODE fixes the packed-row shape at compile time: 1 = two code words in 4-word rows (32 < b <= 64, L <= 64: C4),
 // 2 = four code words in 8-word rows (96 < b <= 128: C5), 0 = read it from the arguments.
+// KP = 256 (b > 128): an operand row is two 128-byte K blocks, stored block after block ([block][row][128 B], each block
+// SWIZZLE_128B) and contracted by 2 x 4 K steps; one CTA per SM.  KP = 32 (b <= 32): SWIZZLE_32B rows, one K step; 2-word
+// packed rows travel as 16-byte row PAIRS (a.rows_paired) because a TMA box row must be a multiple of 16 bytes.
 template <int KP, int MODE>
-__global__ void __launch_bounds__(kUmmaThreads, 2)
+__global__ void __launch_bounds__(kUmmaThreads, UmmaCfg<KP>::CTAS)
 select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_constant__ CUtensorMap tmap_db8,
                    const __grid_constant__ CUtensorMap tmap_rows, const __grid_constant__ CUtensorMap tmap_qx,
                    const __grid_constant__ CUtensorMap tmap_bx, UmmaSelectArgs a)
 {
     constexpr int S = UmmaCfg<KP>::S;
+    constexpr int KB = UmmaCfg<KP>::KB, KW = UmmaCfg<KP>::KW, QW = UmmaCfg<KP>::QW;
     constexpr uint32_t A_BYTES = 2 * 128 * KP;
     constexpr uint32_t AX_BYTES = 2 * 128 * kUmmaXBytes;
     constexpr uint32_t BX_BYTES = 128 * kUmmaXBytes;
     constexpr uint32_t FIXED_BYTES = A_BYTES + AX_BYTES + BX_BYTES;
     constexpr uint32_t B_BYTES = 128 * KP;
-    constexpr uint32_t STAGE_BYTES = B_BYTES + kUmmaRowsMax;
+    constexpr uint32_t STAGE_BYTES = B_BYTES + UmmaCfg<KP>::ROWS_BYTES;
     extern __shared__ __align__(1024) uint8_t usm[];
     const uint32_t base = (smem_u32(usm) + 1023u) & ~1023u;
     uint8_t* const base_ptr = usm + (base - smem_u32(usm));
@@ -265,8 +278,11 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
     if (warp == 0) {
         if (lane == 0) {
             mbar_arrive_expect_tx(&a_full, FIXED_BYTES);
-            tma_load_2d(base, &tmap_q8, smem_u32(&a_full), 0, (int)q0);
-            tma_load_2d(base + 128 * KP, &tmap_q8, smem_u32(&a_full), 0, (int)q0 + 128);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb)  // operand of query half hh: [K block][128 rows][KW bytes]
+                    tma_load_2d(base + (uint32_t)((hh * KB + kb) * 128 * KW), &tmap_q8, smem_u32(&a_full), kb * KW, (int)q0 + hh * 128);
             tma_load_2d(base + A_BYTES, &tmap_qx, smem_u32(&a_full), 0, (int)q0);
             tma_load_2d(base + A_BYTES + 128 * kUmmaXBytes, &tmap_qx, smem_u32(&a_full), 0, (int)q0 + 128);
             tma_load_2d(base + A_BYTES + AX_BYTES, &tmap_bx, smem_u32(&a_full), 0, 0);
@@ -278,10 +294,14 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
                 const uint32_t sb = base + FIXED_BYTES + s * STAGE_BYTES;
                 const int ra = (int)(rowa + (int64_t)t * kUmmaHalfRows);  // rows of the first split; the second one starts SL rows later
                 const int rb = (int)(rowa + a.SL + (int64_t)t * kUmmaHalfRows);
-                tma_load_2d(sb, &tmap_db8, smem_u32(&full_bar[s]), 0, ra);
-                tma_load_2d(sb + 64 * KP, &tmap_db8, smem_u32(&full_bar[s]), 0, rb);
-                tma_load_2d(sb + B_BYTES, &tmap_rows, smem_u32(&full_bar[s]), 0, ra);
-                tma_load_2d(sb + B_BYTES + half_rows_bytes, &tmap_rows, smem_u32(&full_bar[s]), 0, rb);
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {  // B tile: [K block][64 rows of split a | 64 rows of split b][KW bytes]
+                    tma_load_2d(sb + (uint32_t)(kb * 128 * KW), &tmap_db8, smem_u32(&full_bar[s]), kb * KW, ra);
+                    tma_load_2d(sb + (uint32_t)(kb * 128 * KW + 64 * KW), &tmap_db8, smem_u32(&full_bar[s]), kb * KW, rb);
+                }
+                const int rsh = a.rows_paired ? 1 : 0;  // 2-word rows are boxed as 16-byte pairs: ra, rb are even (tile multiples)
+                tma_load_2d(sb + B_BYTES, &tmap_rows, smem_u32(&full_bar[s]), 0, ra >> rsh);
+                tma_load_2d(sb + B_BYTES + half_rows_bytes, &tmap_rows, smem_u32(&full_bar[s]), 0, rb >> rsh);
             }
         }
     } else if (warp == 1) {
@@ -293,7 +313,7 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
                 const int s = t % S;
                 mbar_wait(&full_bar[s], (uint32_t)((t / S) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t bdesc = umma_desc_kmajor(base + FIXED_BYTES + s * STAGE_BYTES, KP);
+                const uint32_t b_addr = base + FIXED_BYTES + s * STAGE_BYTES;
                 // each query half as soon as ITS eight epilogue warps have read the previous tile's accumulator
                 uint32_t todo = 3u;
                 while (todo) {
@@ -303,10 +323,14 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
                         if (todo == (1u << h)) mbar_wait(&tmem_empty[h], (uint32_t)((t & 1) ^ 1));
                         else if (!mbar_try(&tmem_empty[h], (uint32_t)((t & 1) ^ 1))) continue;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint64_t adesc = umma_desc_kmajor(base + h * 128 * KP, KP);
 #pragma unroll
-                        for (int k = 0; k < KP / 32; ++k)  // UMMA_K = 32 int8 = 32 bytes: start address advances by 2 (x16 B)
-                            umma_i8(tmem_base + (uint32_t)(h * 128), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)(k != 0));
+                        for (int kb = 0; kb < KB; ++kb) {
+                            const uint64_t adesc = umma_desc_kmajor(base + (uint32_t)((h * KB + kb) * 128 * KW), KW);
+                            const uint64_t bdesc = umma_desc_kmajor(b_addr + (uint32_t)(kb * 128 * KW), KW);
+#pragma unroll
+                            for (int k = 0; k < KW / 32; ++k)  // UMMA_K = 32 int8 = 32 bytes: start address advances by 2 (x16 B)
+                                umma_i8(tmem_base + (uint32_t)(h * 128), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                        }
                         // threshold K step: ip' = ip + (2 T_q - b)
                         umma_i8(tmem_base + (uint32_t)(h * 128), umma_desc_kmajor(base + A_BYTES + h * 128 * kUmmaXBytes, kUmmaXBytes), bxdesc, idesc, 1u);
                         umma_commit(&tmem_full[h]);
@@ -328,12 +352,16 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
         const bool valid = slot < a.nq && split < a.P;
         const int W = MODE == 1 ? 2 : (MODE == 2 ? 4 : a.W), LW = a.LW, Wr = WrK;
         const uint32_t sel = a.prmt_sel;
-        uint32_t qw[4] = {0, 0, 0, 0}, ql[4] = {0, 0, 0, 0};
+        uint32_t qw[QW], ql[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int w = 0; w < QW; ++w) qw[w] = 0;
         uint32_t pos = 0, nback = 0, start = 0, end = 0;  // front stack (d < T) grows up from start, back stack (d == T) down from end
         int Tq = -1;
         int64_t bin = -1;
         if (valid) {
-            for (int w = 0; w < W && w < 4; ++w) qw[w] = a.q_rows[slot * Wr + w];
+#pragma unroll
+            for (int w = 0; w < QW; ++w)
+                if (w < W) qw[w] = a.q_rows[slot * Wr + w];
             for (int w = 0; w < LW && w < 4; ++w) ql[w] = a.q_rows[slot * Wr + W + w];
             Tq = a.thr[slot];
             bin = slot * a.P + split;
@@ -378,6 +406,8 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
                 const uint32_t cleared = hm & (hm - 1u);
                 if (first) h0 = cleared; else h1 = cleared;
                 const uint32_t* prow = srows + rl * Wr;
+                if (KP == 32 && a.rows_paired && row0 + (int64_t)t * kUmmaHalfRows + rl == a.ndb - 1)
+                    prow = a.db_rows + (a.ndb - 1) * Wr;  // odd database size: the last row has no pair partner in the TMA box
                 int d = 0;
                 uint32_t m = 0;
                 if (MODE == 1) {
@@ -388,14 +418,15 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
                     const uint4 pc = *reinterpret_cast<const uint4*>(prow), pl = *reinterpret_cast<const uint4*>(prow + 4);
                     d = __popc(qw[0] ^ pc.x) + __popc(qw[1] ^ pc.y) + __popc(qw[2] ^ pc.z) + __popc(qw[3] ^ pc.w);
                     m = (ql[0] & pl.x) | (ql[1] & pl.y) | (ql[2] & pl.z) | (ql[3] & pl.w);
-                } else if (Wr == 4) {  // one 16-byte load brings the code words and the label word(s): W = 2 (+ <= 2 label words) or W = 3 (+ 1)
+                } else if (Wr == 4) {  // one 16-byte load brings the code words and the label word(s): W = 1 (+ <= 3 label words), 2 (+ <= 2) or 3 (+ 1)
                     const uint4 pr = *reinterpret_cast<const uint4*>(prow);
-                    d = __popc(qw[0] ^ pr.x) + __popc(qw[1] ^ pr.y);
-                    if (W == 3) { d += __popc(qw[2] ^ pr.z); m = ql[0] & pr.w; }
-                    else { m = (ql[0] & pr.z) | (ql[1] & pr.w); }
+                    d = __popc(qw[0] ^ pr.x);
+                    if (W == 1) { m = (ql[0] & pr.y) | (ql[1] & pr.z) | (ql[2] & pr.w); }
+                    else if (W == 3) { d += __popc(qw[1] ^ pr.y) + __popc(qw[2] ^ pr.z); m = ql[0] & pr.w; }
+                    else { d += __popc(qw[1] ^ pr.y); m = (ql[0] & pr.z) | (ql[1] & pr.w); }
                 } else {
 #pragma unroll
-                    for (int w = 0; w < 4; ++w)
+                    for (int w = 0; w < QW; ++w)
                         if (w < W) d += __popc(qw[w] ^ prow[w]);
 #pragma unroll
                     for (int w = 0; w < 4; ++w)
@@ -422,28 +453,35 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
-static int make_map_u8(CUtensorMap* map, const uint8_t* ptr, int64_t rows, int row_bytes, int box_rows)
+// [rows, row_bytes] bytes, boxes of box_rows x box_bytes (box_bytes = the swizzle width: 32 / 64 / 128; row_bytes = 256
+// is read as two 128-byte column blocks)
+static int make_map_u8(CUtensorMap* map, const uint8_t* ptr, int64_t rows, int row_bytes, int box_rows, int box_bytes = 0)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(HG_ECUDA, "select_umma: cuTensorMapEncodeTiled is not available from the driver");
+    if (box_bytes == 0) box_bytes = row_bytes;
     cuuint64_t gdim[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)row_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)row_bytes, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_bytes, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUtensorMapSwizzle sw = box_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HG_ECUDA, "select_umma: cuTensorMapEncodeTiled(u8, %d B rows) failed (%d)", row_bytes, (int)r);
     return HG_OK;
 }
 
+// packed rows [rows, Wr] words, boxes of 64 rows; 2-word rows (8 bytes, below the 16-byte minimum of a box row) are
+// described as rows/2 PAIRS of 4 words, boxes of 32 pairs (an odd last row is read from global memory by the kernel)
 static int make_map_rows(CUtensorMap* map, const uint32_t* ptr, int64_t rows, int Wr)
 {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(HG_ECUDA, "select_umma: cuTensorMapEncodeTiled is not available from the driver");
+    int box_rows = kUmmaHalfRows;
+    if (Wr == 2) { Wr = 4; rows = std::max<int64_t>(1, rows / 2); box_rows = kUmmaHalfRows / 2; }
     cuuint64_t gdim[2] = {(cuuint64_t)Wr, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)Wr * 4};
-    cuuint32_t box[2] = {(cuuint32_t)Wr, (cuuint32_t)kUmmaHalfRows};
+    cuuint32_t box[2] = {(cuuint32_t)Wr, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -453,10 +491,12 @@ static int make_map_rows(CUtensorMap* map, const uint32_t* ptr, int64_t rows, in
 
 int umma_select_kp(int b, int Wr)
 {
-    // int8 row bytes; 0 = this shape stays on the POPC kernel (b <= 32: one POPC per pair is already cheap;
-    // b > 128 or a packed-row stride that TMA cannot box: not implemented)
-    if (b <= 32 || b > 128 || (Wr != 4 && Wr != 8)) return 0;
-    return b <= 64 ? 64 : 128;
+    // int8 row bytes; 0 = this shape stays on the POPC kernel (a packed-row stride that TMA cannot box: 3- and 5-word rows,
+    // i.e. b <= 32 with more than 32 labels ... 64 or more than 96)
+    if (b <= 0 || b > 256) return 0;
+    if (b <= 32) return (Wr == 2 || Wr == 4) ? 32 : 0;
+    if (b <= 128) return (Wr == 4 || Wr == 8) ? (b <= 64 ? 64 : 128) : 0;
+    return Wr == 12 ? 256 : 0;
 }
 
 static unsigned grid_for(int64_t threads_needed)
@@ -498,7 +538,7 @@ template <int KP, int MODE>
 static int launch_umma(const CUtensorMap& tq, const CUtensorMap& tdb, const CUtensorMap& trows, const CUtensorMap& tqx, const CUtensorMap& tbx,
                        const UmmaSelectArgs& a, cudaStream_t st)
 {
-    const size_t smem = (size_t)2 * 128 * KP + (size_t)3 * 128 * kUmmaXBytes + (size_t)UmmaCfg<KP>::S * (128 * KP + kUmmaRowsMax) + 1024;
+    const size_t smem = (size_t)2 * 128 * KP + (size_t)3 * 128 * kUmmaXBytes + (size_t)UmmaCfg<KP>::S * (128 * KP + UmmaCfg<KP>::ROWS_BYTES) + 1024;
     static thread_local bool configured = false;
     if (!configured) {
         HG_CUDA_TRY(cudaFuncSetAttribute(select_umma_kernel<KP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -522,13 +562,17 @@ int umma_select_launch(const UmmaSelectArgs& a_in, cudaStream_t st)
     CUtensorMap tq, tdb, trows, tqx, tbx;
     int rc;
     if (a.split0 & 1) return fail(HG_EINVAL, "select_umma: a launch must start at an even split");
-    if ((rc = make_map_u8(&tq, a.q8, a.nq, a.KP, 128)) != HG_OK) return rc;
-    if ((rc = make_map_u8(&tdb, a.db8, round_up(a.ndb, 32), a.KP, kUmmaHalfRows)) != HG_OK) return rc;
+    const int kw = a.KP > 128 ? 128 : a.KP;
+    a.rows_paired = a.Wr == 2 ? 1 : 0;
+    if ((rc = make_map_u8(&tq, a.q8, a.nq, a.KP, 128, kw)) != HG_OK) return rc;
+    if ((rc = make_map_u8(&tdb, a.db8, round_up(a.ndb, 32), a.KP, kUmmaHalfRows, kw)) != HG_OK) return rc;
     if ((rc = make_map_rows(&trows, a.db_rows, a.ndb, a.Wr)) != HG_OK) return rc;
     if ((rc = make_map_u8(&tqx, a.qx, std::max<int64_t>(round_up(a.nq, 256), 128), kUmmaXBytes, 128)) != HG_OK) return rc;
     if ((rc = make_map_u8(&tbx, a.bx, 128, kUmmaXBytes, kUmmaHalfRows)) != HG_OK) return rc;
+    if (a.KP == 32) return launch_umma<32, 0>(tq, tdb, trows, tqx, tbx, a, st);
     if (a.KP == 64) return (a.W == 2 && a.Wr == 4) ? launch_umma<64, 1>(tq, tdb, trows, tqx, tbx, a, st) : launch_umma<64, 0>(tq, tdb, trows, tqx, tbx, a, st);
-    return (a.W == 4 && a.Wr == 8) ? launch_umma<128, 2>(tq, tdb, trows, tqx, tbx, a, st) : launch_umma<128, 0>(tq, tdb, trows, tqx, tbx, a, st);
+    if (a.KP == 128) return (a.W == 4 && a.Wr == 8) ? launch_umma<128, 2>(tq, tdb, trows, tqx, tbx, a, st) : launch_umma<128, 0>(tq, tdb, trows, tqx, tbx, a, st);
+    return launch_umma<256, 0>(tq, tdb, trows, tqx, tbx, a, st);
 }
 
 

@@ -134,7 +134,7 @@ class AlexNetHashEncoder:
     """images (uint8, [B, 3*wh*wh] as the loader yields them, lib/dataloader.py:110-113) -> CUDA float32 [B, HASH_DIM]."""
 
     def __init__(self, weights: AlexNetWeights, *, lrn: bool = True, device=None, conv_tf32: bool = False, deterministic: bool = True,
-                 seed: int = 0, conv: Optional[str] = None):
+                 seed: int = 0, conv: Optional[str] = None, fused_stage1: bool = True):
         import torch
 
         if not torch.cuda.is_available():
@@ -151,6 +151,10 @@ class AlexNetHashEncoder:
             raise ValueError("conv must be 'fp32', 'tf32' or 'tf32x3'")
         conv_tf32 = self.conv != "fp32"
         self.conv_tf32 = conv_tf32
+        # fused_stage1: normalise + resize + 10-crop + mean + conv1 + ReLU + pool1 (+LRN) as one kernel on effective filters
+        # (csrc/encoder_stage1.cu) for 32 x 32 and 64 x 64 images; False = the separate kernels (any image size)
+        self.fused_stage1 = bool(fused_stage1)
+        self._fused = {}  # wh -> packed effective conv1 filters
         # deterministic=False: the reference's stochastic eval graph (de-quantisation noise main.py:147, dropout at eval
         # architecture.py:369,377); every encode() call draws with a fresh seed derived from `seed` and the call count
         self.deterministic = deterministic
@@ -225,6 +229,15 @@ class AlexNetHashEncoder:
             flags = (_native.ENC_LRN if self.lrn else 0) | {"fp32": 0, "tf32": _native.ENC_CONV_TF32, "tf32x3": _native.ENC_CONV_TF32X3}[self.conv]
             if self.timing:
                 flags |= _native.ENC_TIMING
+            if self.fused_stage1 and self.lib.hg_conv1_fused_floats(wh) > 0:
+                if wh not in self._fused:
+                    buf = torch.empty((self.lib.hg_conv1_fused_floats(wh),), dtype=torch.float32, device=dev)
+                    _native.check(self.lib.hg_conv1_fused_pack(self._keep["discriminator.conv1.weights"].data_ptr(), wh, buf.data_ptr(),
+                                                               torch.cuda.current_stream(dev).cuda_stream))
+                    self._fused[wh] = buf
+                self._struct.conv1_fused = self._fused[wh].data_ptr()
+                self._struct.conv1_fused_wh = wh
+                flags |= _native.ENC_FUSED_STAGE1
             need = self.lib.hg_alexnet_workspace_bytes(n, flags)
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty((need,), dtype=torch.uint8, device=dev)

@@ -18,7 +18,7 @@ import numpy as np
 
 from .metric import MAPs
 
-__all__ = ["forward_all", "evaluate"]
+__all__ = ["forward_all", "evaluate", "periodic_evaluate", "scalar_summary", "ScalarLog"]
 
 
 def _dist_info(group=None):
@@ -76,9 +76,10 @@ def forward_all(encoder, data_generator, size, cfg, shard=None):
     return SimpleNamespace(output=output, label=label)
 
 
-def evaluate(encoder, dataloader, cfg, metric=None, group=None):
+def evaluate(encoder, dataloader, cfg, metric=None, group=None, precision_recall: bool = False):
     """main.py:161-164.  With an initialised process group of more than one rank the splits are encoded in contiguous blocks
-    per rank and ranked by ShardedMAPs; every rank returns the same value."""
+    per rank and ranked by ShardedMAPs; every rank returns the same value.  precision_recall=True (single process) returns the
+    dict of MAPs.precision_recall (precision@R, recall@R, mAP on one ranking) instead of the scalar."""
     rank, world = _dist_info(group)
     ev = getattr(cfg, "EVAL", None)
     shard = (rank, world) if world > 1 else None
@@ -108,4 +109,48 @@ def evaluate(encoder, dataloader, cfg, metric=None, group=None):
     elif metric is None:
         # EVAL.BINARIZE False = the reference's literal ranking of the raw tanh outputs (lib/metric.py:13-14)
         metric = MAPs(cfg.DATA.MAP_R, binarize=bool(getattr(ev, "BINARIZE", True)))
+    if precision_recall:
+        if not hasattr(metric, "precision_recall"):
+            raise NotImplementedError("precision@R / recall@R are computed by MAPs (single process); run without torchrun")
+        return metric.precision_recall(db, test)
     return metric.get_maps_by_feature(db, test)
+
+
+def scalar_summary(tag, value):
+    """lib/util.py:60-61 builds a one-value tf.Summary; without TensorFlow the record is the (tag, simple_value) pair itself."""
+    return SimpleNamespace(tag=tag, simple_value=float(value))
+
+
+class ScalarLog:
+    """Stand-in for the tf.summary.FileWriter of main.py:176: `add_summary(summary, step)` appends one JSON line per scalar to
+    <LOG_DIR>/scalars.jsonl (TensorBoard event files are out of scope; the call signature is the reference's)."""
+
+    def __init__(self, log_dir):
+        import os
+
+        os.makedirs(log_dir, exist_ok=True)
+        self.path = os.path.join(log_dir, "scalars.jsonl")
+
+    def add_summary(self, summary, global_step=None):
+        import json
+
+        with open(self.path, "a") as fh:
+            fh.write(json.dumps({"tag": summary.tag, "value": summary.simple_value, "step": None if global_step is None else int(global_step)}) + "\n")
+
+
+def periodic_evaluate(iteration, encoder, dataloader, cfg, summary_writer=None, metric=None, group=None):
+    """The in-training evaluation hook, main.py:236-240: a training loop calls this once per iteration; every
+    TRAIN.EVAL_FREQUENCY iterations and on the last one (TRAIN.ITERS) it evaluates, prints `map_val: ...` and logs the scalar
+    `mAP_feature` at step `iteration` -- exactly the reference's condition, line and tag.  Returns map_val, or None when this
+    iteration does not evaluate.  `encoder` is the handle that stands for (session, model): a trainer refreshes its weights
+    before the call (training itself is out of scope)."""
+    due = (iteration + 1) % cfg.TRAIN.EVAL_FREQUENCY == 0 or iteration + 1 == cfg.TRAIN.ITERS   # main.py:237
+    if not due:
+        return None
+    map_val = evaluate(encoder, dataloader, cfg, metric=metric, group=group)                      # main.py:238
+    rank, _ = _dist_info(group)
+    if rank == 0:
+        print('map_val: {}'.format(map_val))                                                      # main.py:239
+        if summary_writer is not None:
+            summary_writer.add_summary(scalar_summary("mAP_feature", map_val), iteration)         # main.py:240
+    return map_val

@@ -107,10 +107,15 @@ int hg_hamming_map_stats(const void* d_workspace, size_t workspace_bytes, int64_
  * Synchronises on the last event. */
 int hg_hamming_map_phase_ms(float out[6]);
 
-/* Which all-pairs kernel hg_hamming_map uses for this shape: 0 = select_kernel (XOR/POPC on the integer pipe),
- * 64 / 128 = select_umma_kernel (exact int8 tcgen05.mma, int8 row bytes); -1 = unsupported shape.
- * The environment variable HG_SELECT_BACKEND=popc forces 0. */
+/* Which all-pairs kernel the row shape (b, L) can run on: 0 = select_kernel only (XOR/POPC on the integer pipe),
+ * 32 / 64 / 128 / 256 = select_umma_kernel (exact int8 tcgen05.mma; the value is the int8 row width: b <= 32, <= 64, <= 128,
+ * <= 256); -1 = unsupported shape.  The environment variable HG_SELECT_BACKEND=popc forces 0. */
 int hg_select_backend(int b, int L);
+
+/* The kernel hg_hamming_map really uses for a whole problem (same values): short codes (b <= 32) keep the POPC kernel when
+ * the top-R is a large part of the database (R * 8 > ndb, e.g. cifar_evaluation.yaml's MAP_R == DB_SIZE), where every pair
+ * is a candidate and the tensor-core kernel's cheap rejection buys nothing.  HG_SELECT_BACKEND=umma lifts that rule. */
+int hg_select_backend_for(int64_t nq, int64_t ndb, int b, int L, int64_t R);
 
 /* Real-valued ranking mode -- the reference's literal behaviour on un-binarised features:
  *   lib/metric.py:13  ips = np.dot(query.output, database.output.T)   fp32 inner products (FMA, increasing k)
@@ -184,10 +189,14 @@ typedef struct HgAlexNetWeights {
     const float* conv_wt[5];  /* tensor-core convolutions: hg_conv_weight_pack of conv_w[i] */
     const float* fc_wt3[3];   /* optional, HG_ENC_CONV_TF32X3: hg_conv_weight_pack(W, 1, 1, K, N, 1) of the fc6 / fc7 / fc8 matrices
                                * [K, N]; when present the dense layers also run error-compensated (fp32-grade end to end) */
+    const float* conv1_fused; /* optional, HG_ENC_FUSED_STAGE1: hg_conv1_fused_pack of conv_w[0] for images of conv1_fused_wh pixels */
+    int conv1_fused_wh;
 } HgAlexNetWeights;
 
 #define HG_ENC_LRN 1u        /* local response normalisation after pool1/pool2: on iff TRAIN.WGAN_SCALE == 0 (architecture.py:268,294) */
 #define HG_ENC_CONV_TF32 2u  /* opt-in: conv1-5 as implicit GEMM on tcgen05 with plain TF32 operands (6x faster than the fp32 CUDA cores, ~1e-3 relative error) */
+#define HG_ENC_FUSED_STAGE1 32u /* normalise + resize + 10-crop + mean + conv1 + ReLU + pool1 (+ LRN) as ONE kernel on effective filters
+                                 * (csrc/encoder_stage1.cu): needs conv1_fused packed for this wh (32 or 64) */
 #define HG_ENC_TIMING 16u    /* record CUDA events between the stages of this call (diagnostics): hg_alexnet_phase_ms */
 #define HG_ENC_CONV_TF32X3 8u /* conv1-5 (and fc6-8 when fc_wt3 is set) as implicit GEMM on tcgen05 with error-compensated TF32 (hi/lo split, 3 MMAs): fp32-grade accuracy */
 
@@ -198,6 +207,14 @@ size_t hg_alexnet_workspace_bytes(int n, unsigned flags);
  * to a multiple of 4, Kpad = KH*KW*Cg4 rounded up to 32, zero padded): the B operand of the tensor-core convolution.  d_out holds 2 * Cout * Kpad floats: first the upper 19 bits of
  * every weight (exactly TF32), then the remainders w - hi used by the error-compensated mode (HG_ENC_CONV_TF32X3). */
 int hg_conv_weight_pack(const float* d_w_hwio, int KH, int KW, int Cg, int Cout, int groups, float* d_out, void* stream);
+
+/* Effective conv1 filters of the fused first stage (HG_ENC_FUSED_STAGE1).  Resize (lib/util.py:19), crop offset, flip
+ * (lib/architecture.py:215-244) and conv1 (:253-258) are linear and compose exactly: per crop type (corner / centre x plain /
+ * flipped) and per phase of the output pixel in the source grid, an 11 x 11 filter over the 256-pixel image becomes a
+ * WIN x WIN filter (4 for wh = 32, 5 for wh = 64) over the SOURCE image.  d_conv1_hwio: discriminator.conv1.weights
+ * [11, 11, 3, 96]; d_out: hg_conv1_fused_floats(wh) floats (0 = this image size is not supported: use the unfused path). */
+size_t hg_conv1_fused_floats(int wh);
+int hg_conv1_fused_pack(const float* d_conv1_hwio, int wh, float* d_out, void* stream);
 
 /* d_images: uint8 [n, 3, wh, wh], RGB planes -- the loader's flattened batch (lib/dataloader.py:110-113), wh <= 256.
  * d_out: float32 [n, hash_dim].  Deterministic mode only: no de-quantisation noise (main.py:147) and no eval-time

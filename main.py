@@ -59,7 +59,12 @@ def main(cfg):
                                          {"database": cfg.DATA.DB_SIZE, "test": cfg.DATA.TEST_SIZE}, cfg.EVAL.SEED)
     else:
         raise SystemExit("{} / {} not found (set EVAL.SYNTHETIC: True for seeded synthetic images)".format(cfg.DATA.DATA_ROOT, cfg.DATA.LIST_ROOT))
-    map_val = evaluate(encoder, dataloader, cfg)
+    pr = None
+    if cfg.EVAL.PRECISION_RECALL and world == 1:
+        pr = evaluate(encoder, dataloader, cfg, precision_recall=True)
+        map_val = pr["mAP"]
+    else:
+        map_val = evaluate(encoder, dataloader, cfg)
     if rank == 0:
         # the reference ranks the raw crop-averaged tanh outputs by inner product (lib/metric.py:13-14); the B200 hot path
         # (EVAL.BINARIZE True, the default) ranks their signs by Hamming distance -- identical on +-1 codes only
@@ -67,6 +72,11 @@ def main(cfg):
                                    'real-valued inner-product ranking)' if cfg.EVAL.BINARIZE else
                                    'real-valued inner product of the raw outputs (EVAL.BINARIZE False, lib/metric.py:13-14)'))
         print('map_val: {}'.format(map_val))
+        if pr is not None:
+            print('precision@{}: {}'.format(pr["R"], pr["precision"]))
+            print('recall@{}: {}'.format(pr["R"], pr["recall"]))
+        elif cfg.EVAL.PRECISION_RECALL:
+            print('precision/recall: skipped (EVAL.PRECISION_RECALL is computed by the single-process metric; run without torchrun)')
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -123,7 +123,15 @@ def test_row_layout_rules():
             if W in (4, 8):
                 assert Wr % 4 == 0
             if 32 < b <= 128:
-                assert Wr in (4, 8) and lib.hg_select_backend(b, L) in (64, 128)
-            else:
-                assert lib.hg_select_backend(b, L) == 0
+                assert Wr in (4, 8) and lib.hg_select_backend(b, L) == (64 if b <= 64 else 128)
+            elif b > 128:
+                assert Wr == 12 and lib.hg_select_backend(b, L) == 256        # two 128-byte K blocks
+            else:  # short codes: 8- or 16-byte rows go through TMA (2-word rows as pairs), 3- and 5-word rows stay on POPC
+                assert lib.hg_select_backend(b, L) == (32 if Wr in (2, 4) else 0)
     assert lib.hg_code_words(0) == 0 and lib.hg_code_words(257) == 0 and lib.hg_label_words(129) == 0 and lib.hg_row_words(64, 0) == 0
+    # the kernel a whole problem gets: short codes leave the POPC kernel only for a sparse top-R (make_plan)
+    assert lib.hg_select_backend_for(1000, 54000, 32, 10, 54000) == 0          # C1: MAP_R == DB_SIZE
+    assert lib.hg_select_backend_for(1000, 1000000, 32, 10, 5000) == 32
+    assert lib.hg_select_backend_for(10000, 1000000, 64, 10, 5000) == 64
+    assert lib.hg_select_backend_for(100, 100000, 200, 10, 5000) == 256
+    assert lib.hg_select_backend_for(100, 1000, 64, 10, 5000) == -1             # R > ndb: no plan

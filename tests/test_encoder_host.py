@@ -67,3 +67,39 @@ def test_alexnet_npy_import_follows_the_reference_dict_layout(tmp_path):
     lim = np.sqrt(2.0 / (4096 + 64)) * np.sqrt(3.0)                      # Glorot uniform, lib/ops.py:213-218
     assert W8.shape == (4096, 64) and np.abs(W8).max() <= lim and W8.std() > 0.4 * lim
     assert not w.tensors["discriminator.ACGANOutput.b"].any()
+
+
+def test_periodic_evaluate_follows_the_reference_schedule(tmp_path, capsys):
+    """main.py:236-240: evaluate every TRAIN.EVAL_FREQUENCY iterations and on the last one, print `map_val: ...`, log the
+    scalar `mAP_feature` at that step.  The metric is injected, so no GPU is involved."""
+    import json
+    from types import SimpleNamespace as NS
+
+    import torch
+
+    from hashgan_b200 import evaluate as ev
+    from hashgan_b200.dataloader import SyntheticDataloader
+
+    cfg = NS(MODEL=NS(HASH_DIM=8), DATA=NS(DB_SIZE=20, TEST_SIZE=6, LABEL_DIM=3, MAP_R=5), TRAIN=NS(BATCH_SIZE=4, EVAL_FREQUENCY=5, ITERS=12),
+             EVAL=NS(SEED=1, BINARIZE=True, DETERMINISTIC=True))
+    loader = SyntheticDataloader(4, 2, 3, {"database": 20, "test": 6}, seed=2)
+    enc = lambda image: torch.from_numpy(np.asarray(image, dtype=np.float32)[:, :8] / 255.0 - 0.5)  # noqa: E731
+    calls = []
+
+    class FakeMetric:
+        def get_maps_by_feature(self, db, q):
+            assert tuple(db.output.shape) == (20, 8) and tuple(q.output.shape) == (6, 8)
+            calls.append(1)
+            return np.float64(0.25 + 0.125 * len(calls))
+
+    log = ev.ScalarLog(str(tmp_path / "logs"))
+    got = [ev.periodic_evaluate(it, enc, loader, cfg, summary_writer=log, metric=FakeMetric()) for it in range(cfg.TRAIN.ITERS)]
+    due = [it for it, v in enumerate(got) if v is not None]
+    assert due == [4, 9, 11]                                       # (it + 1) % 5 == 0, and the last iteration
+    lines = [json.loads(ln) for ln in open(log.path)]
+    assert [(ln["tag"], ln["step"]) for ln in lines] == [("mAP_feature", 4), ("mAP_feature", 9), ("mAP_feature", 11)]
+    assert [ln["value"] for ln in lines] == [0.375, 0.5, 0.625]
+    printed = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("map_val: ")]
+    assert printed == ["map_val: 0.375", "map_val: 0.5", "map_val: 0.625"]
+    s = ev.scalar_summary("mAP_feature", 0.5)
+    assert (s.tag, s.simple_value) == ("mAP_feature", 0.5)

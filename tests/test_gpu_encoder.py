@@ -71,6 +71,61 @@ def test_alexnet_encoder_matches_fp32_oracle():
         assert 0.2 < np.abs(want).mean() < 0.999  # the test exercises the unsaturated range of tanh
 
 
+def test_encoder_at_the_configured_batch_of_128():
+    """cifar_evaluation.yaml runs batches of 128 images (1280 crops) -- a different grid / tile regime from
+    the small batches of the other tests.  Default (error-compensated tensor-core) path against the fp32 oracle, every image."""
+    from hashgan_b200.encoder import AlexNetHashEncoder, AlexNetWeights
+    from oracle import alexnet_oracle
+
+    w = AlexNetWeights.synthetic(64, seed=21)
+    img = np.random.default_rng(8).integers(0, 256, (128, 3 * 32 * 32), dtype=np.uint8)
+    want = np.concatenate([alexnet_oracle.encode(img[i:i + 32], w.tensors, 32, lrn=True) for i in range(0, 128, 32)])
+    enc = AlexNetHashEncoder(w, lrn=True)
+    got = enc(img).cpu().numpy()
+    assert got.shape == (128, 64)
+    assert np.abs(got - want).max() <= 5e-4
+    safe = np.abs(want) > 2e-3
+    assert np.array_equal(got[safe] > 0, want[safe] > 0)
+    # batch invariance: the same image gives the same code whatever batch it travels in
+    again = enc(img[40:52]).cpu().numpy()
+    assert np.abs(again - got[40:52]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("wh,conv", [(64, "tf32x3"), (64, "fp32"), (16, "tf32x3")])
+def test_encoder_other_image_sizes(wh, conv):
+    """DATA.WIDTH_HEIGHT: 64 (config/nuswide_step_1.yaml:12) -- legacy bilinear 64 -> 256 (scale 1/4) instead of 32 -> 256."""
+    from hashgan_b200.encoder import AlexNetHashEncoder, AlexNetWeights
+    from oracle import alexnet_oracle
+
+    n = 5
+    yy, xx = np.meshgrid(np.arange(wh), np.arange(wh), indexing="ij")
+    img = np.stack([np.stack([(7 * yy + 3 * xx + 11 * i) % 256, (5 * yy * (i + 1) + xx) % 256, (yy * xx + 40 * i) % 256]) for i in range(n)]).astype(np.uint8)
+    img[3:] = np.random.default_rng(2).integers(0, 256, img[3:].shape, dtype=np.uint8)
+    w = AlexNetWeights.synthetic(48, seed=13)
+    want = alexnet_oracle.encode(img.reshape(n, -1), w.tensors, wh, lrn=True)
+    got = AlexNetHashEncoder(w, lrn=True, conv=conv)(img.reshape(n, -1)).cpu().numpy()
+    # "fp32" = CUDA-core convolutions + plain-TF32 dense layers (10-bit mantissa): the looser bound of DESIGN.md section 2
+    assert np.abs(got - want).max() <= (5e-4 if conv == "tf32x3" else 5e-3)
+
+
+@pytest.mark.parametrize("wh,lrn,conv", [(32, True, "tf32x3"), (32, False, "fp32"), (64, True, "tf32x3")])
+def test_fused_first_stage_equals_the_separate_kernels(wh, lrn, conv):
+    """csrc/encoder_stage1.cu composes resize + crop + flip + conv1 into effective filters (exact algebra) and fuses pool1 + LRN:
+    against the separate kernels the outputs may differ only by fp32 summation order (and the separate tensor-core conv1's
+    own rounding), in the deterministic and in the stochastic mode; structured images expose offset / flip / phase mistakes."""
+    from hashgan_b200.encoder import AlexNetHashEncoder, AlexNetWeights
+
+    n = 7
+    yy, xx = np.meshgrid(np.arange(wh), np.arange(wh), indexing="ij")
+    img = np.stack([np.stack([(7 * yy + 3 * xx + 11 * i) % 256, (5 * yy * (i + 1) + xx) % 256, (yy * xx + 40 * i) % 256]) for i in range(n)]).astype(np.uint8)
+    img[4:] = np.random.default_rng(3).integers(0, 256, img[4:].shape, dtype=np.uint8)
+    w = AlexNetWeights.synthetic(64, seed=17)
+    for deterministic in (True, False):
+        a = AlexNetHashEncoder(w, lrn=lrn, conv=conv, fused_stage1=True, deterministic=deterministic, seed=5)(img.reshape(n, -1)).cpu().numpy()
+        b = AlexNetHashEncoder(w, lrn=lrn, conv=conv, fused_stage1=False, deterministic=deterministic, seed=5)(img.reshape(n, -1)).cpu().numpy()
+        assert np.abs(a - b).max() <= 2e-4, (deterministic, np.abs(a - b).max())
+
+
 def test_encoder_stages_match_oracle():
     """Stage-by-stage check of the fused prep kernel (normalize + legacy bilinear + 10-crop + mean) through conv1."""
     import torch
