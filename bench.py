@@ -317,7 +317,10 @@ def run_encoder(args):
         _native.check(lib.hg_alexnet_phase_ms(phase))
         phase_acc += np.array(phase[:], dtype=np.float64)
     enc.timing = False
-    phases = dict(zip(("prep_crops", "conv1_5", "pool_lrn", "fc6_8", "tanh_crop_mean"), (phase_acc / n_phase).tolist()))
+    fused = bool(enc.fused_stage1 and lib.hg_conv1_fused_floats(32) > 0)
+    names = (("fused_stage1_crops_conv1_pool1_lrn1", "conv2_5", "pool2_lrn2_pool5", "fc6_8", "tanh_crop_mean") if fused
+             else ("prep_crops", "conv1_5", "pool_lrn", "fc6_8", "tanh_crop_mean"))
+    phases = dict(zip(names, (phase_acc / n_phase).tolist()))
     # e2e: uint8 host batches in, float32 codes out, every step
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     out_host = torch.empty((B, b), dtype=torch.float32).pin_memory()
@@ -370,12 +373,13 @@ def run_encoder(args):
     passes = 3 if conv == "tf32x3" else 1
     crops = 10 * B
     flop_useful = 2.0 * crops * (ENC_MAC_PER_CROP["conv"] + ENC_MAC_PER_CROP["dense"])
-    conv_exec = 2.0 * crops * ENC_MAC_PER_CROP["conv"] * (passes if conv != "fp32" else 0)
+    conv_mac = ENC_MAC_PER_CROP["conv"] - (105.4e6 if fused else 0.0)   # the fused first stage runs conv1 on the CUDA cores (13.9 M MAC per crop, exact fp32)
+    conv_exec = 2.0 * crops * conv_mac * (passes if conv != "fp32" else 0)
     dense_exec = 2.0 * crops * ENC_MAC_PER_CROP["dense"] * passes
     tf32_peak = _tf32_peak(torch, device)
-    conv_ms = phases["conv1_5"]
+    conv_ms = phases["conv2_5" if fused else "conv1_5"]
     achieved = conv_exec / (conv_ms * 1e-3) / 1e12 if conv_exec else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv_gemm_tf32_kernel (conv1-5, implicit GEMM on tcgen05 kind::tf32)", "achieved": achieved, "peak": tf32_peak,
+    roofline = {"bound": "tensor", "kernel": f"conv_gemm_tf32_kernel ({'conv2-5' if fused else 'conv1-5'}, implicit GEMM on tcgen05 kind::tf32)", "achieved": achieved, "peak": tf32_peak,
                 "unit": "TFLOP/s", "frac": achieved / tf32_peak if tf32_peak else None, "traffic": None,
                 "peak_source": "measured in this run: cuBLAS TF32 matmul 8192^3, best of 10",
                 "kernel_ms": conv_ms, "executed_flop_per_step": conv_exec,
@@ -385,7 +389,7 @@ def run_encoder(args):
     line = {
         "metric": ENC_METRIC, "value": world * B / (ms * 1e-3), "unit": ENC_UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if conv != "fp32" else "f32", "data": "synthetic",
-        "config": {"workload": "C3: AlexNet hash-head forward (conv1-5 + fc6-8, 10 crops), 54k db images 32x32, B=128, 64-bit", "conv": conv,
+        "config": {"workload": "C3: AlexNet hash-head forward (conv1-5 + fc6-8, 10 crops), 54k db images 32x32, B=128, 64-bit", "conv": conv, "fused_stage1": fused,
                    "l2": "no flush: every step streams > 1 GB of activations, far beyond the 126 MB L2", "parallelism": f"batches sharded x{world}" if world > 1 else "1 GPU"},
         "warmup_steps_run": n_warm, "roofline": roofline, "parity": parity,
         "full_db": {"images": n_db, "batches": nb_all, "seconds": full_ms * 1e-3, "images_per_s": n_db / (full_ms * 1e-3)},

