@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 namespace hg {
 
@@ -151,7 +152,7 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
     }
     {
         const int64_t hist_qt = ceil_div(nq, kHistThreads);
-        int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(p.n_seg, ceil_div((int64_t)sms * 4, hist_qt)));
+        int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(p.n_seg, ceil_div((int64_t)sms * env_int("HG_HIST_CTAS_PER_SM", 4), hist_qt)));
         p.seg_per_chunk = (int)ceil_div(p.n_seg, chunks);
         p.n_chunks = (int)ceil_div(p.n_seg, p.seg_per_chunk);
     }
@@ -236,14 +237,17 @@ struct HistParams {
     int out_chunks;  // 1 -> all chunks accumulate into one histogram per query
 };
 
-template <int W>
+// NARROW: 16-bit counters (a CTA sees fewer than 65536 rows: the sample pass) -- half the shared memory, so nine instead of
+// five CTAs are resident per SM in this latency-bound kernel; updated by plain load/add/store (there is no 16-bit atomic).
+template <int W, bool NARROW>
 __global__ void __launch_bounds__(kHistThreads) hist_kernel(HistParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
+    using CT = typename std::conditional<NARROW, uint16_t, uint32_t>::type;
     const int nbins = p.b + 1;
     const int Wr = p.Wr;
-    uint32_t* tile = smem;                              // [seg_rows * Wr], 16-byte aligned
-    uint32_t* h = smem + (size_t)p.seg_rows * Wr;       // [nbins][kHistThreads]
+    uint32_t* tile = smem;                                               // [seg_rows * Wr], 16-byte aligned
+    CT* h = reinterpret_cast<CT*>(smem + (size_t)p.seg_rows * Wr);       // [nbins][kHistThreads]
     const int tid = threadIdx.x;
     const int64_t n_act = p.qlist ? (int64_t)*p.n_active : p.nq;
     const int64_t slot0 = (int64_t)blockIdx.x * kHistThreads;
@@ -274,11 +278,15 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(HistParams p)
                 uint32_t v[W];
                 load_code<W>(tile + j * Wr, v);
                 const int d = hamming<W>(qw, v);
-                // a reduction without a result (ATOMS.POPC.INC with no destination): the column is private to this thread, the
-                // point is that nothing waits for the value -- a plain `+= 1` chains load -> add -> store per row.  Measured
-                // on B200 (C4): 0.164 -> 0.139 ms.  (The AP kernel's counters need the old value back; there the atomic with
-                // a result is 2x SLOWER than load/add/store -- measured 0.43 -> 0.85 ms -- so it keeps the plain form.)
-                atomicAdd(&h[d * kHistThreads + tid], 1u);
+                if (NARROW) {
+                    h[d * kHistThreads + tid] = (CT)(h[d * kHistThreads + tid] + 1);
+                } else {
+                    // a reduction without a result (ATOMS.POPC.INC with no destination): the column is private to this thread, the
+                    // point is that nothing waits for the value -- a plain `+= 1` chains load -> add -> store per row.  Measured
+                    // on B200 (C4 sample pass): 0.164 -> 0.139 ms.  (The AP kernel's counters need the old value back; there the
+                    // atomic with a result is 2x SLOWER than load/add/store -- measured 0.43 -> 0.85 ms -- so it keeps the plain form.)
+                    atomicAdd(reinterpret_cast<uint32_t*>(h) + d * kHistThreads + tid, 1u);
+                }
             }
         }
     }
@@ -599,12 +607,15 @@ template <bool WINDOW>
 __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
+    // WINDOW: 16-bit counters (ranks below 65536: a query with more closer-than-threshold candidates goes to the wide list) --
+    // half the shared memory per thread, so more CTAs are resident in this latency-bound kernel
+    using CT = typename std::conditional<WINDOW, uint16_t, uint32_t>::type;
     const int NTB = blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const int nb = p.b + 1;
     const int ncol = WINDOW ? 32 : nb;               // counters per thread and kind
-    uint32_t* cN = smem + tid;                        // cN[c * NTB]: count per distance  -> rank base
-    uint32_t* cM = smem + (size_t)ncol * NTB + tid;   // cM[c * NTB]: relevant per distance -> relevant base
+    CT* cN = reinterpret_cast<CT*>(smem) + tid;      // cN[c * NTB]: count per distance  -> rank base
+    CT* cM = cN + (size_t)ncol * NTB;                // cM[c * NTB]: relevant per distance -> relevant base
     const int G = p.G;
     const bool exact = p.bins_by_slot != 0;
     const int64_t n_act = p.qlist ? (int64_t)*p.n_active : p.nq;
@@ -684,8 +695,8 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
         walk([&](uint32_t ent, int64_t) {
             const uint32_t d = (ent >> kIdxBits) & kDistMask;
             const uint32_t c = col(d);
-            cN[c] += 1u;
-            cM[c] += ent >> 31;
+            cN[c] = (CT)(cN[c] + 1u);
+            cM[c] = (CT)(cM[c] + (ent >> 31));
             if (WINDOW) { dmin = min(dmin, d); dmax = max(dmax, d); }
         });
     }
@@ -694,7 +705,7 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
             dmin = min(dmin, __shfl_xor_sync(FULL, dmin, o));
             dmax = max(dmax, __shfl_xor_sync(FULL, dmax, o));
         }
-        if (live && dmax - dmin >= 32u) {
+        if (live && (dmax - dmin >= 32u || total1 >= 65536ull)) {
             if (g == 0) {
                 const int i = atomicAdd(p.n_wide, 1);
                 p.wide_list[i] = (int)q;
@@ -718,8 +729,8 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
             }
             const uint32_t totN = __shfl_sync(FULL, iN, G - 1, G);
             const uint32_t totM = __shfl_sync(FULL, iM, G - 1, G);
-            cN[c] = cn + (iN - vN);
-            cM[c] = cm + (iM - vM);
+            cN[c] = (CT)(cn + (iN - vN));
+            cM[c] = (CT)(cm + (iM - vM));
             cn += totN; cm += totM;
         }
     }
@@ -735,8 +746,8 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
             const uint32_t c = col(d);
             const uint32_t rank = cN[c] + 1u;
             const uint32_t cum = cM[c] + m;
-            cN[c] = rank;
-            cM[c] = cum;
+            cN[c] = (CT)rank;
+            cM[c] = (CT)cum;
             if (rank <= R32) {
                 if (p.ids) p.ids[q * p.R + (rank - 1u)] = (uint32_t)(row0 + (ent & kIdxMask));
                 if (p.dist) p.dist[q * p.R + (rank - 1u)] = (uint16_t)d;
@@ -896,14 +907,27 @@ __global__ void __launch_bounds__(kApWarps * 32) exact_plan_kernel(ExactPlanPara
 template <int W>
 static int launch_hist(const HistParams& hp, int64_t n_slots_max, int n_chunks, cudaStream_t st)
 {
-    const size_t smem = sizeof(uint32_t) * ((size_t)(hp.b + 1) * kHistThreads + (size_t)hp.seg_rows * hp.Wr);
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        HG_CUDA_TRY(cudaFuncSetAttribute(hist_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    // 16-bit counters (half the shared memory, nine resident CTAs instead of five) were measured on B200: 0.146-0.166 ms for
+    // the C4 sample pass against 0.138 ms with 32-bit result-less atomics -- the load/add/store chain costs more than the
+    // occupancy buys.  HG_HIST_NARROW=1 selects them for experiments.
+    const bool narrow = env_int("HG_HIST_NARROW", 0) != 0 && (int64_t)hp.seg_per_chunk * hp.seg_rows < 65536;
+    const size_t smem = (narrow ? sizeof(uint16_t) : sizeof(uint32_t)) * (size_t)(hp.b + 1) * kHistThreads + sizeof(uint32_t) * (size_t)hp.seg_rows * hp.Wr;
     dim3 grid((unsigned)ceil_div(n_slots_max, kHistThreads), (unsigned)n_chunks);
-    hist_kernel<W><<<grid, kHistThreads, smem, st>>>(hp);
+    if (narrow) {
+        static thread_local size_t configured = 0;
+        if (smem > configured) {
+            HG_CUDA_TRY(cudaFuncSetAttribute(hist_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        hist_kernel<W, true><<<grid, kHistThreads, smem, st>>>(hp);
+    } else {
+        static thread_local size_t configured = 0;
+        if (smem > configured) {
+            HG_CUDA_TRY(cudaFuncSetAttribute(hist_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        hist_kernel<W, false><<<grid, kHistThreads, smem, st>>>(hp);
+    }
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     return HG_OK;
@@ -935,10 +959,11 @@ template <bool WINDOW>
 static int launch_ap(ApParams ap, int64_t n_slots_max, cudaStream_t st)
 {
     const int ncol = WINDOW ? 32 : ap.b + 1;
-    // one shared-memory column of 2*ncol counters per thread
+    // one shared-memory column of 2*ncol counters per thread (16-bit in the window variant)
+    const size_t csize = WINDOW ? sizeof(uint16_t) : sizeof(uint32_t);
     int threads = 128;
-    while (threads > 32 && (size_t)threads * 2 * ncol * sizeof(uint32_t) > 200 * 1024) threads >>= 1;
-    const size_t smem = (size_t)threads * 2 * ncol * sizeof(uint32_t);
+    while (threads > 32 && (size_t)threads * 2 * ncol * csize > 200 * 1024) threads >>= 1;
+    const size_t smem = (size_t)threads * 2 * ncol * csize;
     static thread_local size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         HG_CUDA_TRY(cudaFuncSetAttribute(ap_kernel<WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
