@@ -21,6 +21,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace hg {
 
@@ -92,15 +93,17 @@ struct Stage1Params {
 // Per step m the CTA computes conv rows 2m and 2m+1 (all 55 columns, 96 channels) into shared memory: thread <-> (pixel
 // parity (row, column), 4 pixels of that parity, 8 output channels) -- pixels of one parity share the phase, hence the filter
 // set.  Then pooled row m-1 is completed with conv row 2m, normalised and written, and pooled row m is started.
-template <int WIN>
-__global__ void __launch_bounds__(kS1Threads, 1) conv1_stage_kernel(Stage1Params p)
+// WSMEM: the filter sets of the crop type live in shared memory (74 KB for wh = 32: one CTA per SM); otherwise they are read
+// through L1 (they are hot: every CTA of the SM uses one of 4 types) and two CTAs share an SM (the register file allows no more: 32 accumulators per thread).
+template <int WIN, bool WSMEM>
+__global__ void __launch_bounds__(kS1Threads, WSMEM ? 1 : 2) conv1_stage_kernel(Stage1Params p)
 {
     constexpr int K = WIN * WIN * 3;
     extern __shared__ __align__(16) float s1sm[];
     const int wh = p.wh, sw = wh + 2, s = 256 / wh, NP = s / 4;
-    float* const Wsm = s1sm;                                     // [NP*NP][K][96]
-    float* const Ssm = Wsm + NP * NP * K * kS1Cout;               // [sw][sw][3] source pixels (scaled, mean subtracted, replicated border)
-    float* const rowbuf = Ssm + ((sw * sw * 3 + 3) & ~3);        // [2][56][96] conv rows 2m, 2m+1 (bias + ReLU applied)
+    float* const Wsm = s1sm;                                     // [NP*NP][K][96] (WSMEM only)
+    float* const Ssm = Wsm + (WSMEM ? NP * NP * K * kS1Cout : 0); // [sw][sw][4] source pixels (scaled, mean subtracted, replicated border; RGB + pad: one 16-byte load per pixel)
+    float* const rowbuf = Ssm + sw * sw * 4;                      // [2][56][96] conv rows 2m, 2m+1 (bias + ReLU applied)
     float* const pool = rowbuf + 2 * 56 * kS1Cout;                // [27][96] pooled row under construction
     const int tid = threadIdx.x;
     const int nn = blockIdx.x, crop = nn / p.n, b = nn % p.n;
@@ -111,12 +114,15 @@ __global__ void __launch_bounds__(kS1Threads, 1) conv1_stage_kernel(Stage1Params
     const int type = (kk == 4 ? 2 : 0) + (flip ? 1 : 0);
 
     {
-        const float4* src = reinterpret_cast<const float4*>(p.wfused + (size_t)type * NP * NP * K * kS1Cout);
-        float4* dst = reinterpret_cast<float4*>(Wsm);
-        for (int i = tid; i < NP * NP * K * kS1Cout / 4; i += kS1Threads) dst[i] = __ldg(src + i);
+        if (WSMEM) {
+            const float4* src = reinterpret_cast<const float4*>(p.wfused + (size_t)type * NP * NP * K * kS1Cout);
+            float4* dst = reinterpret_cast<float4*>(Wsm);
+            for (int i = tid; i < NP * NP * K * kS1Cout / 4; i += kS1Threads) dst[i] = __ldg(src + i);
+        }
         const float mean[3] = {103.939f, 116.779f, 123.68f};
-        for (int i = tid; i < sw * sw * 3; i += kS1Threads) {
-            const int ch = i % 3, j = (i / 3) % sw, r = i / (3 * sw);
+        for (int i = tid; i < sw * sw * 4; i += kS1Threads) {
+            const int ch = i & 3, j = (i >> 2) % sw, r = (i >> 2) / sw;
+            if (ch == 3) { Ssm[i] = 0.0f; continue; }
             const int64_t flat = ((int64_t)b * 3 + ch) * wh * wh + min(r, wh - 1) * wh + min(j, wh - 1);
             float noise = 0.0f;  // main.py:147: one draw per source pixel, shared by the 10 crops (same index as prep_crops_kernel)
             if (p.seed) noise = (float)(s1_mix(p.seed ^ kS1StreamNoise, (uint64_t)flat) >> 40) * (1.0f / 16777216.0f) * (1.0f / 128.0f);
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(kS1Threads, 1) conv1_stage_kernel(Stage1Params
         col[q] = 2 * (4 * g + q) + sc;
         const int c = min(col[q], 54);
         const int xb = flip ? 245 - ox - 4 * c : ox + 4 * c;  // position of tap u = 0 in the 256-wide image
-        xoff[q] = (xb / s) * 3;
+        xoff[q] = (xb / s) * 4;
         if (q == 0) setx = (xb % s) >> 2;                       // same for my 4 pixels (their columns differ by multiples of 2: 8 positions)
     }
 
@@ -148,8 +154,8 @@ __global__ void __launch_bounds__(kS1Threads, 1) conv1_stage_kernel(Stage1Params
         const int r = 2 * m + sr;
         if (tid < kS1Compute && r <= 54) {
             const int yb = oy + 4 * r;
-            const float* wp = Wsm + (size_t)(((yb % s) >> 2) * NP + setx) * K * kS1Cout + ch0;
-            const float* sp = Ssm + (yb / s) * sw * 3;
+            const float* wp = (WSMEM ? Wsm : p.wfused + (size_t)type * NP * NP * K * kS1Cout) + (size_t)(((yb % s) >> 2) * NP + setx) * K * kS1Cout + ch0;
+            const float* sp = Ssm + (yb / s) * sw * 4;
             float acc[4][8];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
@@ -157,18 +163,28 @@ __global__ void __launch_bounds__(kS1Threads, 1) conv1_stage_kernel(Stage1Params
                 for (int i = 0; i < 8; ++i) acc[q][i] = 0.0f;
 #pragma unroll 1
             for (int dy = 0; dy < WIN; ++dy) {
-                const float* srow = sp + dy * sw * 3;
+                const float* srow = sp + dy * sw * 4;
 #pragma unroll
-                for (int j = 0; j < WIN * 3; ++j) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(wp + (dy * WIN * 3 + j) * kS1Cout);
-                    const float4 w1 = *reinterpret_cast<const float4*>(wp + (dy * WIN * 3 + j) * kS1Cout + 4);
+                for (int dx = 0; dx < WIN; ++dx) {
+                    float a[4][3];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float a = srow[xoff[q] + j];
-                        acc[q][0] = fmaf(a, w0.x, acc[q][0]); acc[q][1] = fmaf(a, w0.y, acc[q][1]);
-                        acc[q][2] = fmaf(a, w0.z, acc[q][2]); acc[q][3] = fmaf(a, w0.w, acc[q][3]);
-                        acc[q][4] = fmaf(a, w1.x, acc[q][4]); acc[q][5] = fmaf(a, w1.y, acc[q][5]);
-                        acc[q][6] = fmaf(a, w1.z, acc[q][6]); acc[q][7] = fmaf(a, w1.w, acc[q][7]);
+                        const float4 v = *reinterpret_cast<const float4*>(srow + xoff[q] + dx * 4);
+                        a[q][0] = v.x; a[q][1] = v.y; a[q][2] = v.z;
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const float* wk = wp + ((dy * WIN + dx) * 3 + ch) * kS1Cout;
+                        const float4 w0 = WSMEM ? *reinterpret_cast<const float4*>(wk) : __ldg(reinterpret_cast<const float4*>(wk));
+                        const float4 w1 = WSMEM ? *reinterpret_cast<const float4*>(wk + 4) : __ldg(reinterpret_cast<const float4*>(wk + 4));
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float x = a[q][ch];
+                            acc[q][0] = fmaf(x, w0.x, acc[q][0]); acc[q][1] = fmaf(x, w0.y, acc[q][1]);
+                            acc[q][2] = fmaf(x, w0.z, acc[q][2]); acc[q][3] = fmaf(x, w0.w, acc[q][3]);
+                            acc[q][4] = fmaf(x, w1.x, acc[q][4]); acc[q][5] = fmaf(x, w1.y, acc[q][5]);
+                            acc[q][6] = fmaf(x, w1.z, acc[q][6]); acc[q][7] = fmaf(x, w1.w, acc[q][7]);
+                        }
                     }
                 }
             }
@@ -219,10 +235,10 @@ __global__ void __launch_bounds__(kS1Threads, 1) conv1_stage_kernel(Stage1Params
     }
 }
 
-static size_t s1_smem_bytes(int wh)
+static size_t s1_smem_bytes(int wh, bool wsmem)
 {
     const int WIN = s1_win(wh), NP = s1_sets_per_axis(wh), K = WIN * WIN * 3, sw = wh + 2;
-    return sizeof(float) * ((size_t)NP * NP * K * kS1Cout + ((sw * sw * 3 + 3) & ~3) + 2 * 56 * kS1Cout + 27 * kS1Cout);
+    return sizeof(float) * ((wsmem ? (size_t)NP * NP * K * kS1Cout : 0) + (size_t)sw * sw * 4 + 2 * 56 * kS1Cout + 27 * kS1Cout);
 }
 
 bool stage1_supported(int wh) { return wh == 32 || wh == 64; }
@@ -238,16 +254,17 @@ int stage1_launch(const unsigned char* img, int n, int wh, const float* wfused, 
 {
     if (!stage1_supported(wh)) return fail(HG_EINVAL, "fused conv1 stage: image size %d is not supported (32 or 64)", wh);
     Stage1Params p{img, n, wh, wfused, bias, out, seed, lrn ? 1 : 0};
-    const size_t smem = s1_smem_bytes(wh);
-    if (wh == 32) {
-        static thread_local bool cfg = false;
-        if (!cfg) { HG_CUDA_TRY(cudaFuncSetAttribute(conv1_stage_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
-        conv1_stage_kernel<4><<<10 * n, kS1Threads, smem, st>>>(p);
-    } else {
-        static thread_local bool cfg = false;
-        if (!cfg) { HG_CUDA_TRY(cudaFuncSetAttribute(conv1_stage_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
-        conv1_stage_kernel<5><<<10 * n, kS1Threads, smem, st>>>(p);
-    }
+    static const bool wsmem = []() { const char* v = getenv("HG_STAGE1_WSMEM"); return v && *v == '1'; }();  // default: filters through L1, 2 CTAs per SM
+    const size_t smem = s1_smem_bytes(wh, wsmem);
+    auto launch = [&](auto kernel) -> int {
+        HG_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<10 * n, kS1Threads, smem, st>>>(p);
+        return HG_OK;
+    };
+    int rc;
+    if (wh == 32) rc = wsmem ? launch(conv1_stage_kernel<4, true>) : launch(conv1_stage_kernel<4, false>);
+    else rc = wsmem ? launch(conv1_stage_kernel<5, true>) : launch(conv1_stage_kernel<5, false>);
+    if (rc != HG_OK) return rc;
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     return HG_OK;
