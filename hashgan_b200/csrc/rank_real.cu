@@ -15,6 +15,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace hg {
 
@@ -94,6 +95,9 @@ struct ToprParams {
     int W, LW, Wr;
     uint2* bufA;  // global sort buffers [nq_chunk, R] when the top-R does not fit shared memory (else null)
     uint2* bufB;
+    uint2* cand;  // candidate lists [nq_chunk, cand_cap] of the threshold pass (null: always the exact path over the full row)
+    uint32_t cand_cap;
+    int* n_cand_queries;  // diagnostics: queries answered from their candidate list
     double* ap;   // [nq_chunk]
     uint32_t* ids;  // [nq_chunk, R] or null
     float* ips;     // [nq_chunk, R] or null
@@ -132,11 +136,29 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
     return base + inc - v;
 }
 
+// where a query's keys come from: the full key row (entry i = row i), a strided sample of it, or the candidate list
+// (key, row) pairs gathered by the threshold pass
+struct FullKeys {
+    const uint32_t* keys;
+    __device__ __forceinline__ uint32_t key(int64_t i) const { return __ldg(keys + i); }
+    __device__ __forceinline__ uint32_t row(int64_t i) const { return (uint32_t)i; }
+};
+struct SampledKeys {
+    const uint32_t* keys;
+    int64_t stride;
+    __device__ __forceinline__ uint32_t key(int64_t i) const { return __ldg(keys + i * stride); }
+    __device__ __forceinline__ uint32_t row(int64_t i) const { return (uint32_t)(i * stride); }
+};
+struct CandKeys {
+    const uint2* c;
+    __device__ __forceinline__ uint32_t key(int64_t i) const { return c[i].x; }
+    __device__ __forceinline__ uint32_t row(int64_t i) const { return c[i].y; }
+};
+
 // one radix-select pass: histogram of digit(key) over the keys whose higher bits equal `prefix`; returns the digit that
 // holds the `remaining`-th smallest such key and subtracts the keys below it from `remaining`
-template <int SHIFT, int BITS, int HI_SHIFT>
-__device__ __forceinline__ uint32_t select_pass(const uint32_t* __restrict__ keys, int64_t n, uint32_t prefix, uint32_t& remaining,
-                                                uint32_t* hist, uint32_t* s_misc)
+template <int SHIFT, int BITS, int HI_SHIFT, class Src>
+__device__ __forceinline__ uint32_t select_pass(const Src& src, int64_t n, uint32_t prefix, uint32_t& remaining, uint32_t* hist, uint32_t* s_misc)
 {
     constexpr int NB = 1 << BITS;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -147,7 +169,7 @@ __device__ __forceinline__ uint32_t select_pass(const uint32_t* __restrict__ key
         const int64_t i = i0 + tid;
         uint32_t bin = 0xFFFFFFFFu;
         if (i < n) {
-            const uint32_t k = __ldg(keys + i);
+            const uint32_t k = src.key(i);
             if (HI_SHIFT >= 32 || (k >> (HI_SHIFT & 31)) == prefix) bin = (k >> SHIFT) & (NB - 1);
         }
         const uint32_t grp = __match_any_sync(0xffffffffu, bin);
@@ -177,41 +199,33 @@ __device__ __forceinline__ uint32_t select_pass(const uint32_t* __restrict__ key
     return digit;
 }
 
-__global__ void __launch_bounds__(TR_THREADS) topr_ap_kernel(ToprParams p)
+// the `want`-th smallest key of src (1-based) and how many keys equal to it are among those `want`
+template <class Src>
+__device__ __forceinline__ uint32_t radix_select(const Src& src, int64_t n, uint32_t want, uint32_t& quota, uint32_t* hist, uint32_t* s_misc)
 {
-    extern __shared__ __align__(16) uint8_t tr_smem[];
-    __shared__ uint32_t hist[2048];
-    __shared__ uint32_t s_misc[2 * TR_WARPS + 8];
+    uint32_t remaining = want;
+    const uint32_t d1 = select_pass<21, 11, 32>(src, n, 0u, remaining, hist, s_misc);
+    const uint32_t d2 = select_pass<10, 11, 21>(src, n, d1, remaining, hist, s_misc);
+    const uint32_t d3 = select_pass<0, 10, 10>(src, n, (d1 << 11) | d2, remaining, hist, s_misc);
+    quota = remaining;
+    return (d1 << 21) | (d2 << 10) | d3;
+}
+
+// ordered collect: entries with key' < kappa in source order -> A[0, n_lt); the first `quota` entries with key' == kappa in
+// source order -> A[n_lt, n_lt + quota) (they rank last and are already in their final order).  Source order is row order.
+template <class Src>
+__device__ __forceinline__ void ordered_collect(const Src& src, int64_t n, uint32_t kappa, uint32_t quota, uint32_t n_lt, const uint32_t (&ql)[4],
+                                                const ToprParams& p, uint2* A, uint32_t* s_misc)
+{
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t q = blockIdx.x;
-    const uint32_t* keys = p.keys + q * p.key_stride;
-    const int64_t n = p.ndb;
-    const uint32_t R = (uint32_t)p.R;
     const uint32_t ltmask = (1u << lane) - 1u;
-
-    // ---- radix select: kappa = R-th smallest key', quota = how many rows equal to kappa belong to the top-R ----
-    uint32_t remaining = R;
-    const uint32_t d1 = select_pass<21, 11, 32>(keys, n, 0u, remaining, hist, s_misc);
-    const uint32_t d2 = select_pass<10, 11, 21>(keys, n, d1, remaining, hist, s_misc);
-    const uint32_t d3 = select_pass<0, 10, 10>(keys, n, (d1 << 11) | d2, remaining, hist, s_misc);
-    const uint32_t kappa = (d1 << 21) | (d2 << 10) | d3;
-    const uint32_t quota = remaining;
-    const uint32_t n_lt = R - quota;
-
-    uint2* A = p.bufA ? p.bufA + q * p.R : reinterpret_cast<uint2*>(tr_smem);
-    uint2* B = p.bufB ? p.bufB + q * p.R : reinterpret_cast<uint2*>(tr_smem) + p.R;
-
-    // ---- ordered collect: rows with key' < kappa in row order -> A[0, n_lt); the first `quota` rows with key' == kappa
-    //      in row order -> A[n_lt, R) (they rank last and are already in their final order) ----
-    uint32_t ql[4] = {0, 0, 0, 0};
-    for (int w = 0; w < p.LW && w < 4; ++w) ql[w] = p.q_rows[q * p.Wr + p.W + w];
     uint32_t base_lt = 0, base_eq = 0;
     for (int64_t i0 = 0; i0 < n; i0 += TR_THREADS) {
         const int64_t i = i0 + tid;
         uint32_t k = 0xFFFFFFFFu;
         bool is_lt = false, is_eq = false;
         if (i < n) {
-            k = __ldg(keys + i);
+            k = src.key(i);
             is_lt = k < kappa;
             is_eq = k == kappa;
         }
@@ -226,16 +240,93 @@ __global__ void __launch_bounds__(TR_THREADS) topr_ap_kernel(ToprParams p)
             tot_lt += cl; tot_eq += ce;
         }
         if (is_lt || (is_eq && off_eq + (uint32_t)__popc(be & ltmask) < quota)) {
+            const uint32_t row = src.row(i);
             uint32_t m = 0;
-            const uint32_t* lab = p.db_rows + i * p.Wr + p.W;
+            const uint32_t* lab = p.db_rows + (int64_t)row * p.Wr + p.W;
             for (int w = 0; w < p.LW && w < 4; ++w) m |= ql[w] & __ldg(lab + w);
             const uint32_t pos = is_lt ? off_lt + (uint32_t)__popc(bl & ltmask) : n_lt + off_eq + (uint32_t)__popc(be & ltmask);
-            A[pos] = make_uint2(k, (uint32_t)i | (m ? 0x80000000u : 0u));
+            A[pos] = make_uint2(k, row | (m ? 0x80000000u : 0u));
         }
         base_lt += tot_lt;
         base_eq += tot_eq;
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(TR_THREADS) topr_ap_kernel(ToprParams p)
+{
+    extern __shared__ __align__(16) uint8_t tr_smem[];
+    __shared__ uint32_t hist[2048];
+    __shared__ uint32_t s_misc[2 * TR_WARPS + 8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t q = blockIdx.x;
+    const uint32_t* keys = p.keys + q * p.key_stride;
+    const int64_t n = p.ndb;
+    const uint32_t R = (uint32_t)p.R;
+    const uint32_t ltmask = (1u << lane) - 1u;
+    uint32_t ql[4] = {0, 0, 0, 0};
+    for (int w = 0; w < p.LW && w < 4; ++w) ql[w] = p.q_rows[q * p.Wr + p.W + w];
+    uint2* A = p.bufA ? p.bufA + q * p.R : reinterpret_cast<uint2*>(tr_smem);
+    uint2* B = p.bufB ? p.bufB + q * p.R : reinterpret_cast<uint2*>(tr_smem) + p.R;
+
+    // ---- threshold pass (sparse top-R): the (R/n)-quantile of a strided SAMPLE of the keys, with the same 4-sigma margin as
+    //      the Hamming path, bounds kappa from above with high probability; ONE pass over the row then keeps the ~1.3 R rows
+    //      at or below it (row order), and the exact select / collect below run on those candidates instead of walking the
+    //      whole row four times.  Too few (estimate too tight) or too many candidates: the exact path over the full row. ----
+    const FullKeys full{keys};
+    bool use_cand = false;
+    uint32_t cnt = 0;
+    uint2* C = p.cand ? p.cand + q * (int64_t)p.cand_cap : nullptr;
+    const int64_t stride = n / 16384;
+    if (C != nullptr && stride >= 4 && (int64_t)R * 4 <= n) {
+        const int64_t ns = (n + stride - 1) / stride;
+        const double p0 = (double)R / (double)n, mu = p0 * (double)ns;
+        const double need = ceil(mu + 4.0 * sqrt(mu * (1.0 - p0)) + 2.0);
+        if (need < (double)ns) {
+            uint32_t dummy;
+            const uint32_t kest = radix_select(SampledKeys{keys, stride}, ns, (uint32_t)need, dummy, hist, s_misc);
+            // eight consecutive keys per thread and step (two 16-byte loads in flight, one block scan per 4096 keys): the
+            // pass is bound by load latency and barriers, not by bandwidth
+            uint32_t base = 0;
+            const bool vec = (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
+            for (int64_t i0 = 0; i0 < n; i0 += (int64_t)TR_THREADS * 8) {
+                const int64_t i = i0 + (int64_t)tid * 8;
+                uint32_t kk[8];
+                if (vec && i + 8 <= n) {
+                    const uint4 a = __ldg(reinterpret_cast<const uint4*>(keys + i)), b4 = __ldg(reinterpret_cast<const uint4*>(keys + i) + 1);
+                    kk[0] = a.x; kk[1] = a.y; kk[2] = a.z; kk[3] = a.w; kk[4] = b4.x; kk[5] = b4.y; kk[6] = b4.z; kk[7] = b4.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) kk[j] = (i + j < n) ? __ldg(keys + i + j) : 0xFFFFFFFFu;  // beyond the row: never a hit (kest < 2^32 - 1 or a real key)
+                }
+                uint32_t hits = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hits |= (uint32_t)(kk[j] <= kest && i + j < n) << j;
+                uint32_t tot;
+                uint32_t pos = base + block_excl_scan((uint32_t)__popc(hits), s_misc, tot);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (hits & (1u << j)) {
+                        if (pos < p.cand_cap) C[pos] = make_uint2(kk[j], (uint32_t)(i + j));
+                        ++pos;
+                    }
+                }
+                base += tot;
+            }
+            cnt = base;
+            use_cand = cnt >= R && cnt <= p.cand_cap;
+        }
+    }
+    __syncthreads();  // the candidate list is read back by other threads
+
+    // ---- radix select: kappa = R-th smallest key', quota = how many rows equal to kappa belong to the top-R ----
+    uint32_t quota, kappa;
+    if (use_cand) kappa = radix_select(CandKeys{C}, cnt, R, quota, hist, s_misc);
+    else kappa = radix_select(full, n, R, quota, hist, s_misc);
+    const uint32_t n_lt = R - quota;
+    if (use_cand) ordered_collect(CandKeys{C}, cnt, kappa, quota, n_lt, ql, p, A, s_misc);
+    else ordered_collect(full, n, kappa, quota, n_lt, ql, p, A, s_misc);
+    if (p.n_cand_queries && tid == 0 && use_cand) atomicAdd(p.n_cand_queries, 1);
 
     // ---- stable LSD radix sort of A[0, n_lt) by key' (8-bit digits; a pass whose digit is constant is skipped) ----
     uint2* src = A;
@@ -320,7 +411,8 @@ __global__ void __launch_bounds__(TR_THREADS) topr_ap_kernel(ToprParams p)
 struct RealPlan {
     int64_t key_stride = 0, chunk = 0;
     bool smem_sort = false;
-    size_t off_keys = 0, off_a = 0, off_b = 0, total = 0, smem = 0;
+    size_t off_keys = 0, off_a = 0, off_b = 0, off_cand = 0, total = 0, smem = 0;
+    uint32_t cand_cap = 0;
     bool ok = false;
 };
 
@@ -331,7 +423,9 @@ static RealPlan make_real_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R,
     p.key_stride = round_up(ndb, 4);
     p.smem_sort = (size_t)R * 16 <= 160 * 1024;
     p.smem = p.smem_sort ? (size_t)R * 16 : 0;
-    const size_t per_query = (size_t)p.key_stride * 4 + (p.smem_sort ? 0 : (size_t)R * 16);
+    // candidates of the threshold pass: about 1.3 R are expected (4-sigma margin on a 16k-key sample); room for 3 R + 4096
+    p.cand_cap = (uint32_t)std::min<int64_t>(ndb, 3 * R + 4096);
+    const size_t per_query = (size_t)p.key_stride * 4 + (p.smem_sort ? 0 : (size_t)R * 16) + (size_t)p.cand_cap * 8;
     int64_t chunk = std::min<int64_t>(nq, 592);  // 2 resident CTAs x 148 SMs x 2 rounds
     if (ws_bytes) {
         if (ws_bytes < per_query + 1024) return p;  // not even one query fits
@@ -343,6 +437,7 @@ static RealPlan make_real_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R,
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
     p.off_keys = take((size_t)chunk * p.key_stride * 4);
     if (!p.smem_sort) { p.off_a = take((size_t)chunk * R * 8); p.off_b = take((size_t)chunk * R * 8); }
+    p.off_cand = take((size_t)chunk * p.cand_cap * 8);
     p.total = off;
     while (ws_bytes && p.total > ws_bytes && chunk > 1) {  // 256-byte rounding of the sub-buffers: shrink until it fits
         --chunk;
@@ -350,6 +445,7 @@ static RealPlan make_real_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R,
         off = 0;
         p.off_keys = take((size_t)chunk * p.key_stride * 4);
         if (!p.smem_sort) { p.off_a = take((size_t)chunk * R * 8); p.off_b = take((size_t)chunk * R * 8); }
+        p.off_cand = take((size_t)chunk * p.cand_cap * 8);
         p.total = off;
     }
     p.ok = !(ws_bytes && p.total > ws_bytes);
@@ -394,6 +490,12 @@ extern "C" int hg_ip_map(const float* d_q_feat, const uint32_t* d_q_rows, int64_
         tp.q_rows = d_q_rows + s * Wr; tp.db_rows = d_db_rows; tp.W = W; tp.LW = LW; tp.Wr = Wr;
         tp.bufA = pl.smem_sort ? nullptr : reinterpret_cast<uint2*>(ws + pl.off_a);
         tp.bufB = pl.smem_sort ? nullptr : reinterpret_cast<uint2*>(ws + pl.off_b);
+        {
+            static const bool no_cand = []() { const char* v = getenv("HG_REAL_CANDIDATES"); return v && *v == '0'; }();  // diagnostics: exact path only
+            tp.cand = no_cand ? nullptr : reinterpret_cast<uint2*>(ws + pl.off_cand);
+            tp.cand_cap = pl.cand_cap;
+            tp.n_cand_queries = nullptr;
+        }
         tp.ap = d_ap + s; tp.ids = d_ids ? d_ids + s * R : nullptr; tp.ips = d_ips ? d_ips + s * R : nullptr; tp.rel = d_rel ? d_rel + s : nullptr;
         topr_ap_kernel<<<(unsigned)n, TR_THREADS, pl.smem, st>>>(tp);
         count_launch();
