@@ -83,12 +83,42 @@ __global__ void __launch_bounds__(256) ip_keys_kernel(const float* __restrict__ 
     }
 }
 
+// ---- 1b. the same contraction on the tensor cores ------------------------------------------------------------------------
+// The dense layers of the encoder already run as error-compensated TF32 on tcgen05 (conv_gemm_tf32_kernel with a 1 x 1
+// window, gemm_tf32.cu): every fp32 operand is split into its upper 19 bits (exactly a TF32 number) and the remainder, and
+// hi*hi + lo*hi + hi*lo is accumulated in fp32 in tensor memory -- products are reproduced to ~2^-21, exactly when the
+// operands are exactly representable.  Here the "weights" are the database features [ndb, b] (already K-major per row: the
+// layout hg_conv_weight_pack produces), split once per call; the "activations" are the queries of the chunk; the kernel
+// writes the fp32 inner products and topr_ap_kernel forms the keys on load.
+int conv_gemm_tf32(const float* in, const float* wt, const float* wt_lo, const float* bias, float* out, int64_t M, int H, int W, int C, int c0,
+                   int Cg, int KH, int KW, int stride, int pad, int Ho, int Wo, int Kpad, int Cog, int ldc, cudaStream_t st, int relu);  // gemm_tf32.cu
+
+// rows [n, b] -> hi / lo [n, Kpad] (zero padded); lo == nullptr: a plain zero-padded copy [n, Kpad] (the A operand is split
+// by the GEMM's producer warps)
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, int64_t n, int b, int Kpad, float* __restrict__ hi, float* __restrict__ lo)
+{
+    const int64_t total = n * Kpad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % Kpad);
+        const int64_t r = i / Kpad;
+        const float v = k < b ? __ldg(x + r * b + k) : 0.0f;
+        if (lo) {
+            const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            hi[i] = h;
+            lo[i] = v - h;
+        } else {
+            hi[i] = v;
+        }
+    }
+}
+
 // ---- 2. per query: exact top-R by (key' ascending, row ascending), AP ---------------------------------------------------
 constexpr int TR_THREADS = 512;
 constexpr int TR_WARPS = TR_THREADS / 32;
 
 struct ToprParams {
-    const uint32_t* keys;   // [nq_chunk, key_stride]
+    const uint32_t* keys;   // [nq_chunk, key_stride]: order-reversing keys, or the fp32 inner products when keys_are_float
+    int keys_are_float;
     int64_t key_stride, ndb, R;
     const uint32_t* q_rows;   // packed rows of the chunk's queries (label words used)
     const uint32_t* db_rows;
@@ -138,15 +168,24 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
 
 // where a query's keys come from: the full key row (entry i = row i), a strided sample of it, or the candidate list
 // (key, row) pairs gathered by the threshold pass
+// (`flt`: the row holds the fp32 inner products themselves -- the tensor-core GEMM writes floats -- and the order-reversing
+// key is formed on load)
+__device__ __forceinline__ uint32_t load_key(const uint32_t* p, bool flt)
+{
+    const uint32_t u = __ldg(p);
+    return flt ? ip_to_key(__uint_as_float(u)) : u;
+}
 struct FullKeys {
     const uint32_t* keys;
-    __device__ __forceinline__ uint32_t key(int64_t i) const { return __ldg(keys + i); }
+    bool flt;
+    __device__ __forceinline__ uint32_t key(int64_t i) const { return load_key(keys + i, flt); }
     __device__ __forceinline__ uint32_t row(int64_t i) const { return (uint32_t)i; }
 };
 struct SampledKeys {
     const uint32_t* keys;
     int64_t stride;
-    __device__ __forceinline__ uint32_t key(int64_t i) const { return __ldg(keys + i * stride); }
+    bool flt;
+    __device__ __forceinline__ uint32_t key(int64_t i) const { return load_key(keys + i * stride, flt); }
     __device__ __forceinline__ uint32_t row(int64_t i) const { return (uint32_t)(i * stride); }
 };
 struct CandKeys {
@@ -273,7 +312,8 @@ __global__ void __launch_bounds__(TR_THREADS) topr_ap_kernel(ToprParams p)
     //      the Hamming path, bounds kappa from above with high probability; ONE pass over the row then keeps the ~1.3 R rows
     //      at or below it (row order), and the exact select / collect below run on those candidates instead of walking the
     //      whole row four times.  Too few (estimate too tight) or too many candidates: the exact path over the full row. ----
-    const FullKeys full{keys};
+    const bool flt = p.keys_are_float != 0;
+    const FullKeys full{keys, flt};
     bool use_cand = false;
     uint32_t cnt = 0;
     uint2* C = p.cand ? p.cand + q * (int64_t)p.cand_cap : nullptr;
@@ -284,7 +324,7 @@ __global__ void __launch_bounds__(TR_THREADS) topr_ap_kernel(ToprParams p)
         const double need = ceil(mu + 4.0 * sqrt(mu * (1.0 - p0)) + 2.0);
         if (need < (double)ns) {
             uint32_t dummy;
-            const uint32_t kest = radix_select(SampledKeys{keys, stride}, ns, (uint32_t)need, dummy, hist, s_misc);
+            const uint32_t kest = radix_select(SampledKeys{keys, stride, flt}, ns, (uint32_t)need, dummy, hist, s_misc);
             // eight consecutive keys per thread and step (two 16-byte loads in flight, one block scan per 4096 keys): the
             // pass is bound by load latency and barriers, not by bandwidth
             uint32_t base = 0;
@@ -295,9 +335,13 @@ __global__ void __launch_bounds__(TR_THREADS) topr_ap_kernel(ToprParams p)
                 if (vec && i + 8 <= n) {
                     const uint4 a = __ldg(reinterpret_cast<const uint4*>(keys + i)), b4 = __ldg(reinterpret_cast<const uint4*>(keys + i) + 1);
                     kk[0] = a.x; kk[1] = a.y; kk[2] = a.z; kk[3] = a.w; kk[4] = b4.x; kk[5] = b4.y; kk[6] = b4.z; kk[7] = b4.w;
+                    if (flt) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) kk[j] = ip_to_key(__uint_as_float(kk[j]));
+                    }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) kk[j] = (i + j < n) ? __ldg(keys + i + j) : 0xFFFFFFFFu;  // beyond the row: never a hit (kest < 2^32 - 1 or a real key)
+                    for (int j = 0; j < 8; ++j) kk[j] = (i + j < n) ? load_key(keys + i + j, flt) : 0xFFFFFFFFu;  // beyond the row: masked below
                 }
                 uint32_t hits = 0;
 #pragma unroll
@@ -411,8 +455,9 @@ __global__ void __launch_bounds__(TR_THREADS) topr_ap_kernel(ToprParams p)
 struct RealPlan {
     int64_t key_stride = 0, chunk = 0;
     bool smem_sort = false;
-    size_t off_keys = 0, off_a = 0, off_b = 0, off_cand = 0, total = 0, smem = 0;
+    size_t off_keys = 0, off_a = 0, off_b = 0, off_cand = 0, off_dhi = 0, off_dlo = 0, off_bias = 0, off_qpad = 0, total = 0, smem = 0;
     uint32_t cand_cap = 0;
+    int Kpad = 0;       // > 0: the contraction runs on the tensor cores (database split into hi / lo [ndb, Kpad])
     bool ok = false;
 };
 
@@ -425,28 +470,45 @@ static RealPlan make_real_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R,
     p.smem = p.smem_sort ? (size_t)R * 16 : 0;
     // candidates of the threshold pass: about 1.3 R are expected (4-sigma margin on a 16k-key sample); room for 3 R + 4096
     p.cand_cap = (uint32_t)std::min<int64_t>(ndb, 3 * R + 4096);
-    const size_t per_query = (size_t)p.key_stride * 4 + (p.smem_sort ? 0 : (size_t)R * 16) + (size_t)p.cand_cap * 8;
+    {
+        // Measured on B200 (10k x 1M x 64): the tensor-core contraction takes 56 ms against 25 ms for the fp32 FMA kernel -- with
+        // K = b = 64 a 128 x 128 tile is two K steps of work behind a full prologue / epilogue, and 39k such CTAs are launched
+        // per call -- so it is opt-in (HG_REAL_TC=1; same results, tests/test_gpu_real_valued.py passes either way).
+        static const bool tc = []() { const char* v = getenv("HG_REAL_TC"); return v && *v == '1'; }();
+        p.Kpad = tc ? (int)round_up(round_up(b, 4), 32) : 0;
+    }
+    const size_t fixed = p.Kpad ? 2 * (((size_t)ndb * p.Kpad * 4 + 255) & ~size_t(255)) + (((size_t)p.key_stride * 4 + 255) & ~size_t(255)) : 0;
+    const size_t per_query = (size_t)p.key_stride * 4 + (p.smem_sort ? 0 : (size_t)R * 16) + (size_t)p.cand_cap * 8 + (size_t)p.Kpad * 4;
     int64_t chunk = std::min<int64_t>(nq, 592);  // 2 resident CTAs x 148 SMs x 2 rounds
     if (ws_bytes) {
-        if (ws_bytes < per_query + 1024) return p;  // not even one query fits
-        chunk = std::min<int64_t>(nq, (int64_t)((ws_bytes - 1024) / per_query));
+        if (ws_bytes < fixed + per_query + 2048) {
+            if (p.Kpad == 0 || ws_bytes < per_query + 2048) return p;  // not even one query fits
+            p.Kpad = 0;                                                // no room for the split database: fp32 FMA contraction
+        }
+        const size_t fx = p.Kpad ? fixed : 0;
+        chunk = std::min<int64_t>(nq, (int64_t)((ws_bytes - fx - 2048) / per_query));
     }
     if (chunk <= 0) return p;
+    auto layout = [&](int64_t c) {
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+        p.off_keys = take((size_t)c * p.key_stride * 4);
+        if (!p.smem_sort) { p.off_a = take((size_t)c * R * 8); p.off_b = take((size_t)c * R * 8); }
+        p.off_cand = take((size_t)c * p.cand_cap * 8);
+        if (p.Kpad) {
+            p.off_dhi = take((size_t)ndb * p.Kpad * 4);
+            p.off_dlo = take((size_t)ndb * p.Kpad * 4);
+            p.off_bias = take((size_t)p.key_stride * 4);
+            p.off_qpad = take((size_t)c * p.Kpad * 4);
+        }
+        p.total = off;
+    };
     p.chunk = chunk;
-    size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
-    p.off_keys = take((size_t)chunk * p.key_stride * 4);
-    if (!p.smem_sort) { p.off_a = take((size_t)chunk * R * 8); p.off_b = take((size_t)chunk * R * 8); }
-    p.off_cand = take((size_t)chunk * p.cand_cap * 8);
-    p.total = off;
+    layout(chunk);
     while (ws_bytes && p.total > ws_bytes && chunk > 1) {  // 256-byte rounding of the sub-buffers: shrink until it fits
         --chunk;
         p.chunk = chunk;
-        off = 0;
-        p.off_keys = take((size_t)chunk * p.key_stride * 4);
-        if (!p.smem_sort) { p.off_a = take((size_t)chunk * R * 8); p.off_b = take((size_t)chunk * R * 8); }
-        p.off_cand = take((size_t)chunk * p.cand_cap * 8);
-        p.total = off;
+        layout(chunk);
     }
     p.ok = !(ws_bytes && p.total > ws_bytes);
     return p;
@@ -478,15 +540,35 @@ extern "C" int hg_ip_map(const float* d_q_feat, const uint32_t* d_q_rows, int64_
         HG_CUDA_TRY(cudaFuncSetAttribute(topr_ap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         configured = pl.smem;
     }
+    const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
+    float* d_hi = pl.Kpad ? reinterpret_cast<float*>(ws + pl.off_dhi) : nullptr;
+    float* d_lo = pl.Kpad ? reinterpret_cast<float*>(ws + pl.off_dlo) : nullptr;
+    float* d_zero = pl.Kpad ? reinterpret_cast<float*>(ws + pl.off_bias) : nullptr;
+    float* d_qpad = pl.Kpad ? reinterpret_cast<float*>(ws + pl.off_qpad) : nullptr;
+    if (pl.Kpad) {  // once per call: the database as the B operand of the error-compensated tensor-core GEMM
+        split_rows_kernel<<<sms * 16, 256, 0, st>>>(d_db_feat, ndb, b, pl.Kpad, d_hi, d_lo);
+        count_launch();
+        HG_CUDA_TRY(cudaMemsetAsync(d_zero, 0, (size_t)pl.key_stride * 4, st));
+        HG_CUDA_TRY(cudaGetLastError());
+    }
     for (int64_t s = 0; s < nq; s += pl.chunk) {
         const int64_t n = std::min<int64_t>(pl.chunk, nq - s);
         uint32_t* keys = reinterpret_cast<uint32_t*>(ws + pl.off_keys);
-        dim3 grid((unsigned)ceil_div(ndb, IP_BN), (unsigned)ceil_div(n, IP_BM));
-        ip_keys_kernel<<<grid, 256, 0, st>>>(d_q_feat + s * b, n, d_db_feat, ndb, b, keys, pl.key_stride);
-        count_launch();
-        HG_CUDA_TRY(cudaGetLastError());
+        if (pl.Kpad) {
+            split_rows_kernel<<<(unsigned)std::min<int64_t>(sms * 16, ceil_div(n * pl.Kpad, 256)), 256, 0, st>>>(d_q_feat + s * b, n, b, pl.Kpad, d_qpad, nullptr);
+            count_launch();
+            HG_CUDA_TRY(cudaGetLastError());
+            int rc = conv_gemm_tf32(d_qpad, d_hi, d_lo, d_zero, reinterpret_cast<float*>(keys), n, 1, 1, pl.Kpad, 0, pl.Kpad, 1, 1, 1, 0, 1, 1, pl.Kpad, (int)ndb,
+                                    (int)pl.key_stride, st, 0);
+            if (rc != HG_OK) return rc;
+        } else {
+            dim3 grid((unsigned)ceil_div(ndb, IP_BN), (unsigned)ceil_div(n, IP_BM));
+            ip_keys_kernel<<<grid, 256, 0, st>>>(d_q_feat + s * b, n, d_db_feat, ndb, b, keys, pl.key_stride);
+            count_launch();
+            HG_CUDA_TRY(cudaGetLastError());
+        }
         ToprParams tp{};
-        tp.keys = keys; tp.key_stride = pl.key_stride; tp.ndb = ndb; tp.R = R;
+        tp.keys = keys; tp.keys_are_float = pl.Kpad ? 1 : 0; tp.key_stride = pl.key_stride; tp.ndb = ndb; tp.R = R;
         tp.q_rows = d_q_rows + s * Wr; tp.db_rows = d_db_rows; tp.W = W; tp.LW = LW; tp.Wr = Wr;
         tp.bufA = pl.smem_sort ? nullptr : reinterpret_cast<uint2*>(ws + pl.off_a);
         tp.bufB = pl.smem_sort ? nullptr : reinterpret_cast<uint2*>(ws + pl.off_b);
