@@ -718,9 +718,9 @@ def main():
     # ---- roofline of the dominant kernel: the all-pairs select ------------------------------------------------
     peaks, peak_src = _peaks()
     hbm_peak = float(peaks["hbm_gbs"])
-    sel_ms = phases_ms["select"]
     W = lib.hg_code_words(wl.b)
     kp = int(lib.hg_select_backend_for(wl.nq, wl.ndb, wl.b, wl.L, wl.R))
+    sel_ms = phases_ms["ap"] if kp == 1 else phases_ms["select"]   # kp == 1: dense walk, the AP kernel does all pairs itself
     pairs = float(wl.nq) * float(wl.ndb)
     eff_bytes = pairs * 1.0  # 1 byte per (query, db row) pair = the uint8 distance matrix a non-fused design writes
     achieved = eff_bytes / (sel_ms * 1e-3) / 1e9
@@ -728,14 +728,25 @@ def main():
     prof = os.path.join(ROOT, "profiles", "select_kernel_dram_bytes.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get(f"{wl.name}_{'umma' if kp > 0 else 'popc'}")
+            traffic = json.load(open(prof)).get(f"{wl.name}_{'umma' if kp > 1 else 'popc'}")
         except Exception:
             traffic = None
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
         "peak_source": peak_src, "kernel_ms": sel_ms, "algorithmic_bytes_per_launch": eff_bytes, "phases_ms": phases_ms,
     }
-    if kp > 0:
+    if kp == 1:
+        popc_ops, popc_ms = C.c_double(), C.c_double()
+        _native.check(lib.hg_popc_peak(C.byref(popc_ops), C.byref(popc_ms), 1 << 14, None))
+        popc_achieved = 2.0 * pairs * W / (sel_ms * 1e-3)   # two passes over all pairs
+        roofline.update({
+            "kernel": "dense_ap_kernel",
+            "note": ("R >= ndb / 2: no selection, the AP walk recomputes distance and relevance of every pair in both of its passes; 'achieved' "
+                     "is the distance-matrix-equivalent rate (1 B/pair, SURVEY 8(d)); the kernel is bound by shared-memory counter latency, "
+                     "the POPC pipe view is in 'popc'"),
+            "popc": {"achieved_wordops_per_s": popc_achieved, "peak_wordops_per_s": popc_ops.value, "frac": popc_achieved / popc_ops.value,
+                     "peak_source": "hg_popc_peak microbenchmark, same process"}})
+    elif kp > 0:
         tops = 2.0 * pairs * kp / (sel_ms * 1e-3) / 1e12
         i8_ops, i8_ms = C.c_double(), C.c_double()
         _native.check(lib.hg_i8_peak(C.byref(i8_ops), C.byref(i8_ms), 0, None))
@@ -791,7 +802,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": _workload_text(wl, world > 1), "codes": codes,
-                   "queries_total": total_queries, "db_rows": wl.ndb, "bits": wl.b, "R": wl.R, "select_backend": ("tcgen05 int8 (select_umma_kernel)" if kp > 0 else "popc (select_kernel)"),
+                   "queries_total": total_queries, "db_rows": wl.ndb, "bits": wl.b, "R": wl.R, "select_backend": ("dense walk, no selection (dense_ap_kernel)" if kp == 1 else ("tcgen05 int8 (select_umma_kernel)" if kp > 1 else "popc (select_kernel)")),
                    "l2": f"no flush: every step re-reads the float32 feature matrix ({wl.ndb * wl.b * 4 / world / 1e6:.0f} MB per GPU at this shape) " + ("which exceeds the 126 MB L2" if wl.ndb * wl.b * 4 / world > 126e6 else "and writes/re-reads the candidate bins (beyond L2 together)"),
                    "parallelism": f"query-sharded x{world}, db row-sharded for packing; exchange: {exchange}; per-query APs all-gathered" if world > 1 else "1 GPU"},
         "warmup_steps_run": n_warm, "mAP": map_val, "mAP_all_ranks": map_all, "parity": parity, "path_stats": stats, "strong": strong,

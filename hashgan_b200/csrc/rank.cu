@@ -35,6 +35,7 @@ namespace hg {
 struct Plan {
     int b = 0, L = 0, W = 0, LW = 0, Wr = 0, QT = 0, TQ = 0, TILE = 0, P = 0, nqt = 0;
     int umma_kp = 0;  // > 0: the fast-path select runs on the tensor cores (select_umma.cu), int8 rows of this many bytes
+    bool dense = false;  // R is a large part of the database: no selection at all, dense_ap_kernel walks the packed rows
     int64_t nq = 0, ndb = 0, R = 0, SL = 0;
     uint32_t cap = 0;
     // sample pass
@@ -72,6 +73,11 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
     if (p.W == 0 || p.LW == 0 || nq <= 0 || ndb <= 0 || R <= 0 || R > ndb || ndb >= (int64_t(1) << 31) || nq >= (int64_t(1) << 31))
         return p;
     p.b = b; p.L = L; p.nq = nq; p.ndb = ndb; p.R = R;
+    {
+        // every second row or more is in the top-R: selecting costs more than it saves (HG_DENSE=0 / 1 forces the choice)
+        const int dv = env_int("HG_DENSE", -1);
+        p.dense = dv < 0 ? (R * 2 >= ndb && ndb / 32 <= kMaxSplitRows) : (dv != 0 && ndb / 32 <= kMaxSplitRows);
+    }
     const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
     p.QT = nq >= 1024 ? 2 : 1;  // measured on B200 (C4): QT=2 with ~16 CTAs/SM beats QT=4 (scripts/tune_select.py)
     {
@@ -815,6 +821,197 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
 }
 
 // ================================================================================================
+// 4b. Dense top-R (R a large part of the database; cifar_evaluation.yaml ranks the WHOLE database: MAP_R == DB_SIZE).
+//     Every row is a candidate, so nothing is selected and nothing is written: the AP walk of ap_kernel runs directly over
+//     the packed rows, the Hamming distance and the relevance bit of a row are recomputed in both passes (one XOR + POPC per
+//     word) instead of being stored as 54 M candidate entries and read back twice (C1: select 0.46 ms + AP 0.52 ms).
+//     One CTA per query, thread t owns the t-th contiguous row range (thread order == row order, as in ap_kernel);
+//     private per-distance counters -> exact (distance, row) ranks; rows ranked beyond R contribute nothing.
+// ================================================================================================
+struct DenseApParams {
+    const uint32_t* q_rows;
+    const uint32_t* db_rows;
+    int64_t nq, ndb, R;
+    int b, LW, Wr, G;
+    double* ap;
+    uint32_t* ids;
+    uint16_t* dist;
+    int32_t* rel;
+};
+
+// one CTA = one query; thread t owns the t-th of blockDim.x contiguous row ranges.
+// LW1 (label fits one word: the row stride is a compile-time constant): a thread fetches four rows at a time (two or four
+// 16-byte loads in flight; one row for the 8- and 12-word rows) -- the threads of a warp stream 32 different ranges, so every load instruction touches 32
+// cache lines and costs 32 tag look-ups; row-at-a-time loads made the kernel L1-tag bound (1.0 ms at C1).
+template <int W, bool LW1>
+__global__ void __launch_bounds__(256) dense_ap_kernel(DenseApParams p)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int NTB = blockDim.x, NW = NTB >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = p.b + 1;
+    uint32_t* cN = smem + tid;                      // cN[d * NTB]: rows at distance d -> rank base
+    uint32_t* cM = smem + (size_t)nb * NTB + tid;   // cM[d * NTB]: relevant rows at distance d -> relevant base
+    uint2* wtot = reinterpret_cast<uint2*>(smem + (size_t)2 * nb * NTB);  // [nb][NW]: per-warp totals of a distance
+    const uint32_t FULL = 0xffffffffu;
+    const int64_t q = blockIdx.x;
+    const int Wr = LW1 ? RowLW1<W>::Wr : p.Wr, LW = LW1 ? 1 : p.LW;
+    constexpr int RB = LW1 ? (RowLW1<W>::Wr <= 4 ? 4 : 1) : 1;  // rows per batch: 4 (32 bytes of 2-word rows, 64 bytes of 4-word rows: measured best at C1 / C1_64) or 1
+    uint32_t qw[W], ql[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int w = 0; w < W; ++w) qw[w] = p.q_rows[q * Wr + w];
+    for (int w = 0; w < LW && w < 4; ++w) ql[w] = p.q_rows[q * Wr + W + w];
+    for (int c = 0; c < nb; ++c) { cN[c * NTB] = 0; cM[c * NTB] = 0; }
+    // ranges start at multiples of RB rows so that the batches are 16-byte aligned
+    const int64_t lo = ((int64_t)tid * p.ndb / NTB) / RB * RB;
+    const int64_t hi = tid + 1 == NTB ? p.ndb : ((int64_t)(tid + 1) * p.ndb / NTB) / RB * RB;
+
+    auto words_entry = [&](const uint32_t* w, uint32_t& d, uint32_t& m) {  // w: the row's words (registers when LW1)
+        uint32_t v[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) v[i] = w[i];
+        d = (uint32_t)hamming<W>(qw, v);
+        uint32_t mm = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < LW) mm |= ql[i] & w[W + i];
+        m = mm ? 1u : 0u;
+    };
+    // walks my rows in order; fn(row, d, m)
+    auto walk = [&](auto&& fn) {
+        int64_t r = lo;
+        if constexpr (LW1) {
+            constexpr int WrC = RowLW1<W>::Wr;
+            constexpr int NV = WrC * RB / 4;  // 16-byte loads per batch (4 or 2; 3 for the 12-word rows of b > 128)
+            for (; r + RB <= hi; r += RB) {
+                uint32_t buf[NV * 4];
+                const uint4* src = reinterpret_cast<const uint4*>(p.db_rows + r * WrC);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const uint4 t = __ldg(src + i);
+                    buf[4 * i] = t.x; buf[4 * i + 1] = t.y; buf[4 * i + 2] = t.z; buf[4 * i + 3] = t.w;
+                }
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                    uint32_t d, m;
+                    words_entry(buf + j * WrC, d, m);
+                    fn(r + j, d, m);
+                }
+            }
+        }
+        for (; r < hi; ++r) {
+            uint32_t wbuf[12];
+            const uint32_t* row = p.db_rows + r * Wr;
+            for (int i = 0; i < W + LW; ++i) wbuf[i] = __ldg(row + i);
+            uint32_t d, m;
+            words_entry(wbuf, d, m);
+            fn(r, d, m);
+        }
+    };
+
+    // ---- pass A: private histograms ----
+    walk([&](int64_t, uint32_t d, uint32_t m) {
+        cN[d * NTB] += 1u;
+        cM[d * NTB] += m;
+    });
+    // ---- rank bases: distances in ascending order, threads of the query in row order.  Per distance: exclusive scan inside
+    //      the warp (kept in the counter), warp totals through shared memory, then the totals of the closer distances ----
+    for (int i = 0; i < nb; ++i) {
+        const uint32_t vN = cN[i * NTB], vM = cM[i * NTB];
+        uint32_t iN = vN, iM = vM;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t tN = __shfl_up_sync(FULL, iN, o);
+            const uint32_t tM = __shfl_up_sync(FULL, iM, o);
+            if (lane >= o) { iN += tN; iM += tM; }
+        }
+        cN[i * NTB] = iN - vN;
+        cM[i * NTB] = iM - vM;
+        if (lane == 31) wtot[i * NW + warp] = make_uint2(iN, iM);
+    }
+    __syncthreads();
+    {
+        uint32_t cn = 0, cm = 0;
+        for (int i = 0; i < nb; ++i) {
+            uint32_t bN = cn, bM = cm;
+            for (int w = 0; w < NW; ++w) {
+                const uint2 t = wtot[i * NW + w];
+                if (w < warp) { bN += t.x; bM += t.y; }
+                cn += t.x; cm += t.y;
+            }
+            cN[i * NTB] += bN;
+            cM[i * NTB] += bM;
+        }
+    }
+    // ---- pass B: ranks, relevant prefix counts, AP ----
+    double acc = 0.0, acc_lo = 0.0;
+    int relc = 0;
+    const uint32_t R32 = (uint32_t)p.R;
+    walk([&](int64_t r, uint32_t d, uint32_t m) {
+        const uint32_t rank = cN[d * NTB] + 1u;
+        const uint32_t cum = cM[d * NTB] + m;
+        cN[d * NTB] = rank;
+        cM[d * NTB] = cum;
+        if (rank <= R32) {
+            if (p.ids) p.ids[q * p.R + (rank - 1u)] = (uint32_t)r;
+            if (p.dist) p.dist[q * p.R + (rank - 1u)] = (uint16_t)d;
+            if (m) {
+                dd_add(acc, acc_lo, ap_term(cum, rank));
+                relc += 1;
+            }
+        }
+    });
+    // fixed-order reduction (deterministic): lanes by xor tree, then the warps in order
+    for (int o = 1; o < 32; o <<= 1) {
+        const double ohi = __shfl_xor_sync(FULL, acc, o), olo = __shfl_xor_sync(FULL, acc_lo, o);
+        dd_add(acc, acc_lo, ohi);
+        acc_lo = __dadd_rn(acc_lo, olo);
+        relc += __shfl_xor_sync(FULL, relc, o);
+    }
+    __syncthreads();  // wtot is reused for the warp results
+    double* red = reinterpret_cast<double*>(wtot);  // [NW][3]
+    if (lane == 0) { red[warp * 3] = acc; red[warp * 3 + 1] = acc_lo; red[warp * 3 + 2] = (double)relc; }
+    __syncthreads();
+    if (tid == 0) {
+        double hi_ = 0.0, lo_ = 0.0, rc = 0.0;
+        for (int w = 0; w < NW; ++w) { dd_add(hi_, lo_, red[w * 3]); lo_ = __dadd_rn(lo_, red[w * 3 + 1]); rc += red[w * 3 + 2]; }
+        const double sum = __dadd_rn(hi_, lo_);
+        p.ap[q] = rc > 0.0 ? sum / rc : __longlong_as_double(0x7ff8000000000000LL);
+        if (p.rel) p.rel[q] = (int32_t)rc;
+    }
+}
+
+template <int W>
+static int launch_dense_ap(DenseApParams dp, cudaStream_t st)
+{
+    const int nb = dp.b + 1;
+    // threads per query: as many as the shared-memory counters allow (<= 256), but at least a few dozen rows per thread
+    int threads = 256;
+    auto smem_for = [&](int t) { return (size_t)t * 2 * nb * sizeof(uint32_t) + std::max<size_t>((size_t)nb * (t / 32) * sizeof(uint2), (size_t)(t / 32) * 3 * sizeof(double)) + 16; };
+    while (threads > 32 && (smem_for(threads) > 100 * 1024 || dp.ndb / threads < 32)) threads >>= 1;
+    const size_t smem = smem_for(threads);
+    dp.G = threads;
+    if (dp.LW == 1) {
+        static thread_local size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            HG_CUDA_TRY(cudaFuncSetAttribute(dense_ap_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        dense_ap_kernel<W, true><<<(unsigned)dp.nq, threads, smem, st>>>(dp);
+    } else {
+        static thread_local size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            HG_CUDA_TRY(cudaFuncSetAttribute(dense_ap_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        dense_ap_kernel<W, false><<<(unsigned)dp.nq, threads, smem, st>>>(dp);
+    }
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    return HG_OK;
+}
+
+// ================================================================================================
 // 5. Exact path helpers.
 // ================================================================================================
 __global__ void zero_hist2_kernel(uint32_t* __restrict__ hist2, const int* __restrict__ n_fail, int64_t per_query)
@@ -1066,6 +1263,20 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
     HG_CUDA_TRY(cudaMemsetAsync(ctrl, 0, 256, st));
     int rc;
     timer.mark(kPhaseSample, st);
+    if (pl.dense && !force_exact) {
+        if (chunks && prepare && (rc = prepare_upto(chunks->K)) != HG_OK) return rc;  // the walk needs the whole database
+        timer.mark(kPhaseThreshold, st);
+        timer.mark(kPhaseExpand, st);
+        timer.mark(kPhaseSelect, st);
+        timer.mark(kPhaseAp, st);
+        DenseApParams dp{};
+        dp.q_rows = q_rows; dp.db_rows = db_rows; dp.nq = pl.nq; dp.ndb = pl.ndb; dp.R = pl.R; dp.b = pl.b; dp.LW = pl.LW; dp.Wr = pl.Wr;
+        dp.ap = d_ap; dp.ids = d_ids; dp.dist = d_dist; dp.rel = d_rel;
+        if ((rc = launch_dense_ap<W>(dp, st)) != HG_OK) return rc;
+        timer.mark(kPhaseExact, st);
+        timer.mark(kNumPhases, st);
+        return HG_OK;
+    }
     if (!force_exact) {
         // 1. sampled histogram
         HG_CUDA_TRY(cudaMemsetAsync(hist_s, 0, sizeof(uint32_t) * (size_t)pl.nq * nb, st));
@@ -1290,7 +1501,8 @@ extern "C" int hg_select_backend(int b, int L)
 extern "C" int hg_select_backend_for(int64_t nq, int64_t ndb, int b, int L, int64_t R)
 {
     const hg::Plan pl = hg::make_plan(nq, ndb, b, L, R);
-    return pl.ok ? pl.umma_kp : -1;
+    if (!pl.ok) return -1;
+    return pl.dense ? 1 : pl.umma_kp;
 }
 
 extern "C" int hg_hamming_map_stats(const void* d_workspace, size_t workspace_bytes, int64_t nq, int64_t ndb, int b, int L, int64_t R,

@@ -112,9 +112,11 @@ int hg_hamming_map_phase_ms(float out[6]);
  * <= 256); -1 = unsupported shape.  The environment variable HG_SELECT_BACKEND=popc forces 0. */
 int hg_select_backend(int b, int L);
 
-/* The kernel hg_hamming_map really uses for a whole problem (same values): short codes (b <= 32) keep the POPC kernel when
- * the top-R is a large part of the database (R * 8 > ndb, e.g. cifar_evaluation.yaml's MAP_R == DB_SIZE), where every pair
- * is a candidate and the tensor-core kernel's cheap rejection buys nothing.  HG_SELECT_BACKEND=umma lifts that rule. */
+/* The kernel hg_hamming_map really uses for a whole problem (same values, plus 1): short codes (b <= 32) keep the POPC kernel
+ * when the top-R is a large part of the database (R * 8 > ndb), where every pair is a candidate and the tensor-core kernel's
+ * cheap rejection buys nothing (HG_SELECT_BACKEND=umma lifts that rule); and 1 = no selection at all: with R * 2 >= ndb
+ * (cifar_evaluation.yaml ranks the whole database, MAP_R == DB_SIZE) dense_ap_kernel walks the packed rows directly
+ * (HG_DENSE=0 / 1 forces the choice). */
 int hg_select_backend_for(int64_t nq, int64_t ndb, int b, int L, int64_t R);
 
 /* Real-valued ranking mode -- the reference's literal behaviour on un-binarised features:

@@ -130,7 +130,8 @@ def test_row_layout_rules():
                 assert lib.hg_select_backend(b, L) == (32 if Wr in (2, 4) else 0)
     assert lib.hg_code_words(0) == 0 and lib.hg_code_words(257) == 0 and lib.hg_label_words(129) == 0 and lib.hg_row_words(64, 0) == 0
     # the kernel a whole problem gets: short codes leave the POPC kernel only for a sparse top-R (make_plan)
-    assert lib.hg_select_backend_for(1000, 54000, 32, 10, 54000) == 0          # C1: MAP_R == DB_SIZE
+    assert lib.hg_select_backend_for(1000, 54000, 32, 10, 54000) == 1          # C1: MAP_R == DB_SIZE -> dense walk, no selection
+    assert lib.hg_select_backend_for(1000, 54000, 32, 10, 20000) == 0          # dense-ish top-R on short codes: POPC select
     assert lib.hg_select_backend_for(1000, 1000000, 32, 10, 5000) == 32
     assert lib.hg_select_backend_for(10000, 1000000, 64, 10, 5000) == 64
     assert lib.hg_select_backend_for(100, 100000, 200, 10, 5000) == 256

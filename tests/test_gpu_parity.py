@@ -300,8 +300,28 @@ def test_short_codes_dense_top_r_stays_on_popc(hb, c_oracle):
     from hashgan_b200.synthetic import make_workload
 
     wl, db, q = make_workload("C1", nq=100, ndb=20000)
-    assert _native.lib().hg_select_backend_for(100, 20000, 32, 10, 20000) == 0
-    _check_against_c_oracle(hb, c_oracle, db, q, 20000)
+    assert _native.lib().hg_select_backend_for(100, 20000, 32, 10, 5000) == 0
+    _check_against_c_oracle(hb, c_oracle, db, q, 5000)
+
+
+@pytest.mark.parametrize("name,nq,ndb,R", [("C1", 130, 20000, 20000), ("C1_64", 77, 9001, 9001), ("C4", 100, 30000, 16000), ("C5", 60, 12000, 12000),
+                                           ("C2", 50, 40, 40)])
+def test_dense_top_r_walks_the_rows_directly(hb, c_oracle, name, nq, ndb, R):
+    """R >= ndb / 2 (cifar_evaluation.yaml: MAP_R == DB_SIZE): no selection, dense_ap_kernel ranks every row -- ids, distances,
+    relevant counts bit-exact, and identical to the selecting path forced by HG_DENSE=0."""
+    import os
+    from hashgan_b200 import _native
+    from hashgan_b200.synthetic import make_workload
+
+    wl, db, q = make_workload(name, nq=nq, ndb=ndb, correlated=0.3 if name in ("C1", "C4") else None)
+    assert _native.lib().hg_select_backend_for(nq, ndb, wl.b, wl.L, R) == 1
+    ap, _ = _check_against_c_oracle(hb, c_oracle, db, q, R)
+    os.environ["HG_DENSE"] = "0"
+    try:
+        ap_sel = hb.MAPs(R).per_query_ap(db, q)
+    finally:
+        del os.environ["HG_DENSE"]
+    assert np.array_equal(ap, ap_sel, equal_nan=True)
 
 
 @pytest.mark.parametrize("flags", [0, 1])
