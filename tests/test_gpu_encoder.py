@@ -170,6 +170,10 @@ def test_evaluate_loop_and_cli_surface(tmp_path):
     ref = maps_oracle.OracleMAPs(300, tie="stable").get_maps_by_feature(NS(output=codes(db2.output), label=db2.label),
                                                                           NS(output=codes(q2.output), label=q2.label))
     assert abs(val - ref) <= 1e-12
+    # EVAL.PRECISION_RECALL: the same ranking also yields precision@R / recall@R (R == DB_SIZE here: everything is retrieved)
+    pr = evaluate(enc, dl, cfg, precision_recall=True)
+    assert pr["mAP"] == val and pr["R"] == 300 and abs(pr["recall"] - 1.0) <= 1e-12
+    assert abs(pr["precision"] - np.mean(pr["per_query"]["total"] / 300.0)) <= 1e-12
 
 
 def test_tensor_core_convolution_option():
