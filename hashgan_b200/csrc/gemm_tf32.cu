@@ -13,6 +13,7 @@
 #include "umma.cuh"
 
 #include <climits>
+#include <cstdlib>
 
 namespace hg {
 
@@ -171,18 +172,23 @@ __host__ __device__ constexpr int conv_tmem_cols(int BN) { return BN <= 64 ? 64 
 // X3 = error-compensated TF32 ("3xTF32"): every fp32 operand is split into hi (its upper 19 bits, exactly a TF32 number) and
 // lo = x - hi; hi*hi + lo*hi + hi*lo accumulated in the fp32 accumulator reproduces the fp32 product to ~2^-21, so the
 // tensor-core convolution matches the fp32 graph like the CUDA-core one does.  Stage = [A hi][A lo][B hi][B lo].
-__host__ __device__ constexpr int conv_stages(int BN, bool X3) { return X3 ? (BN <= 128 ? 3 : 2) : 3; }
+// MT = M tiles (128 rows each, one accumulator each) per CTA.  With MT = 2 a weight (B) tile fetched from L2 serves 256 output
+// rows: the weight tiles are two thirds of the kernel's L2 traffic at conv2 (every 128-row CTA re-reads the whole 1.2 MB
+// filter bank of its group: 9 of 13 GB), and the kernel is bound by exactly that traffic.
+__host__ __device__ constexpr int conv_stages(int BN, bool X3, int MT) { return X3 ? (MT == 2 ? 2 : (BN <= 128 ? 3 : 2)) : 3; }
 
-template <int BN, bool X3>
-__global__ void __launch_bounds__(kGemmThreads, (!X3 && BN <= 128 ? 2 : 1))
+template <int BN, bool X3, int MT>
+__global__ void __launch_bounds__(kGemmThreads, (!X3 && BN <= 128 && MT == 1 ? 2 : 1))
 conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_blo, ConvGemmArgs a)
 {
     extern __shared__ __align__(1024) uint8_t csm[];
-    constexpr int kConvStages = conv_stages(BN, X3);
+    constexpr int kConvStages = conv_stages(BN, X3, MT);
     constexpr uint32_t A_BYTES = kGemmBM * kGemmBK * 4;  // 16 KB
     constexpr uint32_t B_BYTES = BN * kGemmBK * 4;
-    constexpr uint32_t A_ALL = (X3 ? 2 : 1) * A_BYTES;
+    constexpr uint32_t A_TILE = (X3 ? 2 : 1) * A_BYTES;   // [hi | lo] of one M tile
+    constexpr uint32_t A_ALL = MT * A_TILE;
     constexpr uint32_t STAGE_BYTES = A_ALL + (X3 ? 2 : 1) * B_BYTES;
+    constexpr uint32_t TCOLS = conv_tmem_cols(BN);           // accumulator columns of one M tile
     const uint32_t base = (smem_u32(csm) + 1023u) & ~1023u;
     uint8_t* const base_ptr = csm + (base - smem_u32(csm));
     int2* const tab = reinterpret_cast<int2*>(base_ptr + kConvStages * STAGE_BYTES);  // per 16-byte K chunk: {input offset, ky | kx << 16}
@@ -190,7 +196,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t m0 = (int64_t)blockIdx.y * kGemmBM;
+    const int64_t m0 = (int64_t)blockIdx.y * (kGemmBM * MT);
     const int n0 = blockIdx.x * BN;
     const int nkb = a.Kpad / kGemmBK;
     const int K = a.KH * a.KW * a.Cg;
@@ -210,7 +216,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)conv_tmem_cols(BN)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)(MT * TCOLS)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -236,14 +242,19 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
                 mbar_wait(&full_bar[s], (uint32_t)((kb / kConvStages) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_ALL;
-                const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sb);
+                const uint64_t bdesc = umma_desc_sw128(sb);
 #pragma unroll
-                for (int k = 0; k < kGemmBK / 8; ++k) {
-                    umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-                    if (X3) {
-                        const uint64_t alo = umma_desc_sw128(sa + A_BYTES), blo = umma_desc_sw128(sb + B_BYTES);
-                        umma_tf32(tmem_base, alo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
-                        umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc, 1u);
+                for (int mt = 0; mt < MT; ++mt) {
+                    const uint64_t adesc = umma_desc_sw128(sa + mt * A_TILE);
+                    const uint32_t acc = tmem_base + (uint32_t)(mt * TCOLS);
+#pragma unroll
+                    for (int k = 0; k < kGemmBK / 8; ++k) {
+                        umma_tf32(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                        if (X3) {
+                            const uint64_t alo = umma_desc_sw128(sa + mt * A_TILE + A_BYTES), blo = umma_desc_sw128(sb + B_BYTES);
+                            umma_tf32(acc, alo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                            umma_tf32(acc, adesc + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), idesc, 1u);
+                        }
                     }
                 }
                 umma_commit(&empty_bar[s]);
@@ -254,51 +265,59 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
         // ---- producer: gather the A tiles (thread g: 16-byte chunk g & 7 of rows (g >> 3) + 16 i) ----
         const int g = threadIdx.x - 64;
         const int chunk = g & 7;
-        int rbase[8];      // input offset of the window origin of row i (floats), INT_MIN: row beyond M
-        int ryx[8];        // (iy0 + 1024) | (ix0 + 1024) << 16
-        uint32_t soff[8];  // byte offset of my chunk inside an A stage
+        int rbase[MT][8];  // input offset of the window origin of row i of M tile mt (floats), INT_MIN: row beyond M
+        int ryx[MT][8];    // (iy0 + 1024) | (ix0 + 1024) << 16
+        uint32_t soff[8];  // byte offset of my chunk inside an A tile
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int r = (g >> 3) + 16 * i;
-            const int64_t m = m0 + r;
             soff[i] = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
-            if (m < a.M) {
-                const int ox = (int)(m % a.Wo), oy = (int)((m / a.Wo) % a.Ho);
-                const int64_t n = m / ((int64_t)a.Wo * a.Ho);
-                const int iy0 = oy * a.stride - a.pad, ix0 = ox * a.stride - a.pad;
-                rbase[i] = (int)(((n * a.H + iy0) * a.W + ix0) * a.C + a.c0);
-                ryx[i] = (iy0 + 1024) | ((ix0 + 1024) << 16);
-            } else {
-                rbase[i] = INT_MIN;
-                ryx[i] = 0;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int64_t m = m0 + mt * kGemmBM + r;
+                if (m < a.M) {
+                    const int ox = (int)(m % a.Wo), oy = (int)((m / a.Wo) % a.Ho);
+                    const int64_t n = m / ((int64_t)a.Wo * a.Ho);
+                    const int iy0 = oy * a.stride - a.pad, ix0 = ox * a.stride - a.pad;
+                    rbase[mt][i] = (int)(((n * a.H + iy0) * a.W + ix0) * a.C + a.c0);
+                    ryx[mt][i] = (iy0 + 1024) | ((ix0 + 1024) << 16);
+                } else {
+                    rbase[mt][i] = INT_MIN;
+                    ryx[mt][i] = 0;
+                }
             }
         }
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % kConvStages;
             const int2 t = tab[kb * 8 + chunk];
             const int ky = t.y & 0xffff, kx = t.y >> 16;
-            float4 v[8];
+            float4 v[MT][8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int iy = (ryx[i] & 0xffff) - 1024 + ky, ix = (ryx[i] >> 16) - 1024 + kx;
-                if (t.x >= 0 && rbase[i] != INT_MIN && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
-                    v[i] = __ldg(reinterpret_cast<const float4*>(a.in + rbase[i] + t.x));
-            }
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    v[mt][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int iy = (ryx[mt][i] & 0xffff) - 1024 + ky, ix = (ryx[mt][i] >> 16) - 1024 + kx;
+                    if (t.x >= 0 && rbase[mt][i] != INT_MIN && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+                        v[mt][i] = __ldg(reinterpret_cast<const float4*>(a.in + rbase[mt][i] + t.x));
+                }
             mbar_wait(&empty_bar[s], (uint32_t)(((kb / kConvStages) & 1) ^ 1));  // the loads above are already in flight
-            uint8_t* sa = base_ptr + s * STAGE_BYTES;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (X3) {
-                    float4 hi, lo;
-                    hi.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u); lo.x = v[i].x - hi.x;
-                    hi.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u); lo.y = v[i].y - hi.y;
-                    hi.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u); lo.z = v[i].z - hi.z;
-                    hi.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u); lo.w = v[i].w - hi.w;
-                    *reinterpret_cast<float4*>(sa + soff[i]) = hi;
-                    *reinterpret_cast<float4*>(sa + A_BYTES + soff[i]) = lo;
-                } else {
-                    *reinterpret_cast<float4*>(sa + soff[i]) = v[i];
+            for (int mt = 0; mt < MT; ++mt) {
+                uint8_t* sa = base_ptr + s * STAGE_BYTES + mt * A_TILE;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (X3) {
+                        float4 hi, lo;
+                        hi.x = __uint_as_float(__float_as_uint(v[mt][i].x) & 0xFFFFE000u); lo.x = v[mt][i].x - hi.x;
+                        hi.y = __uint_as_float(__float_as_uint(v[mt][i].y) & 0xFFFFE000u); lo.y = v[mt][i].y - hi.y;
+                        hi.z = __uint_as_float(__float_as_uint(v[mt][i].z) & 0xFFFFE000u); lo.z = v[mt][i].z - hi.z;
+                        hi.w = __uint_as_float(__float_as_uint(v[mt][i].w) & 0xFFFFE000u); lo.w = v[mt][i].w - hi.w;
+                        *reinterpret_cast<float4*>(sa + soff[i]) = hi;
+                        *reinterpret_cast<float4*>(sa + A_BYTES + soff[i]) = lo;
+                    } else {
+                        *reinterpret_cast<float4*>(sa + soff[i]) = v[mt][i];
+                    }
                 }
             }
             fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
@@ -311,11 +330,13 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
         const int quarter = warp & 3;
         mbar_wait(&tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int64_t row = m0 + quarter * 32 + lane;
+#pragma unroll 1
+        for (int mt = 0; mt < MT; ++mt) {
+        const int64_t row = m0 + mt * kGemmBM + quarter * 32 + lane;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * TCOLS + c0);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -348,12 +369,13 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
                 }
             }
         }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)conv_tmem_cols(BN)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(MT * TCOLS)) : "memory");
     }
 }
 
@@ -386,20 +408,32 @@ static int make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t K,
     return HG_OK;
 }
 
-template <int BN, bool X3>
-static int launch_conv_gemm(const CUtensorMap& tb, const CUtensorMap& tblo, const ConvGemmArgs& a, cudaStream_t st)
+template <int BN, bool X3, int MT>
+static int launch_conv_gemm_mt(const CUtensorMap& tb, const CUtensorMap& tblo, const ConvGemmArgs& a, cudaStream_t st)
 {
-    const size_t smem = (size_t)conv_stages(BN, X3) * (X3 ? 2 : 1) * (kGemmBM + BN) * kGemmBK * 4 + (size_t)(a.Kpad / 4) * sizeof(int2) + 1024;
+    const size_t smem = (size_t)conv_stages(BN, X3, MT) * (X3 ? 2 : 1) * (MT * kGemmBM + BN) * kGemmBK * 4 + (size_t)(a.Kpad / 4) * sizeof(int2) + 1024;
     static thread_local size_t configured = 0;
     if (smem > configured) {
-        HG_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HG_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN, X3, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    dim3 grid((unsigned)ceil_div(a.Cog, BN), (unsigned)ceil_div(a.M, kGemmBM));
-    conv_gemm_tf32_kernel<BN, X3><<<grid, kGemmThreads, smem, st>>>(tb, tblo, a);
+    dim3 grid((unsigned)ceil_div(a.Cog, BN), (unsigned)ceil_div(a.M, kGemmBM * MT));
+    conv_gemm_tf32_kernel<BN, X3, MT><<<grid, kGemmThreads, smem, st>>>(tb, tblo, a);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     return HG_OK;
+}
+
+// two M tiles per CTA for the error-compensated mode (BN <= 128: 2 stages x 96 KB; BN = 192 would need 2 x 112 KB plus the tap
+// table) when there are enough rows; HG_CONV_MT=1 keeps one tile per CTA
+template <int BN, bool X3>
+static int launch_conv_gemm(const CUtensorMap& tb, const CUtensorMap& tblo, const ConvGemmArgs& a, cudaStream_t st)
+{
+    static const int mt_env = []() { const char* v = getenv("HG_CONV_MT"); return (v && *v) ? atoi(v) : 0; }();
+    if constexpr (X3 && BN <= 128) {
+        if (mt_env != 1 && a.M >= 2 * kGemmBM) return launch_conv_gemm_mt<BN, X3, 2>(tb, tblo, a, st);
+    }
+    return launch_conv_gemm_mt<BN, X3, 1>(tb, tblo, a, st);
 }
 
 // one channel group of a convolution layer; wt = this group's weights [Cog, Kpad] K-major (hg_conv_weight_pack: upper 19
