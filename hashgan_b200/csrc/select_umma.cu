@@ -452,6 +452,176 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
     }
 }
 
+// ---- bitmap mode ---------------------------------------------------------------------------------------------------
+// Same contraction, but the epilogue only WRITES THE HIT MASKS: bit r of query q's bitmap row says d_H(q, row r) <= T_q.
+// Walking the ~R/Ndb hits inside the epilogue (select_umma_kernel) costs 45 instructions per divergent step at 23 % lane
+// occupancy -- two thirds of that kernel's instructions; here a warp-tile is wait + 2 x (tcgen05.ld, 8 PRMT, 8 multiply-add)
+// + one 8-byte store, and ap_bm_kernel (rank.cu) walks the bitmap with every lane busy.  Nothing but the int8 operands is
+// staged in shared memory, so the MMA warp itself frees a ring stage (tcgen05.commit) and the ring is deeper.
+template <int KP> struct BmCfg {
+    static constexpr int S = (KP == 32 ? 8 : (KP == 64 ? 6 : 4));
+};
+
+template <int KP>
+__global__ void __launch_bounds__(kUmmaThreads, UmmaCfg<KP>::CTAS)
+select_bm_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_constant__ CUtensorMap tmap_db8, const __grid_constant__ CUtensorMap tmap_qx,
+                 const __grid_constant__ CUtensorMap tmap_bx, UmmaSelectArgs a)
+{
+    constexpr int S = BmCfg<KP>::S;
+    constexpr int KB = UmmaCfg<KP>::KB, KW = UmmaCfg<KP>::KW;
+    constexpr uint32_t A_BYTES = 2 * 128 * KP;
+    constexpr uint32_t AX_BYTES = 2 * 128 * kUmmaXBytes;
+    constexpr uint32_t BX_BYTES = 128 * kUmmaXBytes;
+    constexpr uint32_t FIXED_BYTES = A_BYTES + AX_BYTES + BX_BYTES;
+    constexpr uint32_t STAGE_BYTES = 128 * KP;
+    extern __shared__ __align__(1024) uint8_t usm[];
+    const uint32_t base = (smem_u32(usm) + 1023u) & ~1023u;
+    __shared__ __align__(8) uint64_t bars[2 * S + 5];
+    __shared__ uint32_t tmem_base_slot;
+    uint64_t& a_full = bars[0];
+    uint64_t* const full_bar = bars + 1;
+    uint64_t* const empty_bar = bars + 1 + S;
+    uint64_t* const tmem_full = bars + 2 * S + 1;
+    uint64_t* const tmem_empty = bars + 2 * S + 3;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q0 = (int64_t)blockIdx.x * 256;
+    const int split_a = a.split0 + 2 * (int)blockIdx.y;
+    const int64_t rowa = (int64_t)split_a * a.SL;
+    const int64_t rows_first = max((int64_t)0, min(a.SL, a.ndb - rowa));
+    const int ntiles = (int)((rows_first + kUmmaHalfRows - 1) / kUmmaHalfRows);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&a_full, 1);
+        for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int h = 0; h < 2; ++h) { mbar_init(&tmem_full[h], 1); mbar_init(&tmem_empty[h], kUmmaEpiWarps / 2); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&a_full, FIXED_BYTES);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb)
+                    tma_load_2d(base + (uint32_t)((hh * KB + kb) * 128 * KW), &tmap_q8, smem_u32(&a_full), kb * KW, (int)q0 + hh * 128);
+            tma_load_2d(base + A_BYTES, &tmap_qx, smem_u32(&a_full), 0, (int)q0);
+            tma_load_2d(base + A_BYTES + 128 * kUmmaXBytes, &tmap_qx, smem_u32(&a_full), 0, (int)q0 + 128);
+            tma_load_2d(base + A_BYTES + AX_BYTES, &tmap_bx, smem_u32(&a_full), 0, 0);
+            tma_load_2d(base + A_BYTES + AX_BYTES + 64 * kUmmaXBytes, &tmap_bx, smem_u32(&a_full), 0, 64);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % S;
+                mbar_wait(&empty_bar[s], (uint32_t)(((t / S) & 1) ^ 1));
+                mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                const uint32_t sb = base + FIXED_BYTES + s * STAGE_BYTES;
+                const int ra = (int)(rowa + (int64_t)t * kUmmaHalfRows);
+                const int rb = (int)(rowa + a.SL + (int64_t)t * kUmmaHalfRows);
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    tma_load_2d(sb + (uint32_t)(kb * 128 * KW), &tmap_db8, smem_u32(&full_bar[s]), kb * KW, ra);
+                    tma_load_2d(sb + (uint32_t)(kb * 128 * KW + 64 * KW), &tmap_db8, smem_u32(&full_bar[s]), kb * KW, rb);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_i8(128, 128);
+            mbar_wait(&a_full, 0);
+            const uint64_t bxdesc = umma_desc_kmajor(base + A_BYTES + AX_BYTES, kUmmaXBytes);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % S;
+                mbar_wait(&full_bar[s], (uint32_t)((t / S) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t b_addr = base + FIXED_BYTES + s * STAGE_BYTES;
+                uint32_t todo = 3u;
+                while (todo) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (!(todo & (1u << h))) continue;
+                        if (todo == (1u << h)) mbar_wait(&tmem_empty[h], (uint32_t)((t & 1) ^ 1));
+                        else if (!mbar_try(&tmem_empty[h], (uint32_t)((t & 1) ^ 1))) continue;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                        for (int kb = 0; kb < KB; ++kb) {
+                            const uint64_t adesc = umma_desc_kmajor(base + (uint32_t)((h * KB + kb) * 128 * KW), KW);
+                            const uint64_t bdesc = umma_desc_kmajor(b_addr + (uint32_t)(kb * 128 * KW), KW);
+#pragma unroll
+                            for (int k = 0; k < KW / 32; ++k)
+                                umma_i8(tmem_base + (uint32_t)(h * 128), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                        }
+                        umma_i8(tmem_base + (uint32_t)(h * 128), umma_desc_kmajor(base + A_BYTES + h * 128 * kUmmaXBytes, kUmmaXBytes), bxdesc, idesc, 1u);
+                        umma_commit(&tmem_full[h]);
+                        todo &= ~(1u << h);
+                    }
+                }
+                umma_commit(&empty_bar[s]);  // both halves have read the stage once their MMAs retire: the producer may refill it
+            }
+        }
+    } else {
+        // ---- epilogue: thread <-> (query, split).  The bitmap is CHUNK-major: chunk c = rows [128 c, 128 c + 128) of all queries,
+        // one uint4 per query, so the four mask words of a tile pair leave the warp as one coalesced 512-byte store ----
+        const int e = warp - 2;
+        const int quarter = warp & 3;
+        const int h = (e >> 2) & 1;
+        const int ch = e >> 3;
+        const int64_t slot = q0 + h * 128 + quarter * 32 + lane;
+        const int split = split_a + ch;
+        const int64_t row0 = (int64_t)split * a.SL;
+        const int64_t nrows = max((int64_t)0, min(a.SL, a.ndb - row0));
+        const bool valid = slot < a.nq && split < a.P;
+        const uint32_t sel = a.prmt_sel;
+        int Tq = -1;
+        if (valid) Tq = a.thr[slot];
+        const uint32_t live = (valid && Tq >= 0) ? 0xFFFFFFFFu : 0u;
+        uint4* out = reinterpret_cast<uint4*>(a.bitmap) + (valid ? (row0 >> 7) * a.bm_stride + slot : 0);
+        const int64_t ostride = a.bm_stride;  // uint4 per chunk (queries, padded to 32)
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 128 + ch * 64);
+        uint32_t bar0 = smem_u32(&bars[0]);
+        asm volatile("" : "+r"(bar0));
+        const uint32_t tfull_a = bar0 + 8u * (2 * S + 1 + h), tempty_a = bar0 + 8u * (2 * S + 3 + h);
+        const int nrows32 = (int)nrows;
+        const int nfull = nrows32 / kUmmaHalfRows;
+        uint32_t tph = 0;
+        auto tile_masks = [&](int t, uint32_t& h0, uint32_t& h1) {
+            mbar_wait_a(tfull_a, tph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t m0 = hit_mask32(tmem_row, sel);
+            const uint32_t m1 = hit_mask32(tmem_row + 32u, sel);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(tempty_a);
+            h0 = m0 & live; h1 = m1 & live;
+            if (t >= nfull) {
+                const int left = nrows32 - t * kUmmaHalfRows;
+                h0 &= left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
+                h1 &= left <= 32 ? 0u : ((1u << (left - 32)) - 1u);
+            }
+            tph ^= 1u;
+        };
+        for (int t = 0; t < ntiles; t += 2) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            tile_masks(t, v.x, v.y);
+            if (t + 1 < ntiles) tile_masks(t + 1, v.z, v.w);
+            if (valid && !(a.dbg & 1)) out[(int64_t)(t >> 1) * ostride] = v;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------
 // [rows, row_bytes] bytes, boxes of box_rows x box_bytes (box_bytes = the swizzle width: 32 / 64 / 128; row_bytes = 256
 // is read as two 128-byte column blocks)
@@ -551,6 +721,22 @@ static int launch_umma(const CUtensorMap& tq, const CUtensorMap& tdb, const CUte
     return HG_OK;
 }
 
+template <int KP>
+static int launch_bm(const CUtensorMap& tq, const CUtensorMap& tdb, const CUtensorMap& tqx, const CUtensorMap& tbx, const UmmaSelectArgs& a, cudaStream_t st)
+{
+    const size_t smem = (size_t)2 * 128 * KP + (size_t)3 * 128 * kUmmaXBytes + (size_t)BmCfg<KP>::S * (128 * KP) + 1024;
+    static thread_local bool configured = false;
+    if (!configured) {
+        HG_CUDA_TRY(cudaFuncSetAttribute(select_bm_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((unsigned)ceil_div(a.nq, 256), (unsigned)ceil_div(a.n_splits, 2));
+    select_bm_kernel<KP><<<grid, kUmmaThreads, smem, st>>>(tq, tdb, tqx, tbx, a);
+    count_launch();
+    HG_CUDA_TRY(cudaGetLastError());
+    return HG_OK;
+}
+
 int umma_select_launch(const UmmaSelectArgs& a_in, cudaStream_t st)
 {
     UmmaSelectArgs a = a_in;
@@ -566,9 +752,17 @@ int umma_select_launch(const UmmaSelectArgs& a_in, cudaStream_t st)
     a.rows_paired = a.Wr == 2 ? 1 : 0;
     if ((rc = make_map_u8(&tq, a.q8, a.nq, a.KP, 128, kw)) != HG_OK) return rc;
     if ((rc = make_map_u8(&tdb, a.db8, round_up(a.ndb, 32), a.KP, kUmmaHalfRows, kw)) != HG_OK) return rc;
-    if ((rc = make_map_rows(&trows, a.db_rows, a.ndb, a.Wr)) != HG_OK) return rc;
     if ((rc = make_map_u8(&tqx, a.qx, std::max<int64_t>(round_up(a.nq, 256), 128), kUmmaXBytes, 128)) != HG_OK) return rc;
     if ((rc = make_map_u8(&tbx, a.bx, 128, kUmmaXBytes, kUmmaHalfRows)) != HG_OK) return rc;
+    if (a.bitmap) {  // bitmap mode: hit masks only (ap_bm_kernel does the rest)
+        { const char* v = getenv("HG_BM_DEBUG"); a.dbg = (v && *v) ? atoi(v) : 0; }
+        if (a.SL & 127) return fail(HG_EINVAL, "select_umma: bitmap mode needs splits of whole 128-row chunks");
+        if (a.KP == 32) return launch_bm<32>(tq, tdb, tqx, tbx, a, st);
+        if (a.KP == 64) return launch_bm<64>(tq, tdb, tqx, tbx, a, st);
+        if (a.KP == 128) return launch_bm<128>(tq, tdb, tqx, tbx, a, st);
+        return launch_bm<256>(tq, tdb, tqx, tbx, a, st);
+    }
+    if ((rc = make_map_rows(&trows, a.db_rows, a.ndb, a.Wr)) != HG_OK) return rc;
     if (a.KP == 32) return launch_umma<32, 0>(tq, tdb, trows, tqx, tbx, a, st);
     if (a.KP == 64) return (a.W == 2 && a.Wr == 4) ? launch_umma<64, 1>(tq, tdb, trows, tqx, tbx, a, st) : launch_umma<64, 0>(tq, tdb, trows, tqx, tbx, a, st);
     if (a.KP == 128) return (a.W == 4 && a.Wr == 8) ? launch_umma<128, 2>(tq, tdb, trows, tqx, tbx, a, st) : launch_umma<128, 0>(tq, tdb, trows, tqx, tbx, a, st);
