@@ -73,9 +73,8 @@ struct UmmaSelectArgs {
     const uint8_t* db8;  // [round_up(ndb, 32), KP], rows of every 32-row group permuted (select_umma.cu)
     const uint8_t* qx;   // [round_up(nq, 256), 32] threshold columns of the A operand
     const uint8_t* bx;   // [128, 32] threshold columns of the B operand (constant)
-    uint32_t* bitmap;    // bitmap mode (non-null): hit masks only, chunk-major: uint4 [P * SL / 128 chunks][bm_stride queries], bit r % 128 of chunk r / 128 = row r
-    int64_t bm_stride;   // queries per chunk of the bitmap (nq rounded up to 32)
-    int dbg;             // experiments (HG_BM_DEBUG)
+    int queued;          // 1 = select_q_kernel where it applies (parked mask words), 0 = select_umma_kernel (hits walked tile by tile)
+    int drain_lanes;     // queued mode: lanes that must have parked work before a waiting warp spends a hit step
     uint32_t prmt_sel;   // PRMT selector of the epilogue's sign gather
     int rows_paired;     // set by the launcher: 2-word packed rows are staged as 16-byte row pairs
 };

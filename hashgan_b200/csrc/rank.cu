@@ -36,10 +36,7 @@ struct Plan {
     int b = 0, L = 0, W = 0, LW = 0, Wr = 0, QT = 0, TQ = 0, TILE = 0, P = 0, nqt = 0;
     int umma_kp = 0;  // > 0: the fast-path select runs on the tensor cores (select_umma.cu), int8 rows of this many bytes
     bool dense = false;  // R is a large part of the database: no selection at all, dense_ap_kernel walks the packed rows
-    bool bitmap = false; // tensor-core select writes hit bitmaps (select_bm_kernel), ap_bm_kernel ranks from them: no candidate bins
-    int64_t bm_stride = 0;  // queries per chunk of the bitmap (nq rounded up to 32)
-    uint32_t capL = 0;      // entries per (query, warp) list of ap_bm_kernel
-    int apG = 0;            // warps per 32-query CTA of ap_bm_kernel
+    bool queued = false; // select_q_kernel (mask words parked, hits consumed asynchronously) instead of select_umma_kernel
     int64_t nq = 0, ndb = 0, R = 0, SL = 0;
     uint32_t cap = 0;
     // sample pass
@@ -47,7 +44,7 @@ struct Plan {
     int seg_per_chunk = 0, n_chunks = 0;
     // workspace byte offsets
     size_t off_ctrl = 0, off_thr = 0, off_thr2 = 0, off_fail = 0, off_wide = 0, off_hist_s = 0, off_bin_cnt = 0, off_bin_cnt0 = 0, off_bin_cnt2 = 0,
-           off_bin_off2 = 0, off_bin_cap2 = 0, off_quota2 = 0, off_hist2 = 0, off_lists = 0, off_bitmap = 0, off_q8 = 0, off_db8 = 0, off_qx = 0, off_bx = 0, total = 0;
+           off_bin_off2 = 0, off_bin_cap2 = 0, off_quota2 = 0, off_hist2 = 0, off_lists = 0, off_q8 = 0, off_db8 = 0, off_qx = 0, off_bx = 0, total = 0;
     bool ok = false;
 };
 
@@ -66,20 +63,6 @@ static int env_int(const char* name, int fallback)
 {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : fallback;
-}
-
-// warps per 32-query CTA of ap_bm_kernel and its dynamic shared memory
-static size_t ap_bm_smem(int G, int ncol, bool window)
-{
-    const size_t k = window ? 1 : 2;
-    return sizeof(uint32_t) * (k * ncol * 32 * (size_t)G + 4 * 32 + k * ncol * 32) + (sizeof(double) * 2 + sizeof(int)) * 32 * (size_t)G + 16;
-}
-static int ap_bm_warps(int b, bool window)
-{
-    int G = env_int("HG_AP_G", 16);
-    G = std::max(1, std::min(32, G));
-    while (G > 1 && ap_bm_smem(G, window ? 32 : b + 1, window) > (window ? 100 : 200) * 1024) G >>= 1;
-    return G;
 }
 
 static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas_mult = 1)
@@ -161,17 +144,13 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
     while (cap * p.P < R) cap += 8;  // the exact path reuses the list area and needs R entries per query
     p.cap = (uint32_t)cap;
     {
-        // HG_SELECT_MODE=lists keeps the round-1 organisation (hits appended to per-(query, split) bins inside the select kernel)
+        // The queued select (select_q_kernel) pays off while hits are sparse: at most ~2 per lane and 64-row tile (C4: 0.57); a dense
+        // top-R (C2: 5.8) keeps the kernel that walks the hits from the staged tile.  HG_SELECT_MODE=lists / queue forces the choice.
         const char* mode = getenv("HG_SELECT_MODE");
-        p.apG = ap_bm_warps(b, true);
-        const int64_t range_rows = (ceil_div(ndb, 128) / p.apG + 1) * 128;  // rows of one warp's range in ap_bm_kernel
-        p.bitmap = p.umma_kp > 0 && !(mode && mode[0] == 'l') && (SL % 128) == 0 && range_rows <= kMaxSplitRows;
-        p.bm_stride = round_up(nq, 32);
-        // per-thread candidate lists of ap_bm_kernel: 6 R / G entries (the expected count is ~1.8 R / G; a thread that overflows only
-        // costs its query a second bitmap walk), never more than the rows of its range
-        p.capL = (uint32_t)std::min<int64_t>(round_up(range_rows, 8), round_up(std::max<int64_t>(256, 6 * R / p.apG + 64), 8));
+        const bool sparse = 64.0 * 1.8 * (double)R <= 2.0 * (double)ndb;
+        p.queued = p.umma_kp == 64 && p.W == 2 && p.Wr == 4 && (mode && mode[0] == 'l' ? false : (mode && mode[0] == 'q' ? true : sparse));
     }
-    if ((!p.bitmap && (double)nq * p.P * (double)cap >= 4294967295.0) || (double)nq * (double)R >= 4294967295.0)
+    if ((double)nq * p.P * (double)cap >= 4294967295.0 || (double)nq * (double)R >= 4294967295.0)
         return p;  // bins are addressed with 32-bit word offsets: the caller must split the query batch
     // sample: kSampleTarget rows in TILE-row segments spread evenly; the whole db when it is small
     const int64_t tiles_total = ceil_div(ndb, p.TILE);
@@ -208,10 +187,7 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
     p.off_bin_cap2 = take(sizeof(uint32_t) * bins);
     p.off_quota2 = take(sizeof(uint32_t) * bins);
     p.off_hist2 = take(sizeof(uint32_t) * bins * (b + 1));
-    // bitmap mode: the list area only serves the exact path (R entries per failed query)
-    // bitmap mode: per-(query, warp) lists; the exact path reuses the area and needs R entries per query (capL * G >= R by construction)
-    p.off_lists = take(sizeof(uint32_t) * (p.bitmap ? (size_t)nq * p.apG * p.capL : bins * p.cap));
-    if (p.bitmap) p.off_bitmap = take(sizeof(uint4) * (size_t)p.bm_stride * (size_t)((int64_t)p.P * SL / 128));
+    p.off_lists = take(sizeof(uint32_t) * bins * p.cap);
     if (p.umma_kp) {
         p.off_q8 = take((size_t)nq * p.umma_kp);
         p.off_db8 = take((size_t)round_up(ndb, 128) * p.umma_kp);
@@ -853,342 +829,6 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
 }
 
 // ================================================================================================
-// 4a. AP kernel of the bitmap mode (select_bm_kernel wrote one bit per (query, row): d <= T_q, chunk-major: chunk c holds rows
-//     [128 c, 128 c + 128) of every query as one uint4 per query).  A CTA serves 32 consecutive queries with G warps:
-//     lane <-> query, warp g <-> the g-th contiguous range of chunks (warp order == row order), so the bitmap loads of a warp
-//     are 16 bytes per lane at consecutive addresses.
-//       phase A  every lane walks ITS query's chunks as a state machine in one flat loop: the lanes do not wait for each other
-//                at chunk boundaries, so a hit step has ~70 % of the lanes busy (the hit loop inside select_umma_kernel ran at
-//                23 %).  Two chunks are in flight ahead of the one being consumed and the packed row of hit i + 1 is requested
-//                before hit i is consumed (random 16-byte gathers from the L2-resident database).  Per hit: distance and
-//                relevance from the packed row, private per-distance counters, entry appended to the thread's private list.
-//       phase A2 rank bases: per (query, distance) exclusive scan over the G warps and running totals over the distances,
-//                through shared memory (the counters already live there).
-//       phase B  walk the thread's list: rank / relevant-prefix from the counters, fp64 AP; a query with an overflowed list
-//                (candidates concentrated in a few row ranges: a class-sorted database) re-walks the bitmap instead.
-//     WINDOW packs the two 16-bit counters of a distance into one shared-memory word (one load, one store per hit).
-//     No bins, so nothing overflows fatally: the only way to the exact path is a threshold that admitted fewer than R rows.
-// ================================================================================================
-struct ApBmParams {
-    const uint32_t* q_rows;
-    const uint32_t* db_rows;
-    int64_t nq, ndb, R;
-    int b, W, LW, Wr, G;
-    const uint4* bitmap;  // [chunks][bm_stride] uint4
-    int64_t bm_stride;    // queries per chunk (nq rounded up to 32)
-    uint32_t* lists;      // [nq, G, capL] entries
-    uint32_t capL;
-    const int* n_active;  // indirect mode: number of listed queries
-    const int* qlist;     // indirect mode: query ids (wide list)
-    const int* thr;
-    double* ap;
-    uint32_t* ids;
-    uint16_t* dist;
-    int32_t* rel;
-    int* fail_list;
-    int* n_fail;
-    int* wide_list;
-    int* n_wide;
-    int* n_rewalk;        // statistics: queries that took the bitmap re-walk in phase B
-    int no_fallback;
-};
-
-template <int MODE> struct RowData { uint4 a, b; };  // packed row of a pending hit (b: MODE 2 only; unused members cost nothing)
-
-// MODE 1: two code words in 4-word rows (C4), 2: four code words in 8-word rows (C5), 0: generic
-template <int MODE, bool WINDOW>
-__global__ void __launch_bounds__(1024) ap_bm_kernel(ApBmParams p)
-{
-    extern __shared__ __align__(16) uint32_t smem[];
-    const int NTB = blockDim.x;
-    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
-    const int G = p.G;
-    const int nb = p.b + 1;
-    const int ncol = WINDOW ? 32 : nb;
-    // WINDOW: cN[c * NTB] = relevant count << 16 | count; else cN / cM are separate 32-bit columns
-    uint32_t* cN = smem + tid;
-    uint32_t* cM = cN + (size_t)ncol * NTB;
-    // per-query scratch behind the counters: [0] candidates, [1] min distance, [2] max distance, [3] flags (1 = re-walk, 2 = dead)
-    uint32_t* qs = smem + (size_t)(WINDOW ? 1 : 2) * ncol * NTB;  // [4][32]
-    uint32_t* colbase = qs + 4 * 32;                             // [ncol][32] (x2 when !WINDOW): totals -> bases per (distance, query)
-    double* red = reinterpret_cast<double*>(colbase + (size_t)(WINDOW ? 1 : 2) * ncol * 32);  // [G][32][2] AP partial sums; then int [G][32]
-    const int64_t n_act = p.qlist ? (int64_t)*p.n_active : p.nq;
-    const int64_t slot = (int64_t)blockIdx.x * 32 + lane;
-    if ((int64_t)blockIdx.x * 32 >= n_act) return;  // whole CTA beyond the active queries
-    const bool active = slot < n_act;
-    const int64_t q = active ? (p.qlist ? (int64_t)p.qlist[slot] : slot) : 0;
-    const int T = active ? p.thr[q] : -1;
-    const int W = MODE == 1 ? 2 : (MODE == 2 ? 4 : p.W), LW = p.LW, Wr = MODE == 1 ? 4 : (MODE == 2 ? 8 : p.Wr);
-
-    for (int c = 0; c < ncol; ++c) {
-        cN[c * NTB] = 0;
-        if (!WINDOW) cM[c * NTB] = 0;
-    }
-    if (g == 0) { qs[lane] = 0; qs[32 + lane] = 0xffffffffu; qs[64 + lane] = 0; qs[96 + lane] = 0; }
-
-    uint32_t qw[8], ql[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int w = 0; w < 8; ++w) qw[w] = 0;
-    {
-        const uint32_t* qr = p.q_rows + q * Wr;
-#pragma unroll
-        for (int w = 0; w < 8; ++w)
-            if (w < W) qw[w] = __ldg(qr + w);
-#pragma unroll
-        for (int w = 0; w < 4; ++w)
-            if (w < LW) ql[w] = __ldg(qr + W + w);
-    }
-    __syncthreads();
-
-    // my chunks (128 rows each): warp g owns [c0, c1)
-    const int nchunks = (int)((p.ndb + 127) >> 7);
-    const int c0 = (int)((int64_t)g * nchunks / G), c1 = (int)((int64_t)(g + 1) * nchunks / G);
-    const uint32_t row_base = (uint32_t)c0 * 128u;
-    const uint4* bmq = p.bitmap + q;
-    const int64_t cstride = p.bm_stride;
-    uint32_t* mylist = p.lists + ((size_t)q * G + g) * p.capL;
-    asm volatile("" : "+l"(mylist));  // keep the list base in registers
-    const uint32_t capL = p.capL;
-    const uint32_t* const db_rows = p.db_rows;
-
-    auto fetch = [&](uint32_t row, RowData<MODE>& r) {
-        if (MODE == 1) r.a = __ldg(reinterpret_cast<const uint4*>(db_rows + (size_t)row * 4));
-        if (MODE == 2) {
-            const uint4* pr = reinterpret_cast<const uint4*>(db_rows + (size_t)row * 8);
-            r.a = __ldg(pr);
-            r.b = __ldg(pr + 1);
-        }
-    };
-    // distance and relevance of one row
-    auto probe = [&](uint32_t row, const RowData<MODE>& r, uint32_t& d, uint32_t& m) {
-        if (MODE == 1) {
-            d = __popc(qw[0] ^ r.a.x) + __popc(qw[1] ^ r.a.y);
-            m = ((ql[0] & r.a.z) | (ql[1] & r.a.w)) ? 1u : 0u;
-        } else if (MODE == 2) {
-            const uint4 pc = r.a, pl = r.b;
-            d = __popc(qw[0] ^ pc.x) + __popc(qw[1] ^ pc.y) + __popc(qw[2] ^ pc.z) + __popc(qw[3] ^ pc.w);
-            m = ((ql[0] & pl.x) | (ql[1] & pl.y) | (ql[2] & pl.z) | (ql[3] & pl.w)) ? 1u : 0u;
-        } else {
-            const uint32_t* prow = db_rows + (size_t)row * Wr;
-            uint32_t dd = 0, mm = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w)
-                if (w < W) dd += __popc(qw[w] ^ __ldg(prow + w));
-#pragma unroll
-            for (int w = 0; w < 4; ++w)
-                if (w < LW) mm |= ql[w] & __ldg(prow + W + w);
-            d = dd;
-            m = mm ? 1u : 0u;
-        }
-    };
-    // Per-lane state machine, ONE flat loop.  An iteration (1) refills an exhausted chunk (two more are in flight; a load may
-    // name a chunk past the lane's range -- clamped to the last chunk, its value is never used), (2) takes at most one hit
-    // off the chunk and requests its packed row, (3) consumes the hit found one iteration earlier, whose row has arrived by
-    // now.  A lane idles only when the refilled chunk is empty too; there is no inner loop at which lanes wait for each other.
-    auto walk_bitmap = [&](auto&& fn) {
-        const int clast = nchunks - 1;
-        int c = c0;
-        bool more = active && c0 < c1;
-        const uint4 zero4 = make_uint4(0, 0, 0, 0);
-        uint4 cur = more ? __ldg(bmq + (int64_t)c * cstride) : zero4;
-        uint4 n1 = __ldg(bmq + (int64_t)min(c + 1, clast) * cstride);
-        uint4 n2 = __ldg(bmq + (int64_t)min(c + 2, clast) * cstride);
-        bool pv = false;
-        uint32_t prow = 0;
-        RowData<MODE> pdat;
-        while (more || pv) {
-            bool have = false;
-            uint32_t row = 0;
-            RowData<MODE> dat;
-            if (more) {
-                if ((cur.x | cur.y | cur.z | cur.w) == 0u) {
-                    ++c;
-                    cur = n1;
-                    n1 = n2;
-                    n2 = __ldg(bmq + (int64_t)min(c + 2, clast) * cstride);
-                    more = c < c1;
-                }
-                if (more && (cur.x | cur.y | cur.z | cur.w) != 0u) {
-                    // lowest set bit of the 128-bit chunk, branch-free (the lanes of a warp are in different words)
-                    const bool px = cur.x != 0u, py = cur.y != 0u, pz = cur.z != 0u;
-                    const uint32_t wv = px ? cur.x : (py ? cur.y : (pz ? cur.z : cur.w));
-                    const uint32_t j = px ? 0u : (py ? 32u : (pz ? 64u : 96u));
-                    const uint32_t nw = wv & (wv - 1u);
-                    const bool sy = !px && py, sz = !px && !py && pz, sw = !px && !py && !pz;
-                    cur.x = px ? nw : cur.x;
-                    cur.y = sy ? nw : cur.y;
-                    cur.z = sz ? nw : cur.z;
-                    cur.w = sw ? nw : cur.w;
-                    row = (uint32_t)c * 128u + j + (uint32_t)(__ffs((int)wv) - 1);
-                    have = true;
-                    fetch(row, dat);
-                }
-            }
-            if (pv) {
-                uint32_t d, m;
-                probe(prow, pdat, d, m);
-                fn(prow, d, m);
-            }
-            pv = have; prow = row; pdat = dat;
-        }
-    };
-    auto col = [&](uint32_t d) -> uint32_t { return (WINDOW ? (d & 31u) : d) * (uint32_t)NTB; };
-
-    // ---- phase A: private histograms, candidate lists, distance span --------------------------
-    uint32_t dmin = 0xffffffffu, dmax = 0, cnt = 0;
-    if (T >= 0) {
-        walk_bitmap([&](uint32_t row, uint32_t d, uint32_t m) {
-            const uint32_t c = col(d);
-            if (WINDOW) {
-                cN[c] += 1u + (m << 16);
-            } else {
-                cN[c] += 1u;
-                cM[c] += m;
-            }
-            if (WINDOW && cnt < capL) mylist[cnt] = (m << 31) | (d << kIdxBits) | (row - row_base);  // the wide variant re-walks
-            cnt += 1u;
-            dmin = min(dmin, d); dmax = max(dmax, d);
-        });
-    }
-    if (cnt) {
-        atomicAdd(&qs[lane], cnt);
-        atomicMin(&qs[32 + lane], dmin);
-        atomicMax(&qs[64 + lane], dmax);
-        if (!WINDOW || cnt > capL) atomicOr(&qs[96 + lane], 1u);
-    }
-    __syncthreads();
-    if (g == 0 && active) {
-        const uint32_t total = qs[lane];
-        uint32_t flags = qs[96 + lane];
-        if (T < 0 || (int64_t)total < p.R) {
-            if (p.fail_list != nullptr && !p.no_fallback) {
-                const int i = atomicAdd(p.n_fail, 1);
-                p.fail_list[i] = (int)q;
-            } else {
-                p.ap[q] = -1.0;  // diagnostics only
-                if (p.n_fail) atomicAdd(p.n_fail, 1);
-            }
-            flags |= 2u;
-        } else if (WINDOW && (qs[64 + lane] - qs[32 + lane] >= 32u || total >= 65536u)) {
-            const int i = atomicAdd(p.n_wide, 1);
-            p.wide_list[i] = (int)q;
-            flags |= 2u;
-        } else if (WINDOW && (flags & 1u) && p.n_rewalk) {
-            atomicAdd(p.n_rewalk, 1);
-        }
-        qs[96 + lane] = flags;
-    }
-    __syncthreads();
-    const uint32_t qflags = qs[96 + lane];
-    const bool live = active && !(qflags & 2u);
-    const bool rewalk = (qflags & 1u) != 0;
-    const uint32_t qdmin = (WINDOW && live) ? qs[32 + lane] : 0u;
-
-    // ---- phase A2: rank bases.  Warp g scans the distances i = g, g + G, ... of its 32 queries over the G warps (exclusive,
-    //      in place) and leaves the totals in colbase; warp 0 then turns the totals into running bases in distance order ----
-    for (int i = g; i < ncol; i += G) {
-        const uint32_t c = col(WINDOW ? qdmin + (uint32_t)i : (uint32_t)i);
-        uint32_t runN = 0, runM = 0;
-        for (int gg = 0; gg < G; ++gg) {
-            uint32_t* pn = smem + c + gg * 32 + lane;
-            const uint32_t v = *pn;
-            *pn = runN;
-            runN += v;
-            if (!WINDOW) {
-                uint32_t* pm = pn + (size_t)ncol * NTB;
-                const uint32_t vm = *pm;
-                *pm = runM;
-                runM += vm;
-            }
-        }
-        colbase[i * 32 + lane] = runN;
-        if (!WINDOW) colbase[(ncol + i) * 32 + lane] = runM;
-    }
-    __syncthreads();
-    if (g == 0) {
-        uint32_t cn = 0, cm = 0;
-        for (int i = 0; i < ncol; ++i) {
-            const uint32_t v = colbase[i * 32 + lane];
-            colbase[i * 32 + lane] = cn;
-            cn += v;  // WINDOW: both halves at once (live queries: both below 65536)
-            if (!WINDOW) {
-                const uint32_t vm = colbase[(ncol + i) * 32 + lane];
-                colbase[(ncol + i) * 32 + lane] = cm;
-                cm += vm;
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = 0; i < ncol; ++i) {
-        const uint32_t c = col(WINDOW ? qdmin + (uint32_t)i : (uint32_t)i);
-        cN[c] += colbase[i * 32 + lane];
-        if (!WINDOW) cM[c] += colbase[(ncol + i) * 32 + lane];
-    }
-
-    // ---- phase B: ranks, relevant prefix counts, AP -----------------------------------------------
-    double acc = 0.0, acc_lo = 0.0;
-    int relc = 0;
-    const uint32_t R32 = (uint32_t)p.R;
-    auto rank_one = [&](uint32_t d, uint32_t m, uint32_t row) {
-        const uint32_t c = col(d);
-        uint32_t rank, cum;
-        if (WINDOW) {
-            const uint32_t v = cN[c] + 1u + (m << 16);
-            cN[c] = v;
-            rank = v & 0xFFFFu; cum = v >> 16;
-        } else {
-            rank = cN[c] + 1u; cum = cM[c] + m;
-            cN[c] = rank; cM[c] = cum;
-        }
-        if (rank <= R32) {
-            if (p.ids) p.ids[q * p.R + (rank - 1u)] = row;
-            if (p.dist) p.dist[q * p.R + (rank - 1u)] = (uint16_t)d;
-            if (m) {
-                dd_add(acc, acc_lo, ap_term(cum, rank));
-                relc += 1;
-            }
-        }
-    };
-    if (live && !rewalk) {
-        // 32 bytes of entries in flight per thread while the previous 32 are consumed
-        auto one = [&](uint32_t ent) { rank_one((ent >> kIdxBits) & kDistMask, ent >> 31, row_base + (ent & kIdxMask)); };
-        const uint4* vp = reinterpret_cast<const uint4*>(mylist);  // capL is a multiple of 8: 32-byte aligned
-        uint32_t e = 0;
-        if (cnt >= 8u) {
-            uint4 a0 = __ldcs(vp), a1 = __ldcs(vp + 1);
-            for (; e + 8u <= cnt; e += 8u) {
-                uint4 n0 = a0, n1 = a1;
-                if (e + 16u <= cnt) { n0 = __ldcs(vp + (e >> 2) + 2); n1 = __ldcs(vp + (e >> 2) + 3); }
-                one(a0.x); one(a0.y); one(a0.z); one(a0.w);
-                one(a1.x); one(a1.y); one(a1.z); one(a1.w);
-                a0 = n0; a1 = n1;
-            }
-        }
-        for (; e < cnt; ++e) one(__ldcs(mylist + e));
-    } else if (live) {
-        walk_bitmap([&](uint32_t row, uint32_t d, uint32_t m) { rank_one(d, m, row); });
-    }
-    // fixed-order reduction over the G warps of the query (deterministic)
-    red[(g * 32 + lane) * 2] = acc;
-    red[(g * 32 + lane) * 2 + 1] = acc_lo;
-    int* redc = reinterpret_cast<int*>(red + (size_t)G * 64);
-    redc[g * 32 + lane] = relc;
-    __syncthreads();
-    if (g == 0 && live) {
-        double a = 0.0, alo = 0.0;
-        int rc = 0;
-        for (int gg = 0; gg < G; ++gg) {
-            dd_add(a, alo, red[(gg * 32 + lane) * 2]);
-            alo = __dadd_rn(alo, red[(gg * 32 + lane) * 2 + 1]);
-            rc += redc[gg * 32 + lane];
-        }
-        a = __dadd_rn(a, alo);
-        p.ap[q] = rc ? a / (double)rc : __longlong_as_double(0x7ff8000000000000LL);
-        if (p.rel) p.rel[q] = rc;
-    }
-}
-
-// ================================================================================================
 // 4b. Dense top-R (R a large part of the database; cifar_evaluation.yaml ranks the WHOLE database: MAP_R == DB_SIZE).
 //     Every row is a candidate, so nothing is selected and nothing is written: the AP walk of ap_kernel runs directly over
 //     the packed rows, the Hamming distance and the relevance bit of a row are recomputed in both passes (one XOR + POPC per
@@ -1550,34 +1190,6 @@ static int launch_ap(ApParams ap, int64_t n_slots_max, cudaStream_t st)
     return HG_OK;
 }
 
-template <bool WINDOW>
-static int launch_ap_bm(ApBmParams ap, int64_t n_slots_max, cudaStream_t st)
-{
-    const int ncol = WINDOW ? 32 : ap.b + 1;
-    const int G = ap_bm_warps(ap.b, WINDOW);  // the wide variant (no lists) may run fewer warps per CTA
-    ap.G = G;
-    const size_t smem = ap_bm_smem(G, ncol, WINDOW);
-    const int threads = 32 * G;
-    const int mode = (ap.W == 2 && ap.Wr == 4) ? 1 : ((ap.W == 4 && ap.Wr == 8) ? 2 : 0);
-    const unsigned blocks = (unsigned)ceil_div(n_slots_max, 32);
-#define HG_LAUNCH_AP_BM(M)                                                                                                              \
-    do {                                                                                                                                \
-        static thread_local size_t configured = 0;                                                                                      \
-        if (smem > 48 * 1024 && smem > configured) {                                                                                    \
-            HG_CUDA_TRY(cudaFuncSetAttribute(ap_bm_kernel<M, WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-            configured = smem;                                                                                                          \
-        }                                                                                                                               \
-        ap_bm_kernel<M, WINDOW><<<blocks, threads, smem, st>>>(ap);                                                                      \
-    } while (0)
-    if (mode == 1) HG_LAUNCH_AP_BM(1);
-    else if (mode == 2) HG_LAUNCH_AP_BM(2);
-    else HG_LAUNCH_AP_BM(0);
-#undef HG_LAUNCH_AP_BM
-    count_launch();
-    HG_CUDA_TRY(cudaGetLastError());
-    return HG_OK;
-}
-
 template <int W>
 static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_rows, unsigned flags, double* d_ap, uint32_t* d_ids, uint16_t* d_dist, int32_t* d_rel, char* ws, cudaStream_t st,
                    const MapChunks* chunks = nullptr, PrepareRowsFn prepare = nullptr, void* user = nullptr)
@@ -1705,7 +1317,7 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
             ua.q_rows = q_rows; ua.db_rows = db_rows; ua.nq = pl.nq; ua.ndb = pl.ndb; ua.b = pl.b; ua.W = pl.W; ua.LW = pl.LW; ua.Wr = pl.Wr;
             ua.KP = pl.umma_kp; ua.thr = thr; ua.P = pl.P; ua.SL = pl.SL; ua.lists = lists; ua.cap = pl.cap; ua.bin_cnt = bin_cnt; ua.bin_cnt0 = bin_cnt0;
             ua.q8 = q8; ua.db8 = db8;
-            ua.bitmap = pl.bitmap ? reinterpret_cast<uint32_t*>(ws + pl.off_bitmap) : nullptr; ua.bm_stride = pl.bm_stride;
+            ua.queued = pl.queued ? 1 : 0;
             ua.qx = reinterpret_cast<uint8_t*>(ws + pl.off_qx); ua.bx = reinterpret_cast<uint8_t*>(ws + pl.off_bx);
             if ((rc = umma_expand_q(q_rows, pl.nq, pl.b, pl.Wr, pl.umma_kp, q8, st)) != HG_OK) return rc;
             if ((rc = umma_thr_columns(thr, pl.nq, pl.b, const_cast<uint8_t*>(ua.qx), const_cast<uint8_t*>(ua.bx), st)) != HG_OK) return rc;
@@ -1729,27 +1341,14 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
                 if ((rc = launch_select_w<W, false>(sp, pl, n_splits, st)) != HG_OK) return rc;
             }
         }
-    } else if (!pl.bitmap) {
+    } else {
         HG_CUDA_TRY(cudaMemsetAsync(bin_cnt, 0, sizeof(uint32_t) * (size_t)pl.nq * pl.P, st));
         HG_CUDA_TRY(cudaMemsetAsync(bin_cnt0, 0, sizeof(uint32_t) * (size_t)pl.nq * pl.P, st));
     }
     if (!select_marked) timer.mark(kPhaseSelect, st);
     // 4. AP (queries that cannot be answered exactly from their candidates go to the fail list)
     timer.mark(kPhaseAp, st);
-    if (pl.bitmap) {
-        ApBmParams ap{};
-        ap.q_rows = q_rows; ap.db_rows = db_rows; ap.nq = pl.nq; ap.ndb = pl.ndb; ap.R = pl.R; ap.b = pl.b; ap.W = pl.W; ap.LW = pl.LW; ap.Wr = pl.Wr;
-        ap.bitmap = reinterpret_cast<const uint4*>(ws + pl.off_bitmap); ap.bm_stride = pl.bm_stride;
-        ap.lists = lists; ap.capL = pl.capL; ap.n_rewalk = ctrl + 3;
-        ap.n_active = nullptr; ap.qlist = nullptr; ap.thr = thr;
-        ap.ap = d_ap; ap.ids = d_ids; ap.dist = d_dist; ap.rel = d_rel;
-        ap.fail_list = fail_list; ap.n_fail = n_fail; ap.no_fallback = no_fallback ? 1 : 0;
-        ap.wide_list = wide_list; ap.n_wide = ctrl + 2;
-        if ((rc = launch_ap_bm<true>(ap, pl.nq, st)) != HG_OK) return rc;
-        // queries whose candidate distances span >= 32 values or with >= 65536 candidates: full-width counters
-        ap.n_active = ctrl + 2; ap.qlist = wide_list; ap.wide_list = nullptr; ap.n_wide = nullptr;
-        if ((rc = launch_ap_bm<false>(ap, pl.nq, st)) != HG_OK) return rc;
-    } else {
+    {
         ApParams ap{};
         ap.nq = pl.nq; ap.n_active = nullptr; ap.qlist = nullptr; ap.bins_by_slot = 0; ap.P = pl.P; ap.b = pl.b; ap.SL = pl.SL; ap.R = pl.R;
         ap.lists = lists; ap.cap = pl.cap; ap.bin_off2 = nullptr; ap.bin_cap2 = nullptr; ap.bin_cnt = bin_cnt; ap.bin_cnt0 = bin_cnt0; ap.thr = thr;

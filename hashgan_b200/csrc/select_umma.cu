@@ -87,6 +87,21 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// one probe on a precomputed shared-space address
+__device__ __forceinline__ bool mbar_try_a(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity)
 {
     asm volatile(
@@ -452,23 +467,29 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
     }
 }
 
-// ---- bitmap mode ---------------------------------------------------------------------------------------------------
-// Same contraction, but the epilogue only WRITES THE HIT MASKS: bit r of query q's bitmap row says d_H(q, row r) <= T_q.
-// Walking the ~R/Ndb hits inside the epilogue (select_umma_kernel) costs 45 instructions per divergent step at 23 % lane
-// occupancy -- two thirds of that kernel's instructions; here a warp-tile is wait + 2 x (tcgen05.ld, 8 PRMT, 8 multiply-add)
-// + one 8-byte store, and ap_bm_kernel (rank.cu) walks the bitmap with every lane busy.  Nothing but the int8 operands is
-// staged in shared memory, so the MMA warp itself frees a ring stage (tcgen05.commit) and the ring is deeper.
-template <int KP> struct BmCfg {
-    static constexpr int S = (KP == 32 ? 8 : (KP == 64 ? 6 : 4));
+// ---- queued mode: the list-appending epilogue without its 23 % lane occupancy -----------------------------------------------
+// select_umma_kernel walks the hits of a tile before it touches the next one, so every warp-tile costs max-over-lanes hit
+// steps (2.5 at C4 for 0.57 hits per lane).  Here a lane only PARKS its non-zero mask words in a private shared-memory FIFO
+// (word + tile tag) and the warp drains the FIFOs one hit per lane and step (a) while it waits for the next accumulator and
+// (b) whenever a FIFO is about to fill, and only when enough lanes have work: the lanes no longer wait for each other at tile
+// boundaries, the steps run mostly full, and the waiting time of the accumulator hand-off is filled with useful work.  Hits may
+// be consumed many tiles late, so their packed rows come from global memory (L2-resident) instead of the staged tile; the ring
+// therefore holds only the int8 operands and is released by the MMA warp itself (tcgen05.commit).  Bins, entry format, order
+// (one writer per bin, ascending rows) and the AP kernel are those of select_umma_kernel.
+template <int KP> struct QCfg {
+    static constexpr int S = (KP == 32 ? 8 : (KP == 64 ? 4 : 3));  // ring depth
+    static constexpr int D = (KP == 128 ? 4 : 8);                  // FIFO entries per lane (power of two)
 };
 
-template <int KP>
+template <int KP, int MODE>
 __global__ void __launch_bounds__(kUmmaThreads, UmmaCfg<KP>::CTAS)
-select_bm_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_constant__ CUtensorMap tmap_db8, const __grid_constant__ CUtensorMap tmap_qx,
-                 const __grid_constant__ CUtensorMap tmap_bx, UmmaSelectArgs a)
+select_q_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_constant__ CUtensorMap tmap_db8, const __grid_constant__ CUtensorMap tmap_qx,
+                const __grid_constant__ CUtensorMap tmap_bx, UmmaSelectArgs a)
 {
-    constexpr int S = BmCfg<KP>::S;
-    constexpr int KB = UmmaCfg<KP>::KB, KW = UmmaCfg<KP>::KW;
+    constexpr int S = QCfg<KP>::S, D = QCfg<KP>::D;
+    constexpr int NBUF = 1;          // accumulators per query half
+    constexpr uint32_t ACC = 128u;   // tensor-memory columns of one 128 x 128 accumulator
+    constexpr int KB = UmmaCfg<KP>::KB, KW = UmmaCfg<KP>::KW, QW = UmmaCfg<KP>::QW;
     constexpr uint32_t A_BYTES = 2 * 128 * KP;
     constexpr uint32_t AX_BYTES = 2 * 128 * kUmmaXBytes;
     constexpr uint32_t BX_BYTES = 128 * kUmmaXBytes;
@@ -476,13 +497,14 @@ select_bm_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_const
     constexpr uint32_t STAGE_BYTES = 128 * KP;
     extern __shared__ __align__(1024) uint8_t usm[];
     const uint32_t base = (smem_u32(usm) + 1023u) & ~1023u;
-    __shared__ __align__(8) uint64_t bars[2 * S + 5];
+    uint8_t* const base_ptr = usm + (base - smem_u32(usm));
+    __shared__ __align__(8) uint64_t bars[2 * S + 1 + 4 * NBUF];
     __shared__ uint32_t tmem_base_slot;
     uint64_t& a_full = bars[0];
     uint64_t* const full_bar = bars + 1;
     uint64_t* const empty_bar = bars + 1 + S;
-    uint64_t* const tmem_full = bars + 2 * S + 1;
-    uint64_t* const tmem_empty = bars + 2 * S + 3;
+    uint64_t* const tmem_full = bars + 2 * S + 1;              // [2 halves][NBUF]
+    uint64_t* const tmem_empty = bars + 2 * S + 1 + 2 * NBUF;  // [2 halves][NBUF]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t q0 = (int64_t)blockIdx.x * 256;
@@ -494,7 +516,7 @@ select_bm_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_const
     if (threadIdx.x == 0) {
         mbar_init(&a_full, 1);
         for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int h = 0; h < 2; ++h) { mbar_init(&tmem_full[h], 1); mbar_init(&tmem_empty[h], kUmmaEpiWarps / 2); }
+        for (int h = 0; h < 2 * NBUF; ++h) { mbar_init(&tmem_full[h], 1); mbar_init(&tmem_empty[h], kUmmaEpiWarps / 2); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -537,8 +559,11 @@ select_bm_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_const
             constexpr uint32_t idesc = umma_idesc_i8(128, 128);
             mbar_wait(&a_full, 0);
             const uint64_t bxdesc = umma_desc_kmajor(base + A_BYTES + AX_BYTES, kUmmaXBytes);
+            auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) { umma_i8(d, ad, bd, idesc, acc); };
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t % S;
+                const int pb = 0;                 // accumulator buffer of this tile (NBUF = 1)
+                const uint32_t use = (uint32_t)t;  // how often that buffer was filled before
                 mbar_wait(&full_bar[s], (uint32_t)((t / S) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t b_addr = base + FIXED_BYTES + s * STAGE_BYTES;
@@ -547,28 +572,29 @@ select_bm_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_const
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         if (!(todo & (1u << h))) continue;
-                        if (todo == (1u << h)) mbar_wait(&tmem_empty[h], (uint32_t)((t & 1) ^ 1));
-                        else if (!mbar_try(&tmem_empty[h], (uint32_t)((t & 1) ^ 1))) continue;
+                        uint64_t* const te = &tmem_empty[h * NBUF + pb];
+                        if (todo == (1u << h)) mbar_wait(te, (use & 1u) ^ 1u);
+                        else if (!mbar_try(te, (use & 1u) ^ 1u)) continue;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t dcol = tmem_base + (uint32_t)(h * NBUF + pb) * ACC;
 #pragma unroll
                         for (int kb = 0; kb < KB; ++kb) {
                             const uint64_t adesc = umma_desc_kmajor(base + (uint32_t)((h * KB + kb) * 128 * KW), KW);
                             const uint64_t bdesc = umma_desc_kmajor(b_addr + (uint32_t)(kb * 128 * KW), KW);
 #pragma unroll
                             for (int k = 0; k < KW / 32; ++k)
-                                umma_i8(tmem_base + (uint32_t)(h * 128), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                                mma(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (uint32_t)((kb | k) != 0));
                         }
-                        umma_i8(tmem_base + (uint32_t)(h * 128), umma_desc_kmajor(base + A_BYTES + h * 128 * kUmmaXBytes, kUmmaXBytes), bxdesc, idesc, 1u);
-                        umma_commit(&tmem_full[h]);
+                        mma(dcol, umma_desc_kmajor(base + A_BYTES + h * 128 * kUmmaXBytes, kUmmaXBytes), bxdesc, 1u);
+                        umma_commit(&tmem_full[h * NBUF + pb]);
                         todo &= ~(1u << h);
                     }
                 }
-                umma_commit(&empty_bar[s]);  // both halves have read the stage once their MMAs retire: the producer may refill it
+                umma_commit(&empty_bar[s]);  // the operands of this stage are free once both MMAs retire
             }
         }
     } else {
-        // ---- epilogue: thread <-> (query, split).  The bitmap is CHUNK-major: chunk c = rows [128 c, 128 c + 128) of all queries,
-        // one uint4 per query, so the four mask words of a tile pair leave the warp as one coalesced 512-byte store ----
+        // ---- epilogue: thread <-> (query, split) = one bin -------------------------------------------------------
         const int e = warp - 2;
         const int quarter = warp & 3;
         const int h = (e >> 2) & 1;
@@ -578,41 +604,120 @@ select_bm_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_const
         const int64_t row0 = (int64_t)split * a.SL;
         const int64_t nrows = max((int64_t)0, min(a.SL, a.ndb - row0));
         const bool valid = slot < a.nq && split < a.P;
+        const int W = MODE == 1 ? 2 : (MODE == 2 ? 4 : a.W), LW = a.LW, Wr = MODE == 1 ? 4 : (MODE == 2 ? 8 : a.Wr);
         const uint32_t sel = a.prmt_sel;
+        uint32_t qw[QW], ql[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int w = 0; w < QW; ++w) qw[w] = 0;
+        uint32_t pos = 0, nback = 0, start = 0, end = 0;  // front stack (d < T) grows up from start, back stack (d == T) down from end
         int Tq = -1;
-        if (valid) Tq = a.thr[slot];
+        int64_t bin = -1;
+        if (valid) {
+#pragma unroll
+            for (int w = 0; w < QW; ++w)
+                if (w < W) qw[w] = a.q_rows[slot * Wr + w];
+            for (int w = 0; w < LW && w < 4; ++w) ql[w] = a.q_rows[slot * Wr + W + w];
+            Tq = a.thr[slot];
+            bin = slot * a.P + split;
+            start = (uint32_t)(bin * (int64_t)a.cap);
+            end = start + a.cap;
+            pos = start;
+        }
         const uint32_t live = (valid && Tq >= 0) ? 0xFFFFFFFFu : 0u;
-        uint4* out = reinterpret_cast<uint4*>(a.bitmap) + (valid ? (row0 >> 7) * a.bm_stride + slot : 0);
-        const int64_t ostride = a.bm_stride;  // uint4 per chunk (queries, padded to 32)
-        const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * 128 + ch * 64);
+        uint32_t* const lists = a.lists;
+        const uint32_t* const split_rows = a.db_rows + (valid ? row0 : 0) * Wr;  // packed rows of my split (global, L2-resident)
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ch * (ACC / 2u);
         uint32_t bar0 = smem_u32(&bars[0]);
         asm volatile("" : "+r"(bar0));
-        const uint32_t tfull_a = bar0 + 8u * (2 * S + 1 + h), tempty_a = bar0 + 8u * (2 * S + 3 + h);
+        const uint32_t tfull_0 = bar0 + 8u * (2 * S + 1 + h * NBUF), tempty_0 = bar0 + 8u * (2 * S + 1 + 2 * NBUF + h * NBUF);
         const int nrows32 = (int)nrows;
         const int nfull = nrows32 / kUmmaHalfRows;
-        uint32_t tph = 0;
-        auto tile_masks = [&](int t, uint32_t& h0, uint32_t& h1) {
-            mbar_wait_a(tfull_a, tph);
+        // private FIFO of parked mask words: entry i of my lane at fifo[i * 32] = (word, 2 * tile + word index)
+        uint2* const fifo = reinterpret_cast<uint2*>(base_ptr + FIXED_BYTES + S * STAGE_BYTES) + (size_t)e * (D * 32) + lane;
+        uint32_t rd = 0, wr = 0, cur = 0, curtag = 0;
+        const uint32_t FULLM = 0xFFFFFFFFu;
+        const int min_lanes = a.drain_lanes;
+
+        // A hit is consumed in two halves so that the L2 latency of its packed row is never waited for:
+        //   take():    the lowest row of the word being consumed (rows ascend within a word, words ascend in the FIFO) -> request the row
+        //   consume(): distance, relevance, append -- one call later, when the row has long arrived
+        bool pv = false;       // a requested row is pending
+        uint32_t prl = 0;      // its row inside the split
+        uint4 pa = make_uint4(0, 0, 0, 0), pb = make_uint4(0, 0, 0, 0);  // its packed words (MODE 1: pa, MODE 2: pa + pb)
+        auto take = [&]() {
+            if (cur == 0u && rd != wr) {
+                const uint2 en = fifo[(rd & (uint32_t)(D - 1)) * 32];
+                cur = en.x; curtag = en.y;
+                ++rd;
+            }
+            if (cur != 0u) {
+                prl = curtag * 32u + (uint32_t)(__ffs((int)cur) - 1);
+                cur &= cur - 1u;
+                pv = true;
+                const uint32_t* prow = split_rows + (size_t)prl * Wr;
+                if (MODE == 1) pa = __ldg(reinterpret_cast<const uint4*>(prow));
+                if (MODE == 2) { pa = __ldg(reinterpret_cast<const uint4*>(prow)); pb = __ldg(reinterpret_cast<const uint4*>(prow + 4)); }
+            }
+        };
+        auto consume = [&]() {
+            if (pv) {
+                int d = 0;
+                uint32_t m = 0;
+                if (MODE == 1) {
+                    d = __popc(qw[0] ^ pa.x) + __popc(qw[1] ^ pa.y);
+                    m = (ql[0] & pa.z) | (ql[1] & pa.w);
+                } else if (MODE == 2) {
+                    d = __popc(qw[0] ^ pa.x) + __popc(qw[1] ^ pa.y) + __popc(qw[2] ^ pa.z) + __popc(qw[3] ^ pa.w);
+                    m = (ql[0] & pb.x) | (ql[1] & pb.y) | (ql[2] & pb.z) | (ql[3] & pb.w);
+                } else {
+                    const uint32_t* prow = split_rows + (size_t)prl * Wr;
+#pragma unroll
+                    for (int w = 0; w < QW; ++w)
+                        if (w < W) d += __popc(qw[w] ^ __ldg(prow + w));
+#pragma unroll
+                    for (int w = 0; w < 4; ++w)
+                        if (w < LW) m |= ql[w] & __ldg(prow + W + w);
+                }
+                const bool eq = d == Tq;
+                if (pos + nback < end) lists[eq ? end - 1u - nback : pos] = ((uint32_t)d * (1u << kIdxBits) + prl) | (m ? 0x80000000u : 0u);
+                if (eq) nback += 1; else pos += 1;
+                pv = false;
+            }
+        };
+
+        for (int t = 0; t < ntiles; ++t) {
+            const uint32_t pb = 0u;
+            const uint32_t tph = (uint32_t)t & 1u;
+            const uint32_t tfull_a = tfull_0 + 8u * pb, tempty_a = tempty_0 + 8u * pb;
+            const uint32_t tmem_row = tmem_lane + (uint32_t)(h * NBUF + (int)pb) * ACC;
+            // request the next parked hit of every lane, then wait for the accumulator of tile t; a long wait with a large backlog
+            // (>= min_lanes lanes with work) is spent on further hits
+            if (!__any_sync(FULLM, pv)) take();
+            while (!__all_sync(FULLM, mbar_try_a(tfull_a, tph))) {
+                const uint32_t pend = __ballot_sync(FULLM, (cur != 0u) | (rd != wr));
+                if (__popc(pend) >= min_lanes) { consume(); take(); }
+            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t m0 = hit_mask32(tmem_row, sel);
             const uint32_t m1 = hit_mask32(tmem_row + 32u, sel);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive_a(tempty_a);
-            h0 = m0 & live; h1 = m1 & live;
+            uint32_t h0 = m0 & live, h1 = m1 & live;
             if (t >= nfull) {
                 const int left = nrows32 - t * kUmmaHalfRows;
                 h0 &= left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
                 h1 &= left <= 32 ? 0u : ((1u << (left - 32)) - 1u);
             }
-            tph ^= 1u;
-        };
-        for (int t = 0; t < ntiles; t += 2) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            tile_masks(t, v.x, v.y);
-            if (t + 1 < ntiles) tile_masks(t + 1, v.z, v.w);
-            if (valid && !(a.dbg & 1)) out[(int64_t)(t >> 1) * ostride] = v;
+            consume();  // the row requested before the wait
+            // room for two more words in every FIFO
+            while (__any_sync(FULLM, wr - rd > (uint32_t)(D - 2))) { take(); consume(); }
+            if (h0) { fifo[(wr & (uint32_t)(D - 1)) * 32] = make_uint2(h0, 2u * (uint32_t)t); ++wr; }
+            if (h1) { fifo[(wr & (uint32_t)(D - 1)) * 32] = make_uint2(h1, 2u * (uint32_t)t + 1u); ++wr; }
         }
+        consume();
+        while (__any_sync(FULLM, (cur != 0u) | (rd != wr))) { take(); consume(); }
+        if (bin >= 0) { a.bin_cnt[bin] = pos - start; a.bin_cnt0[bin] = nback; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -721,17 +826,17 @@ static int launch_umma(const CUtensorMap& tq, const CUtensorMap& tdb, const CUte
     return HG_OK;
 }
 
-template <int KP>
-static int launch_bm(const CUtensorMap& tq, const CUtensorMap& tdb, const CUtensorMap& tqx, const CUtensorMap& tbx, const UmmaSelectArgs& a, cudaStream_t st)
+template <int KP, int MODE>
+static int launch_q(const CUtensorMap& tq, const CUtensorMap& tdb, const CUtensorMap& tqx, const CUtensorMap& tbx, const UmmaSelectArgs& a, cudaStream_t st)
 {
-    const size_t smem = (size_t)2 * 128 * KP + (size_t)3 * 128 * kUmmaXBytes + (size_t)BmCfg<KP>::S * (128 * KP) + 1024;
+    const size_t smem = (size_t)2 * 128 * KP + (size_t)3 * 128 * kUmmaXBytes + (size_t)QCfg<KP>::S * (128 * KP) + (size_t)kUmmaEpiWarps * QCfg<KP>::D * 32 * sizeof(uint2) + 1024;
     static thread_local bool configured = false;
     if (!configured) {
-        HG_CUDA_TRY(cudaFuncSetAttribute(select_bm_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HG_CUDA_TRY(cudaFuncSetAttribute(select_q_kernel<KP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     dim3 grid((unsigned)ceil_div(a.nq, 256), (unsigned)ceil_div(a.n_splits, 2));
-    select_bm_kernel<KP><<<grid, kUmmaThreads, smem, st>>>(tq, tdb, tqx, tbx, a);
+    select_q_kernel<KP, MODE><<<grid, kUmmaThreads, smem, st>>>(tq, tdb, tqx, tbx, a);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     return HG_OK;
@@ -754,13 +859,10 @@ int umma_select_launch(const UmmaSelectArgs& a_in, cudaStream_t st)
     if ((rc = make_map_u8(&tdb, a.db8, round_up(a.ndb, 32), a.KP, kUmmaHalfRows, kw)) != HG_OK) return rc;
     if ((rc = make_map_u8(&tqx, a.qx, std::max<int64_t>(round_up(a.nq, 256), 128), kUmmaXBytes, 128)) != HG_OK) return rc;
     if ((rc = make_map_u8(&tbx, a.bx, 128, kUmmaXBytes, kUmmaHalfRows)) != HG_OK) return rc;
-    if (a.bitmap) {  // bitmap mode: hit masks only (ap_bm_kernel does the rest)
-        { const char* v = getenv("HG_BM_DEBUG"); a.dbg = (v && *v) ? atoi(v) : 0; }
-        if (a.SL & 127) return fail(HG_EINVAL, "select_umma: bitmap mode needs splits of whole 128-row chunks");
-        if (a.KP == 32) return launch_bm<32>(tq, tdb, tqx, tbx, a, st);
-        if (a.KP == 64) return launch_bm<64>(tq, tdb, tqx, tbx, a, st);
-        if (a.KP == 128) return launch_bm<128>(tq, tdb, tqx, tbx, a, st);
-        return launch_bm<256>(tq, tdb, tqx, tbx, a, st);
+    if (a.queued && a.KP == 64 && a.W == 2 && a.Wr == 4 && (a.SL & 63) == 0) {  // parked mask words, hits consumed asynchronously (select_q_kernel)
+        const char* v = getenv("HG_DRAIN_LANES");
+        a.drain_lanes = (v && *v) ? atoi(v) : 12;
+        return launch_q<64, 1>(tq, tdb, tqx, tbx, a, st);
     }
     if ((rc = make_map_rows(&trows, a.db_rows, a.ndb, a.Wr)) != HG_OK) return rc;
     if (a.KP == 32) return launch_umma<32, 0>(tq, tdb, trows, tqx, tbx, a, st);
@@ -864,3 +966,4 @@ extern "C" int hg_i8_peak(double* ops_per_s, double* ms_out, int iters, void* st
     if (!hg::device_facts().ok) return hg::fail(HG_ECUDA, "hg_i8_peak: no CUDA device");
     return hg::i8_peak(ops_per_s, ms_out, iters, (cudaStream_t)stream);
 }
+
