@@ -720,6 +720,8 @@ def main():
     hbm_peak = float(peaks["hbm_gbs"])
     W = lib.hg_code_words(wl.b)
     kp = int(lib.hg_select_backend_for(wl.nq, wl.ndb, wl.b, wl.L, wl.R))
+    queued = kp > 1 and int(lib.hg_select_queued_for(wl.nq, wl.ndb, wl.b, wl.L, wl.R)) == 1
+    umma_kernel = "select_q_kernel" if queued else "select_umma_kernel"
     sel_ms = phases_ms["ap"] if kp == 1 else phases_ms["select"]   # kp == 1: dense walk, the AP kernel does all pairs itself
     pairs = float(wl.nq) * float(wl.ndb)
     eff_bytes = pairs * 1.0  # 1 byte per (query, db row) pair = the uint8 distance matrix a non-fused design writes
@@ -728,7 +730,7 @@ def main():
     prof = os.path.join(ROOT, "profiles", "select_kernel_dram_bytes.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get(f"{wl.name}_{'umma' if kp > 1 else 'popc'}")
+            traffic = json.load(open(prof)).get(f"{wl.name}_{('queued' if queued else 'umma') if kp > 1 else 'popc'}")
         except Exception:
             traffic = None
     roofline = {
@@ -752,20 +754,20 @@ def main():
         _native.check(lib.hg_i8_peak(C.byref(i8_ops), C.byref(i8_ms), 0, None))
         i8_peak = i8_ops.value / 1e12
         roofline.update({
-            "kernel": f"select_umma_kernel<{kp}>",
+            "kernel": f"{umma_kernel}<{kp}>",
             "note": ("fused kernel: the distance matrix is never written, 'achieved' is the distance-matrix-equivalent rate (1 B/pair, "
                      "SURVEY 8(d)) -- the rate a kernel that materialises the uint8 distance matrix would need, so frac > 1 means "
                      "faster than any such kernel could be on this HBM; 'traffic' is what the kernel really moves. The contraction "
-                     "is an exact int8 tcgen05.mma; the binding resource is the CUDA-core epilogue (integer ALU pipe), see "
+                     "is an exact int8 tcgen05.mma; the binding resource is the instruction issue of the CUDA-core epilogue warps, see "
                      "'binding' and 'tensor'"),
             "tensor": {"achieved_tops_int8": tops, "peak_tops_int8": i8_peak, "frac": tops / i8_peak,
                        "peak_source": "hg_i8_peak microbenchmark in this process: back-to-back tcgen05.mma kind::i8 128x256x32 from resident shared-memory tiles on every SM"},
         })
         for name in ("r02_ncu_summary_C4.json", "r01_ncu_summary_C4.json"):
             try:  # binding-resource view from the committed ncu capture of this kernel
-                summ = json.load(open(os.path.join(ROOT, "profiles", name)))["select_umma_kernel"]
+                summ = json.load(open(os.path.join(ROOT, "profiles", name)))[umma_kernel]
                 roofline["binding"] = {
-                    "resource": "integer ALU pipe of the epilogue warps (64 lanes/clk/SM)",
+                    "resource": "instruction issue of the epilogue warps (mask building + hit handling on the CUDA cores)",
                     "alu_pipe_pct": summ["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]["value"],
                     "issue_slots_pct": summ["smsp__issue_active.avg.pct_of_peak_sustained_active"]["value"],
                     "tensor_pipe_pct": summ["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]["value"],
@@ -802,7 +804,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": _workload_text(wl, world > 1), "codes": codes,
-                   "queries_total": total_queries, "db_rows": wl.ndb, "bits": wl.b, "R": wl.R, "select_backend": ("dense walk, no selection (dense_ap_kernel)" if kp == 1 else ("tcgen05 int8 (select_umma_kernel)" if kp > 1 else "popc (select_kernel)")),
+                   "queries_total": total_queries, "db_rows": wl.ndb, "bits": wl.b, "R": wl.R, "select_backend": ("dense walk, no selection (dense_ap_kernel)" if kp == 1 else (f"tcgen05 int8 ({umma_kernel})" if kp > 1 else "popc (select_kernel)")),
                    "l2": f"no flush: every step re-reads the float32 feature matrix ({wl.ndb * wl.b * 4 / world / 1e6:.0f} MB per GPU at this shape) " + ("which exceeds the 126 MB L2" if wl.ndb * wl.b * 4 / world > 126e6 else "and writes/re-reads the candidate bins (beyond L2 together)"),
                    "parallelism": f"query-sharded x{world}, db row-sharded for packing; exchange: {exchange}; per-query APs all-gathered" if world > 1 else "1 GPU"},
         "warmup_steps_run": n_warm, "mAP": map_val, "mAP_all_ranks": map_all, "parity": parity, "path_stats": stats, "strong": strong,

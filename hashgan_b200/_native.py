@@ -41,6 +41,7 @@ SIGNATURES = {
     "hg_hamming_map_phase_ms": (_int, [C.POINTER(C.c_float)]),
     "hg_select_backend": (_int, [_int, _int]),
     "hg_select_backend_for": (_int, [_i64, _i64, _int, _int, _i64]),
+    "hg_select_queued_for": (_int, [_i64, _i64, _int, _int, _i64]),
     "hg_ip_map_workspace_bytes": (_sz, [_i64, _i64, _int, _int, _i64]),
     "hg_ip_map": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _int, _int, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hg_relevant_totals": (_int, [_vp, _i64, _vp, _i64, _int, _int, _vp, _vp]),

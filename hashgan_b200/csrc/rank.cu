@@ -1514,6 +1514,13 @@ extern "C" int hg_select_backend_for(int64_t nq, int64_t ndb, int b, int L, int6
     return pl.dense ? 1 : pl.umma_kp;
 }
 
+extern "C" int hg_select_queued_for(int64_t nq, int64_t ndb, int b, int L, int64_t R)
+{
+    const hg::Plan pl = hg::make_plan(nq, ndb, b, L, R);
+    if (!pl.ok) return -1;
+    return (!pl.dense && pl.umma_kp && pl.queued) ? 1 : 0;
+}
+
 extern "C" int hg_hamming_map_stats(const void* d_workspace, size_t workspace_bytes, int64_t nq, int64_t ndb, int b, int L, int64_t R,
                                     int64_t out[8], void* stream)
 {

@@ -119,6 +119,12 @@ int hg_select_backend(int b, int L);
  * (HG_DENSE=0 / 1 forces the choice). */
 int hg_select_backend_for(int64_t nq, int64_t ndb, int b, int L, int64_t R);
 
+/* 1 when that tensor-core select is the QUEUED kernel (select_q_kernel: non-zero hit-mask words are parked in per-lane
+ * shared-memory FIFOs and consumed one hit per lane and tile, around the wait for the next accumulator), 0 when the hits
+ * are walked tile by tile (select_umma_kernel).  The plan queues while the top-R is sparse (about two hits per lane and
+ * 64-row tile or fewer) on two-word codes in four-word rows (C4); HG_SELECT_MODE=queue / lists forces the choice. */
+int hg_select_queued_for(int64_t nq, int64_t ndb, int b, int L, int64_t R);
+
 /* Real-valued ranking mode -- the reference's literal behaviour on un-binarised features:
  *   lib/metric.py:13  ips = np.dot(query.output, database.output.T)   fp32 inner products (FMA, increasing k)
  *   lib/metric.py:14  np.argsort(-ips, 1)[:, :R]                       exact top-R by (ip descending, database row ascending)

@@ -295,6 +295,36 @@ def test_tensor_core_select_short_and_long_codes(hb, c_oracle, b, L, ndb, nq, R,
     _check_against_c_oracle(hb, c_oracle, db, q, R)
 
 
+@pytest.mark.parametrize("b,L,ndb,nq,R,corr", [
+    (64, 10, 150000, 300, 600, None),     # sparse top-R: the shape the plan itself gives to the queued kernel
+    (64, 10, 99991, 257, 3000, 0.25),     # ragged database / query counts, class-correlated codes: heavy ties, dense hits
+    (48, 10, 40000, 513, 5000, None),     # 16 zero pad bits; R / ndb = 12.5 %: every FIFO runs full (forced drains)
+    (40, 64, 30011, 100, 200, None),      # two label words
+    (64, 10, 700, 40, 300, 0.3),          # one short split pair
+])
+def test_queued_select_equals_the_tile_walking_kernel(hb, c_oracle, b, L, ndb, nq, R, corr):
+    """select_q_kernel (mask words parked in per-lane FIFOs, hits consumed asynchronously, packed rows from global memory) is
+    what ranks C4; the plan only picks it for a sparse top-R, so force it (HG_SELECT_MODE=queue) on small, ragged and dense
+    shapes as well: ids, distances and APs must match the C oracle and the kernel that walks the hits tile by tile."""
+    import os
+    from hashgan_b200 import _native
+    from hashgan_b200.synthetic import Workload, make_workload
+
+    assert _native.lib().hg_select_backend_for(nq, ndb, b, L, R) == 64
+    wl = Workload("Q", nq, ndb, b, L, R, "onehot" if L <= 20 else "multi", 70 + b)
+    if corr is not None and L > 20:
+        corr = None
+    _, db, q = make_workload(wl, correlated=corr)
+    aps = {}
+    for mode in ("queue", "lists"):
+        os.environ["HG_SELECT_MODE"] = mode
+        try:
+            aps[mode], _ = _check_against_c_oracle(hb, c_oracle, db, q, R)
+        finally:
+            del os.environ["HG_SELECT_MODE"]
+    assert np.array_equal(aps["queue"], aps["lists"], equal_nan=True)
+
+
 def test_short_codes_dense_top_r_stays_on_popc(hb, c_oracle):
     from hashgan_b200 import _native
     from hashgan_b200.synthetic import make_workload
