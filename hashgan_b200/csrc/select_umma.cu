@@ -609,7 +609,7 @@ select_q_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_consta
         uint32_t qw[QW], ql[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int w = 0; w < QW; ++w) qw[w] = 0;
-        uint32_t pos = 0, nback = 0, start = 0, end = 0;  // front stack (d < T) grows up from start, back stack (d == T) down from end
+        uint32_t pos = 0, bpos = 0, start = 0, end = 0;  // front stack (d < T): next slot pos, grows up from start; back stack (d == T): next slot bpos, grows down from end - 1
         int Tq = -1;
         int64_t bin = -1;
         if (valid) {
@@ -622,8 +622,9 @@ select_q_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_consta
             start = (uint32_t)(bin * (int64_t)a.cap);
             end = start + a.cap;
             pos = start;
+            bpos = end - 1u;
         }
-        const uint32_t live = (valid && Tq >= 0) ? 0xFFFFFFFFu : 0u;
+        // (no lane mask: queries beyond nq and queries without a threshold carry never-hit threshold columns, rows beyond the split are masked below)
         uint32_t* const lists = a.lists;
         const uint32_t* const split_rows = a.db_rows + (valid ? row0 : 0) * Wr;  // packed rows of my split (global, L2-resident)
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ch * (ACC / 2u);
@@ -633,7 +634,9 @@ select_q_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_consta
         const int nrows32 = (int)nrows;
         const int nfull = nrows32 / kUmmaHalfRows;
         // private FIFO of parked mask words: entry i of my lane at fifo[i * 32] = (word, 2 * tile + word index)
-        uint2* const fifo = reinterpret_cast<uint2*>(base_ptr + FIXED_BYTES + S * STAGE_BYTES) + (size_t)e * (D * 32) + lane;
+        // (rd, wr count in bytes of one ring row: 32 lanes x 8 bytes)
+        uint8_t* const fifo = base_ptr + FIXED_BYTES + S * STAGE_BYTES + ((size_t)e * (D * 32) + lane) * sizeof(uint2);
+        constexpr uint32_t ROW = 32u * (uint32_t)sizeof(uint2), RING = (uint32_t)(D - 1) * ROW;
         uint32_t rd = 0, wr = 0, cur = 0, curtag = 0;
         const uint32_t FULLM = 0xFFFFFFFFu;
         const int min_lanes = a.drain_lanes;
@@ -646,9 +649,9 @@ select_q_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_consta
         uint4 pa = make_uint4(0, 0, 0, 0), pb = make_uint4(0, 0, 0, 0);  // its packed words (MODE 1: pa, MODE 2: pa + pb)
         auto take = [&]() {
             if (cur == 0u && rd != wr) {
-                const uint2 en = fifo[(rd & (uint32_t)(D - 1)) * 32];
+                const uint2 en = *reinterpret_cast<const uint2*>(fifo + (rd & RING));
                 cur = en.x; curtag = en.y;
-                ++rd;
+                rd += ROW;
             }
             if (cur != 0u) {
                 prl = curtag * 32u + (uint32_t)(__ffs((int)cur) - 1);
@@ -679,8 +682,9 @@ select_q_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_consta
                         if (w < LW) m |= ql[w] & __ldg(prow + W + w);
                 }
                 const bool eq = d == Tq;
-                if (pos + nback < end) lists[eq ? end - 1u - nback : pos] = ((uint32_t)d * (1u << kIdxBits) + prl) | (m ? 0x80000000u : 0u);
-                if (eq) nback += 1; else pos += 1;
+                const uint32_t idx = eq ? bpos : pos;
+                if ((int32_t)(bpos - pos) >= 0) lists[idx] = ((uint32_t)d * (1u << kIdxBits) + prl) | (m ? 0x80000000u : 0u);  // room left: pos <= bpos
+                if (eq) bpos -= 1; else pos += 1;
                 pv = false;
             }
         };
@@ -703,7 +707,7 @@ select_q_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_consta
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive_a(tempty_a);
-            uint32_t h0 = m0 & live, h1 = m1 & live;
+            uint32_t h0 = m0, h1 = m1;
             if (t >= nfull) {
                 const int left = nrows32 - t * kUmmaHalfRows;
                 h0 &= left >= 32 ? 0xFFFFFFFFu : (left <= 0 ? 0u : ((1u << left) - 1u));
@@ -711,13 +715,13 @@ select_q_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_consta
             }
             consume();  // the row requested before the wait
             // room for two more words in every FIFO
-            while (__any_sync(FULLM, wr - rd > (uint32_t)(D - 2))) { take(); consume(); }
-            if (h0) { fifo[(wr & (uint32_t)(D - 1)) * 32] = make_uint2(h0, 2u * (uint32_t)t); ++wr; }
-            if (h1) { fifo[(wr & (uint32_t)(D - 1)) * 32] = make_uint2(h1, 2u * (uint32_t)t + 1u); ++wr; }
+            while (__any_sync(FULLM, wr - rd > (uint32_t)(D - 2) * ROW)) { take(); consume(); }
+            if (h0) { *reinterpret_cast<uint2*>(fifo + (wr & RING)) = make_uint2(h0, 2u * (uint32_t)t); wr += ROW; }
+            if (h1) { *reinterpret_cast<uint2*>(fifo + (wr & RING)) = make_uint2(h1, 2u * (uint32_t)t + 1u); wr += ROW; }
         }
         consume();
         while (__any_sync(FULLM, (cur != 0u) | (rd != wr))) { take(); consume(); }
-        if (bin >= 0) { a.bin_cnt[bin] = pos - start; a.bin_cnt0[bin] = nback; }
+        if (bin >= 0) { a.bin_cnt[bin] = pos - start; a.bin_cnt0[bin] = end - 1u - bpos; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
