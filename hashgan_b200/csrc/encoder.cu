@@ -256,6 +256,79 @@ __global__ void __launch_bounds__(256) maxpool3s2_lrn_kernel(const float* __rest
     }
 }
 
+// The same, one WARP per pooled pixel (C == 256: a lane owns 8 consecutive channels as two float4): 18 independent 16-byte loads
+// per lane instead of nine 4-byte loads and a block barrier per pixel, the four channel neighbours of the LRN window come from the
+// adjacent lanes by shuffle.  Same arithmetic, same summation order as maxpool3s2_lrn_kernel (bit-identical output).
+__global__ void __launch_bounds__(256) maxpool3s2_lrn_c256_kernel(const float* __restrict__ in, int N, int H, int W, int Ho, int Wo, float* __restrict__ out)
+{
+    constexpr int C = 256;
+    const int lane = threadIdx.x & 31;
+    const int64_t pixels = (int64_t)N * Ho * Wo;
+    const int64_t px = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (px >= pixels) return;
+    const int ox = (int)(px % Wo);
+    const int oy = (int)((px / Wo) % Ho);
+    const int64_t n = px / ((int64_t)Wo * Ho);
+    const float4* p = reinterpret_cast<const float4*>(in + ((n * H + oy * 2) * W + ox * 2) * C) + 2 * lane;
+    float4 v[9][2];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const float4* q = p + ((int64_t)dy * W + dx) * (C / 4);
+            v[dy * 3 + dx][0] = __ldg(q);
+            v[dy * 3 + dx][1] = __ldg(q + 1);
+        }
+    float e[12];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[2 + j] = -3.402823466e38f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        e[2] = fmaxf(e[2], v[t][0].x); e[3] = fmaxf(e[3], v[t][0].y); e[4] = fmaxf(e[4], v[t][0].z); e[5] = fmaxf(e[5], v[t][0].w);
+        e[6] = fmaxf(e[6], v[t][1].x); e[7] = fmaxf(e[7], v[t][1].y); e[8] = fmaxf(e[8], v[t][1].z); e[9] = fmaxf(e[9], v[t][1].w);
+    }
+    const unsigned FULL = 0xffffffffu;
+    const float u6 = __shfl_up_sync(FULL, e[8], 1), u7 = __shfl_up_sync(FULL, e[9], 1);
+    const float d0 = __shfl_down_sync(FULL, e[2], 1), d1 = __shfl_down_sync(FULL, e[3], 1);
+    e[0] = lane == 0 ? 0.0f : u6; e[1] = lane == 0 ? 0.0f : u7;      // channels -2, -1 do not exist
+    e[10] = lane == 31 ? 0.0f : d0; e[11] = lane == 31 ? 0.0f : d1;  // channels C, C + 1
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float s = 0.0f;
+#pragma unroll
+        for (int d = 0; d <= 4; ++d) s = fmaf(e[j + d], e[j + d], s);
+        r[j] = e[2 + j] * powf(1.0f + 2e-5f * s, -0.75f);
+    }
+    float4* o = reinterpret_cast<float4*>(out + px * C) + 2 * lane;
+    o[0] = make_float4(r[0], r[1], r[2], r[3]);
+    o[1] = make_float4(r[4], r[5], r[6], r[7]);
+}
+
+// 3x3 / stride 2 max pooling, four channels per thread (C % 4 == 0, 16-byte aligned tensors)
+__global__ void __launch_bounds__(256) maxpool3s2_v4_kernel(const float* __restrict__ in, int N, int H, int W, int C, int Ho, int Wo, float* __restrict__ out)
+{
+    const int C4 = C >> 2;
+    const int64_t total = (int64_t)N * Ho * Wo * C4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        const int64_t px = i / C4;
+        const int ox = (int)(px % Wo);
+        const int oy = (int)((px / Wo) % Ho);
+        const int64_t n = px / ((int64_t)Wo * Ho);
+        const float4* p = reinterpret_cast<const float4*>(in + ((n * H + oy * 2) * W + ox * 2) * C) + c4;
+        float4 m = make_float4(-3.402823466e38f, -3.402823466e38f, -3.402823466e38f, -3.402823466e38f);
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const float4 v = __ldg(p + ((int64_t)dy * W + dx) * C4);
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+        reinterpret_cast<float4*>(out)[i] = m;
+    }
+}
+
 // K7: tf.nn.local_response_normalization(depth_radius=2, bias=1, alpha=2e-5, beta=0.75) over the channel axis
 __global__ void __launch_bounds__(256) lrn_kernel(const float* __restrict__ in, int64_t pixels, int C, float* __restrict__ out)
 {
@@ -317,6 +390,12 @@ __global__ void __launch_bounds__(256) conv_weight_pack_kernel(const float* __re
         out[i] = hi;
         out[total + i] = v - hi;  // remainder, used by the error-compensated (3xTF32) convolution
     }
+}
+
+static bool env_flag(const char* name)
+{
+    const char* v = getenv(name);
+    return v && *v && *v != '0';
 }
 
 static unsigned grid_1d(int64_t total, int threads)
@@ -526,7 +605,10 @@ static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgA
     std::swap(cur, other);
     if (lrn) {  // pool2 + LRN2 in one kernel
         const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
-        maxpool3s2_lrn_kernel<<<(unsigned)std::min<int64_t>((int64_t)N * 13 * 13, (int64_t)sms * 16), 256, 0, st>>>(cur, N, 27, 27, 256, 13, 13, other);
+        if (env_flag("HG_POOL_LRN_BLOCK"))  // the block-per-pixel kernel (kept for comparison)
+            maxpool3s2_lrn_kernel<<<(unsigned)std::min<int64_t>((int64_t)N * 13 * 13, (int64_t)sms * 16), 256, 0, st>>>(cur, N, 27, 27, 256, 13, 13, other);
+        else
+            maxpool3s2_lrn_c256_kernel<<<(unsigned)ceil_div((int64_t)N * 13 * 13, 8), 256, 0, st>>>(cur, N, 27, 27, 13, 13, other);
         count_launch();
         std::swap(cur, other);
     } else {
@@ -545,7 +627,7 @@ static int alexnet_encode_impl(const uint8_t* d_images, int n, int wh, const HgA
     tm.mark(kEncConv, st);
     std::swap(cur, other);
     // pool5 -> [N,6,6,256] == [N, 9216] in (h, w, c) order, the row order of the fc6 weights
-    maxpool3s2_kernel<<<grid_1d((int64_t)N * 6 * 6 * 256, 256), 256, 0, st>>>(cur, N, 13, 13, 256, 6, 6, other);
+    maxpool3s2_v4_kernel<<<grid_1d((int64_t)N * 6 * 6 * 64, 256), 256, 0, st>>>(cur, N, 13, 13, 256, 6, 6, other);
     count_launch();
     HG_CUDA_TRY(cudaGetLastError());
     tm.mark(kEncPool, st);

@@ -123,6 +123,10 @@ static Plan make_plan(int64_t nq, int64_t ndb, int b, int L, int64_t R, int ctas
             if (cost < best * 0.995) { best = cost; SL = pair / 2; }  // prefer fewer splits unless clearly better
         }
     }
+    {
+        const int want = env_int("HG_SPLITS", 0);  // tuning override: number of database splits
+        if (want > 0) SL = round_up(ceil_div(ndb, want), p.umma_kp ? 2 * p.TILE : p.TILE) ;
+    }
     SL = std::min<int64_t>(SL, kMaxSplitRows);
     SL = std::max<int64_t>(SL, p.TILE);
     p.SL = SL;
