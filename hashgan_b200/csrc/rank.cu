@@ -625,15 +625,16 @@ template <bool WINDOW>
 __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    // WINDOW: 16-bit counters (ranks below 65536: a query with more closer-than-threshold candidates goes to the wide list) --
-    // half the shared memory per thread, so more CTAs are resident in this latency-bound kernel
-    using CT = typename std::conditional<WINDOW, uint16_t, uint32_t>::type;
+    // WINDOW: the two 16-bit counters of a distance share ONE shared-memory word, relevant count << 16 | count (ranks below 65536:
+    // a query with more closer-than-threshold candidates goes to the wide list) -- half the shared memory per thread, so more CTAs
+    // are resident in this latency-bound kernel, and one load / add / store per candidate and one shuffle per scan step instead of two
+    using CT = uint32_t;
     const int NTB = blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const int nb = p.b + 1;
     const int ncol = WINDOW ? 32 : nb;               // counters per thread and kind
     CT* cN = reinterpret_cast<CT*>(smem) + tid;      // cN[c * NTB]: count per distance  -> rank base
-    CT* cM = cN + (size_t)ncol * NTB;                // cM[c * NTB]: relevant per distance -> relevant base
+    CT* cM = cN + (size_t)ncol * NTB;                // cM[c * NTB]: relevant per distance -> relevant base (!WINDOW only)
     const int G = p.G;
     const bool exact = p.bins_by_slot != 0;
     const int64_t n_act = p.qlist ? (int64_t)*p.n_active : p.nq;
@@ -647,7 +648,10 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
     const int T = live ? p.thr[q] : -1;
     const int s0 = (int)((int64_t)g * p.P / G), s1 = (int)((int64_t)(g + 1) * p.P / G);
 
-    for (int c = 0; c < ncol; ++c) { cN[c * NTB] = 0; cM[c * NTB] = 0; }
+    for (int c = 0; c < ncol; ++c) {
+        cN[c * NTB] = 0;
+        if (!WINDOW) cM[c * NTB] = 0;
+    }
 
     // ---- totals / overflow over the query's bins (group reduction) -------------------------
     unsigned long long total = 0, total1 = 0;  // all candidates / candidates closer than the threshold distance
@@ -713,9 +717,13 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
         walk([&](uint32_t ent, int64_t) {
             const uint32_t d = (ent >> kIdxBits) & kDistMask;
             const uint32_t c = col(d);
-            cN[c] = (CT)(cN[c] + 1u);
-            cM[c] = (CT)(cM[c] + (ent >> 31));
-            if (WINDOW) { dmin = min(dmin, d); dmax = max(dmax, d); }
+            if (WINDOW) {
+                cN[c] += 1u + ((ent >> 15) & 0x10000u);
+                dmin = min(dmin, d); dmax = max(dmax, d);
+            } else {
+                cN[c] += 1u;
+                cM[c] += ent >> 31;
+            }
         });
     }
     if (WINDOW) {
@@ -734,10 +742,24 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
     }
 
     // ---- phase A2: rank bases, distances in ascending order (all 32 lanes take part in the shuffles) ----
-    {
+    if (WINDOW) {  // both halves of the packed word at once: live queries keep every partial sum below 65536
+        uint32_t cn = 0;
+        for (int i = 0; i < ncol; ++i) {
+            const uint32_t c = col(dmin + (uint32_t)i);
+            const uint32_t v = cN[c];
+            uint32_t iv = v;
+            for (int o = 1; o < G; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, iv, o, G);
+                if (g >= o) iv += t;
+            }
+            const uint32_t tot = __shfl_sync(FULL, iv, G - 1, G);
+            cN[c] = cn + (iv - v);
+            cn += tot;
+        }
+    } else {
         uint32_t cn = 0, cm = 0;
         for (int i = 0; i < ncol; ++i) {
-            const uint32_t c = col(WINDOW ? dmin + (uint32_t)i : (uint32_t)i);
+            const uint32_t c = col((uint32_t)i);
             const uint32_t vN = cN[c], vM = cM[c];
             uint32_t iN = vN, iM = vM;
             for (int o = 1; o < G; o <<= 1) {
@@ -747,8 +769,8 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
             }
             const uint32_t totN = __shfl_sync(FULL, iN, G - 1, G);
             const uint32_t totM = __shfl_sync(FULL, iM, G - 1, G);
-            cN[c] = (CT)(cn + (iN - vN));
-            cM[c] = (CT)(cm + (iM - vM));
+            cN[c] = cn + (iN - vN);
+            cM[c] = cm + (iM - vM);
             cn += totN; cm += totM;
         }
     }
@@ -762,10 +784,15 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
             const uint32_t d = (ent >> kIdxBits) & kDistMask;
             const uint32_t m = ent >> 31;
             const uint32_t c = col(d);
-            const uint32_t rank = cN[c] + 1u;
-            const uint32_t cum = cM[c] + m;
-            cN[c] = (CT)rank;
-            cM[c] = (CT)cum;
+            uint32_t rank, cum;
+            if (WINDOW) {
+                const uint32_t v = cN[c] + 1u + (m << 16);
+                cN[c] = v;
+                rank = v & 0xFFFFu; cum = v >> 16;
+            } else {
+                rank = cN[c] + 1u; cum = cM[c] + m;
+                cN[c] = rank; cM[c] = cum;
+            }
             if (rank <= R32) {
                 if (p.ids) p.ids[q * p.R + (rank - 1u)] = (uint32_t)(row0 + (ent & kIdxMask));
                 if (p.dist) p.dist[q * p.R + (rank - 1u)] = (uint16_t)d;
