@@ -743,8 +743,10 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
 
     // ---- phase A2: rank bases, distances in ascending order (all 32 lanes take part in the shuffles) ----
     if (WINDOW) {  // both halves of the packed word at once: live queries keep every partial sum below 65536
+        // only the distances that occur: dmin .. dmax of the queries of this warp (typically a dozen of the 32 window slots)
+        const int span = (int)__reduce_max_sync(FULL, live ? dmax - dmin + 1u : 0u);
         uint32_t cn = 0;
-        for (int i = 0; i < ncol; ++i) {
+        for (int i = 0; i < span; ++i) {
             const uint32_t c = col(dmin + (uint32_t)i);
             const uint32_t v = cN[c];
             uint32_t iv = v;
