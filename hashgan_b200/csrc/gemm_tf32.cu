@@ -431,7 +431,10 @@ static int launch_conv_gemm(const CUtensorMap& tb, const CUtensorMap& tblo, cons
 {
     static const int mt_env = []() { const char* v = getenv("HG_CONV_MT"); return (v && *v) ? atoi(v) : 0; }();
     if constexpr (X3 && BN <= 128) {
-        if (mt_env != 1 && a.M >= 2 * kGemmBM) return launch_conv_gemm_mt<BN, X3, 2>(tb, tblo, a, st);
+        // (a grid that cannot even fill a quarter of the SMs -- fc8: 64 outputs, M = 1280 -> 5 CTAs of 256 rows -- keeps 128-row CTAs)
+        const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
+        const bool tiny = ceil_div(a.Cog, BN) * ceil_div(a.M, 2 * kGemmBM) * 4 < sms;
+        if (mt_env != 1 && a.M >= 2 * kGemmBM && (mt_env == 2 || !tiny)) return launch_conv_gemm_mt<BN, X3, 2>(tb, tblo, a, st);
     }
     return launch_conv_gemm_mt<BN, X3, 1>(tb, tblo, a, st);
 }
