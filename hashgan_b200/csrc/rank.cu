@@ -605,6 +605,7 @@ struct ApParams {
     int* wide_list;  // queries whose distance span does not fit the window (WINDOW only)
     int* n_wide;
     int no_fallback;
+    int halves;  // the lanes of a query share half bins instead of whole bins (set by the launcher)
 };
 
 // Error-free accumulation (Knuth TwoSum): hi + lo carries the AP sum to ~2^-100, so the rounded result does not depend
@@ -690,15 +691,23 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
     auto col = [&](uint32_t d) -> uint32_t { return (WINDOW ? (d & 31u) : d) * (uint32_t)NTB; };
 
     // walks my bins in row order; 32 bytes of entries in flight per thread while the previous 32 are consumed
+    // The lanes share HALF bins (first / second half of a bin's entries, split at a multiple of 8 entries so that the 16-byte loads
+    // stay aligned): with P bins over G lanes a lane owned 1 or 2 bins (C4: 44 bins over 32 lanes, 69 % balance), now 2 or 3 halves.
+    // (only where that improves the balance: p.halves, chosen by the launcher)
+    const int hsh = p.halves ? 1 : 0;
+    const int h0 = (int)((int64_t)g * (p.P << hsh) / G), h1 = (int)((int64_t)(g + 1) * (p.P << hsh) / G);
     auto walk = [&](auto&& fn) {
-        for (int s = s0; s < s1; ++s) {
-            const uint32_t c = p.bin_cnt[binbase + s];
+        for (int hb = h0; hb < h1; ++hb) {
+            const int s = hb >> hsh;
+            const uint32_t cnt = p.bin_cnt[binbase + s];
+            const uint32_t mid = hsh ? ((cnt >> 1) & ~7u) : 0u;
+            const uint32_t c = (hsh && !(hb & 1)) ? mid : cnt;  // entries [e, c) of the bin
+            uint32_t e = (hsh && (hb & 1)) ? mid : 0u;
             const uint32_t* lp = bin_ptr(s);
             const int64_t row0 = (int64_t)s * p.SL;
-            uint32_t e = 0;
-            if ((reinterpret_cast<uintptr_t>(lp) & 15) == 0 && c >= 8) {
+            if ((reinterpret_cast<uintptr_t>(lp) & 15) == 0 && c >= e + 8) {
                 const uint4* vp = reinterpret_cast<const uint4*>(lp);
-                uint4 a0 = __ldg(vp), a1 = __ldg(vp + 1);
+                uint4 a0 = __ldg(vp + (e >> 2)), a1 = __ldg(vp + (e >> 2) + 1);
                 for (; e + 8 <= c; e += 8) {
                     uint4 n0 = a0, n1 = a1;
                     if (e + 16 <= c) { n0 = __ldg(vp + (e >> 2) + 2); n1 = __ldg(vp + (e >> 2) + 3); }
@@ -1216,6 +1225,13 @@ static int launch_ap(ApParams ap, int64_t n_slots_max, cudaStream_t st)
     G = env_int("HG_AP_G", G);
     if (G < 1 || G > 32 || (G & (G - 1)) || G > ap.P) G = 1;
     ap.G = G;
+    {
+        // whole bins: a lane owns floor or ceil(P / G) of them; halves pay off when that leaves the lanes unevenly loaded (C4: 44 bins
+        // over 32 lanes = 69 % -> 88 halves = 92 %; C5: 88 bins = 92 % either way, where the halves only add loop overhead)
+        const double whole = (double)ap.P / ((double)G * (double)ceil_div(ap.P, G));
+        const double half = (double)(2 * ap.P) / ((double)G * (double)ceil_div(2 * ap.P, G));
+        ap.halves = half > whole + 0.1 ? 1 : 0;
+    }
     const int64_t blocks = ceil_div(n_slots_max * G, threads);
     ap_kernel<WINDOW><<<(unsigned)blocks, threads, smem, st>>>(ap);
     count_launch();
