@@ -24,6 +24,7 @@
 // The PRMT / multiply-add gather leaves accumulator column 4i+k of a 32-column group at mask bit 8k+i; expand_db_kernel stores
 // the int8 database rows of every 32-row group in the inverse order, so that mask bit j IS row j of the group.
 // The bins, thresholds, AP kernel and exactness guard are shared with the POPC path (rank.cu).
+// select_q_kernel (below) is the same contraction with a QUEUED epilogue: the hot kernel of C4 (sparse top-R, 33..64-bit codes).
 #include "umma.cuh"
 
 #include <algorithm>
@@ -470,12 +471,16 @@ select_umma_kernel(const __grid_constant__ CUtensorMap tmap_q8, const __grid_con
 // ---- queued mode: the list-appending epilogue without its 23 % lane occupancy -----------------------------------------------
 // select_umma_kernel walks the hits of a tile before it touches the next one, so every warp-tile costs max-over-lanes hit
 // steps (2.5 at C4 for 0.57 hits per lane).  Here a lane only PARKS its non-zero mask words in a private shared-memory FIFO
-// (word + tile tag) and the warp drains the FIFOs one hit per lane and step (a) while it waits for the next accumulator and
-// (b) whenever a FIFO is about to fill, and only when enough lanes have work: the lanes no longer wait for each other at tile
-// boundaries, the steps run mostly full, and the waiting time of the accumulator hand-off is filled with useful work.  Hits may
-// be consumed many tiles late, so their packed rows come from global memory (L2-resident) instead of the staged tile; the ring
-// therefore holds only the int8 operands and is released by the MMA warp itself (tcgen05.commit).  Bins, entry format, order
-// (one writer per bin, ascending rows) and the AP kernel are those of select_umma_kernel.
+// (word + tile tag) and per tile the warp consumes ONE parked hit per lane, in two halves around the accumulator hand-off:
+//   take()     before the wait: pop / pick the lowest row of the word being consumed, REQUEST its packed row from global memory
+//              (L2-resident; hits may be consumed many tiles late, so the staged tile is gone -- the ring therefore holds only
+//              the int8 operands and is released by the MMA warp itself, tcgen05.commit);
+//   consume()  after the masks of the tile are built and the accumulator is handed back: distance, relevance, append.
+// The row's L2 latency hides behind the wait and the mask building (loading it inside the hit step put ~700 cycles on the
+// hand-off path: no gain over the tile-walking kernel), the lanes no longer wait for each other at tile boundaries, and a
+// lane's backlog is smoothed over the following tiles.  A FIFO about to fill, or a long wait with many lanes holding work,
+// triggers extra (blocking) steps.  Measured at C4: 1.306 -> 1.125 ms, 1085 M -> 792 M warp instructions.  Bins, entry format,
+// order (one writer per bin, ascending rows) and the AP kernel are those of select_umma_kernel.
 template <int KP> struct QCfg {
     static constexpr int S = (KP == 32 ? 8 : (KP == 64 ? 4 : 3));  // ring depth
     static constexpr int D = (KP == 128 ? 4 : 8);                  // FIFO entries per lane (power of two)
