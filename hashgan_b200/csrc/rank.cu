@@ -887,6 +887,8 @@ struct DenseApParams {
     uint32_t* ids;
     uint16_t* dist;
     int32_t* rel;
+    const int* n_active;  // indirect mode (exact path of a few failed queries): number of listed queries
+    const int* qlist;     // indirect mode: query ids; the grid is sized for the largest list, CTAs beyond it exit at once
 };
 
 // one CTA = one query; thread t owns the t-th of blockDim.x contiguous row ranges.
@@ -904,7 +906,8 @@ __global__ void __launch_bounds__(256) dense_ap_kernel(DenseApParams p)
     uint32_t* cM = smem + (size_t)nb * NTB + tid;   // cM[d * NTB]: relevant rows at distance d -> relevant base
     uint2* wtot = reinterpret_cast<uint2*>(smem + (size_t)2 * nb * NTB);  // [nb][NW]: per-warp totals of a distance
     const uint32_t FULL = 0xffffffffu;
-    const int64_t q = blockIdx.x;
+    if (p.qlist != nullptr && (int)blockIdx.x >= *p.n_active) return;  // whole CTA
+    const int64_t q = p.qlist ? (int64_t)p.qlist[blockIdx.x] : (int64_t)blockIdx.x;
     const int Wr = LW1 ? RowLW1<W>::Wr : p.Wr, LW = LW1 ? 1 : p.LW;
     constexpr int RB = LW1 ? (RowLW1<W>::Wr <= 4 ? 4 : 1) : 1;  // rows per batch: 4 (32 bytes of 2-word rows, 64 bytes of 4-word rows: measured best at C1 / C1_64) or 1
     uint32_t qw[W], ql[4] = {0, 0, 0, 0};
@@ -1038,7 +1041,9 @@ static int launch_dense_ap(DenseApParams dp, cudaStream_t st)
     // threads per query: as many as the shared-memory counters allow (<= 256), but at least a few dozen rows per thread
     int threads = 256;
     auto smem_for = [&](int t) { return (size_t)t * 2 * nb * sizeof(uint32_t) + std::max<size_t>((size_t)nb * (t / 32) * sizeof(uint2), (size_t)(t / 32) * 3 * sizeof(double)) + 16; };
-    while (threads > 32 && (smem_for(threads) > 100 * 1024 || dp.ndb / threads < 32)) threads >>= 1;
+    // (a short list of failed queries leaves most SMs empty anyway: take all the threads one CTA can have)
+    const size_t smem_cap = dp.qlist ? 200 * 1024 : 100 * 1024;
+    while (threads > 32 && (smem_for(threads) > smem_cap || dp.ndb / threads < 32)) threads >>= 1;
     const size_t smem = smem_for(threads);
     dp.G = threads;
     if (dp.LW == 1) {
@@ -1064,9 +1069,19 @@ static int launch_dense_ap(DenseApParams dp, cudaStream_t st)
 // ================================================================================================
 // 5. Exact path helpers.
 // ================================================================================================
-__global__ void zero_hist2_kernel(uint32_t* __restrict__ hist2, const int* __restrict__ n_fail, int64_t per_query)
+// The failed queries of a call go ONE of two ways, decided on the device (the call stays asynchronous): up to `dense_max` of
+// them are ranked by dense_ap_kernel, one CTA per query walking the whole database twice -- the per-split machinery below is
+// thread-per-query and leaves the GPU idle for a handful of queries (26 failed queries of a class-sorted 1M-row database:
+// 5.1 ms, against 0.3 ms for the walk); larger lists (HG_FLAG_FORCE_EXACT on a big batch, degenerate codes) keep the
+// per-split path, whose database tiles are shared by 128 queries.  ctrl[4] / ctrl[5] = the count each path sees.
+// The routing costs no launch of its own: zero_hist2_kernel (first kernel of the per-split path) derives its count from ctrl[0] and
+// publishes both counts for the kernels behind it.
+__global__ void zero_hist2_kernel(uint32_t* __restrict__ hist2, int* __restrict__ ctrl, int dense_max, int64_t per_query)
 {
-    const int64_t n = (int64_t)*n_fail * per_query;
+    const int n_all = ctrl[0];
+    const int small = n_all <= dense_max ? n_all : 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrl[4] = small; ctrl[5] = n_all - small; }
+    const int64_t n = (int64_t)(n_all - small) * per_query;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) hist2[i] = 0;
 }
 
@@ -1414,9 +1429,19 @@ static int run_map(const Plan& pl, const uint32_t* q_rows, const uint32_t* db_ro
     // 5. exact path for the fail list (grids sized for nq, CTAs beyond the fail count exit immediately)
     {
         const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
-        zero_hist2_kernel<<<sms * 4, 256, 0, st>>>(hist2, n_fail, (int64_t)pl.P * nb);
+        // up to 512 failed queries: one dense walk each (zero_hist2_kernel publishes the routing); HG_EXACT_DENSE_MAX=0 keeps every list on the per-split path
+        const int dense_max = (pl.ndb / 32 <= kMaxSplitRows) ? (int)std::min<int64_t>(pl.nq, env_int("HG_EXACT_DENSE_MAX", 512)) : 0;
+        zero_hist2_kernel<<<sms * 4, 256, 0, st>>>(hist2, ctrl, dense_max, (int64_t)pl.P * nb);
         count_launch();
         HG_CUDA_TRY(cudaGetLastError());
+        if (dense_max > 0) {
+            DenseApParams dp{};
+            dp.q_rows = q_rows; dp.db_rows = db_rows; dp.nq = dense_max; dp.ndb = pl.ndb; dp.R = pl.R; dp.b = pl.b; dp.LW = pl.LW; dp.Wr = pl.Wr;
+            dp.ap = d_ap; dp.ids = d_ids; dp.dist = d_dist; dp.rel = d_rel;
+            dp.n_active = ctrl + 4; dp.qlist = fail_list;
+            if ((rc = launch_dense_ap<W>(dp, st)) != HG_OK) return rc;
+        }
+        n_fail = ctrl + 5;  // what is left for the per-split path
         HistParams hp{};
         hp.q_rows = q_rows; hp.db_rows = db_rows; hp.nq = pl.nq; hp.ndb = pl.ndb; hp.b = pl.b; hp.Wr = pl.Wr;
         hp.n_active = n_fail; hp.qlist = fail_list;

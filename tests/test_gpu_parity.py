@@ -354,12 +354,22 @@ def test_dense_top_r_walks_the_rows_directly(hb, c_oracle, name, nq, ndb, R):
     assert np.array_equal(ap, ap_sel, equal_nan=True)
 
 
-@pytest.mark.parametrize("flags", [0, 1])
-def test_force_exact_equals_fast(hb, c_oracle, flags):
+@pytest.mark.parametrize("flags,dense_max", [(0, None), (1, None), (1, "0"), (1, "100"), (1, "4096")])
+def test_force_exact_equals_fast(hb, c_oracle, flags, dense_max):
+    """flags = 1 sends every query through the exact path.  A short fail list is ranked by one dense walk per query
+    (dense_ap_kernel over the list), a long one by the per-split histograms / exact select / AP: HG_EXACT_DENSE_MAX = 0 and
+    = 100 (< 700 queries) keep the per-split path under test, 4096 takes the walk (the default, 512, leaves this batch on the
+    per-split path too)."""
+    import os
     from hashgan_b200.synthetic import make_workload
 
     wl, db, q = make_workload("C2", nq=700, ndb=60000)
-    _check_against_c_oracle(hb, c_oracle, db, q, 2000, flags=flags)
+    if dense_max is not None:
+        os.environ["HG_EXACT_DENSE_MAX"] = dense_max
+    try:
+        _check_against_c_oracle(hb, c_oracle, db, q, 2000, flags=flags)
+    finally:
+        os.environ.pop("HG_EXACT_DENSE_MAX", None)
 
 
 def test_small_and_ragged_sizes(hb, c_oracle):
