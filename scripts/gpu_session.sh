@@ -29,7 +29,7 @@ if [[ $what == all || $what == ncu ]]; then
       python bench.py --steps 2 --warmup 3 --no-e2e --no-parity --cpu-sample 0 > $out/ncu_launches.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"select_umma|select_q" -s 3 -c 1 -f -o $out/prof_select \
       python bench.py --steps 1 --warmup 3 --no-e2e --no-parity --cpu-sample 0 > $out/ncu_full.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:ap_kernel -s 9 -c 1 -f -o $out/prof_ap \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:^ap_kernel -s 9 -c 1 -f -o $out/prof_ap \
       python bench.py --steps 1 --warmup 3 --no-e2e --no-parity --cpu-sample 0 > $out/ncu_full_ap.log 2>&1
   ls -la $out
 fi

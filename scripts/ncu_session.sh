@@ -7,7 +7,7 @@ mkdir -p $out
 B="python bench.py --steps 2 --warmup 3 --no-e2e --no-parity --cpu-sample 0"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/r02_launches_C4.csv $B > $out/ncu_l1.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"select_umma|select_q" -s 3 -c 1 -f -o $out/r02_prof_select $B > $out/ncu_f1.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:ap_kernel -s 6 -c 1 -f -o $out/r02_prof_ap $B > $out/ncu_f2.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:^ap_kernel -s 6 -c 1 -f -o $out/r02_prof_ap $B > $out/ncu_f2.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:hist_kernel -s 6 -c 1 -f -o $out/r02_prof_hist $B > $out/ncu_f3.log 2>&1
 E="python bench.py --workload C3 --steps 1 --warmup 3 --ref-images 1"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $out/r02_launches_C3.csv $E > $out/ncu_l2.log 2>&1
