@@ -359,6 +359,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
                         const float x = __uint_as_float(r[j + t]) + (n < a.Cog ? __ldg(a.bias + n) : 0.0f);
                         o[t] = a.relu ? fmaxf(x, 0.0f) : x;
                     }
+                    if ((BN % 32) != 0 && c0 + j >= BN) break;  // BN = 144: the last 32-column chunk is half a tile wide (BN % 4 == 0)
                     if (vec) {
                         *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
                     } else {
@@ -430,7 +431,7 @@ template <int BN, bool X3>
 static int launch_conv_gemm(const CUtensorMap& tb, const CUtensorMap& tblo, const ConvGemmArgs& a, cudaStream_t st)
 {
     static const int mt_env = []() { const char* v = getenv("HG_CONV_MT"); return (v && *v) ? atoi(v) : 0; }();
-    if constexpr (X3 && BN <= 128) {
+    if constexpr (X3 && BN <= 144) {
         // (a grid that cannot even fill a quarter of the SMs -- fc8: 64 outputs, M = 1280 -> 5 CTAs of 256 rows -- keeps 128-row CTAs)
         const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
         const bool tiny = ceil_div(a.Cog, BN) * ceil_div(a.M, 2 * kGemmBM) * 4 < sms;
@@ -450,7 +451,16 @@ int conv_gemm_tf32(const float* in, const float* wt, const float* wt_lo, const f
     ConvGemmArgs a{};
     a.in = in; a.bias = bias; a.out = out; a.M = M; a.H = H; a.W = W; a.C = C; a.c0 = c0; a.Cg = Cg; a.KH = KH; a.KW = KW; a.stride = stride;
     a.pad = pad; a.Ho = Ho; a.Wo = Wo; a.Kpad = Kpad; a.Cog = Cog; a.ldc = ldc; a.relu = relu;
-    const int BN = (Cog % 128 == 0) ? 128 : ((Cog % 192 == 0) ? 192 : ((Cog % 96 == 0) ? 96 : (Cog <= 64 ? 64 : 128)));
+    int BN = (Cog % 128 == 0) ? 128 : ((Cog % 192 == 0) ? 192 : ((Cog % 96 == 0) ? 96 : (Cog <= 64 ? 64 : 128)));
+    if (wt_lo && BN == 128 && M >= 2 * kGemmBM) {
+        // One 256-row CTA per SM: the launch takes ceil(CTAs / SMs) rounds, each ~BN long.  fc6 / fc7 (4096 outputs, M = 1280): 32 x 5 =
+        // 160 CTAs of 128 columns are two rounds, the second one 8 % full; 29 x 5 = 145 CTAs of 144 columns (the last tile 64 wide)
+        // are ONE round -- fc6 + fc7 1.20 -> 0.60 ms.  Convolutions (thousands of CTAs) keep 128.
+        const int sms = device_facts().sm_count > 0 ? device_facts().sm_count : 148;
+        const int64_t my = ceil_div(M, 2 * kGemmBM);
+        const int64_t cost128 = ceil_div(ceil_div(Cog, 128) * my, sms) * 128, cost144 = ceil_div(ceil_div(Cog, 144) * my, sms) * 144;
+        if (cost144 < cost128) BN = 144;
+    }
     CUtensorMap tb, tblo;
     int rc;
     if ((rc = make_map(&tb, wt, Cog, Kpad, Kpad, BN)) != HG_OK) return rc;
@@ -459,6 +469,7 @@ int conv_gemm_tf32(const float* in, const float* wt, const float* wt_lo, const f
         switch (BN) {
             case 64: return launch_conv_gemm<64, true>(tb, tblo, a, st);
             case 96: return launch_conv_gemm<96, true>(tb, tblo, a, st);
+            case 144: return launch_conv_gemm<144, true>(tb, tblo, a, st);
             case 192: return launch_conv_gemm<192, true>(tb, tblo, a, st);
             default: return launch_conv_gemm<128, true>(tb, tblo, a, st);
         }
