@@ -826,8 +826,8 @@ __global__ void __launch_bounds__(128) ap_kernel(ApParams p)
         uint32_t n_done = 0, m_done = 0;
         const uint32_t gmask = G >= 32 ? FULL : ((1u << G) - 1u);
         const int gshift = lane - g;  // first lane of my group
-        // the class counts of G bins at a time (one coalesced load per lane, handed round by shuffle): a load per bin inside this serial
-        // loop cost one L2 round trip per bin -- 72 us of the 122 us the kernel took for 1250 queries over 237 splits (N = 8, strong)
+        // the class counts of G bins at a time (one coalesced load per lane, handed round by shuffle) instead of one dependent load per
+        // bin inside this serial loop (1250 queries over 237 splits, the N = 8 strong-scaling share: 0.122 -> 0.116 ms)
         for (int sb = 0; sb < p.P; sb += G) {
         if (!__any_sync(FULL, need0 && n_done < quota)) break;  // every query of the warp has its top-R
         const uint32_t cblk = (need0 && sb + g < p.P) ? p.bin_cnt0[binbase + sb + g] : 0u;
