@@ -134,5 +134,13 @@ def test_row_layout_rules():
     assert lib.hg_select_backend_for(1000, 54000, 32, 10, 20000) == 0          # dense-ish top-R on short codes: POPC select
     assert lib.hg_select_backend_for(1000, 1000000, 32, 10, 5000) == 32
     assert lib.hg_select_backend_for(10000, 1000000, 64, 10, 5000) == 64
+    # which tensor-core select: the queued epilogue while the top-R is sparse on 33..64-bit codes in 4-word rows (C4), the
+    # tile-walking one for a dense top-R (C2), 128-bit codes (C5); no select at all on the dense walk (C1)
+    assert lib.hg_select_queued_for(10000, 1000000, 64, 10, 5000) == 1
+    assert lib.hg_select_queued_for(1250, 1000000, 64, 10, 5000) == 1              # one rank's share at N = 8 (strong scaling)
+    assert lib.hg_select_queued_for(10000, 100000, 48, 10, 5000) == 0
+    assert lib.hg_select_queued_for(5000, 2000000, 128, 81, 5000) == 0
+    assert lib.hg_select_queued_for(1000, 54000, 32, 10, 54000) == 0
+    assert lib.hg_select_queued_for(10, 100, 64, 10, 101) == -1                    # R > ndb: no plan
     assert lib.hg_select_backend_for(100, 100000, 200, 10, 5000) == 256
     assert lib.hg_select_backend_for(100, 1000, 64, 10, 5000) == -1             # R > ndb: no plan
